@@ -1,0 +1,24 @@
+# Builds everything in-tree (the .so files travel to the GPU box with the snapshot; they are git-ignored).
+#   make lib      fdreadoutlibs_b200/libswtpg_b200.so   CUDA kernels + C ABI (include/swtpg.h), sm_100a only
+#   make oracle   oracle/liboracle.so and (where /root/reference exists) oracle/_ref/libswtpg_ref.so
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH = -gencode arch=compute_100a,code=sm_100a
+NVFLAGS = $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v --expt-relaxed-constexpr
+CSRC = fdreadoutlibs_b200/csrc
+LIB = fdreadoutlibs_b200/libswtpg_b200.so
+
+all: lib oracle
+
+lib: $(LIB)
+
+$(LIB): $(CSRC)/swtpg_capi.cu $(CSRC)/framegen_capi.cu $(CSRC)/swtpg_kernels.cuh $(CSRC)/swtpg_device.cuh $(CSRC)/framegen.h include/swtpg.h include/swtpg_framegen.h
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/swtpg_capi.cu $(CSRC)/framegen_capi.cu 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
+	@grep -E "error|warning: v" build_ptxas.log || true
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -f $(LIB) build_ptxas.log
+	$(MAKE) -C oracle clean
+.PHONY: all lib oracle clean

@@ -1,0 +1,207 @@
+// Device-side building blocks of the fused SWTPG kernels (sm_100a).
+//
+// Data model: a "group" is 64 consecutive channels = one tick row of 112 bytes = one warp.
+// Lane l of the warp owns the channel PAIR (2l, 2l+1) of the group: 28 contiguous bits of the row. All per-channel
+// quantities live packed two-to-a-register as s16x2 / u16x2 (low half = even channel), so the reference's 16-bit
+// AVX2 lane arithmetic maps onto Blackwell's packed-16x2 integer instructions (VIADD.16x2, VIMNMX.S16x2,
+// VIADDMNMX.S16x2, HSET2) — see profiles/r01_ubench_pipes.txt for their measured issue rates.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/swtpg.h"
+
+namespace swtpg {
+
+// ---- packed 16x2 primitives ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t
+add2(uint32_t a, uint32_t b)
+{ // per-half wrapping add: VIADD.16x2 (_mm256_add_epi16)
+  uint32_t r;
+  asm("add.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t
+max2(uint32_t a, uint32_t b)
+{
+  uint32_t r;
+  asm("max.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t
+min2(uint32_t a, uint32_t b)
+{
+  uint32_t r;
+  asm("min.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t
+addmax2(uint32_t a, uint32_t b, uint32_t c)
+{ // max(a + b, c) per signed half: one VIADDMNMX.S16x2
+  uint32_t r;
+  asm("{.reg .b32 t; add.s16x2 t, %1, %2; max.s16x2 %0, t, %3;}" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t
+addmin2(uint32_t a, uint32_t b, uint32_t c)
+{ // min(a + b, c) per signed half
+  uint32_t r;
+  asm("{.reg .b32 t; add.s16x2 t, %1, %2; min.s16x2 %0, t, %3;}" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t
+neg2(uint32_t a)
+{ // per-half two's complement negate
+  return add2(~a, 0x00010001u);
+}
+// Per-half "a > b" as 0xFFFF / 0x0000, computed by the half2 comparator (HSET2) on the BIT PATTERNS. Valid as a
+// signed-integer compare when b is in [0, 0x7BFF] and a is either in [0, 0x7BFF] (finite non-negative halves order
+// like their bit patterns; subnormals are not flushed) or negative (sign bit set: a negative half or a NaN, both of
+// which compare "not greater"). All call sites below document why their operands stay in that range.
+__device__ __forceinline__ uint32_t
+gt2_mask_nonneg(uint32_t a, uint32_t b)
+{
+  uint32_t r;
+  asm("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t
+pack2(int lo, int hi)
+{
+  return (uint32_t(lo) & 0xFFFFu) | (uint32_t(hi) << 16);
+}
+__device__ __forceinline__ int
+lo16s(uint32_t v)
+{
+  return int(int16_t(v & 0xFFFFu));
+}
+__device__ __forceinline__ int
+hi16s(uint32_t v)
+{
+  return int(int16_t(v >> 16));
+}
+__device__ __forceinline__ int
+wrap16(int x)
+{
+  return int(int16_t(uint16_t(x)));
+}
+__device__ __forceinline__ int
+sat16(int x)
+{
+  return x > 32767 ? 32767 : (x < -32768 ? -32768 : x);
+}
+
+// ---- async bulk copy + mbarrier (TMA engine, SASS UBLKCP / SYNCS) -------------------------------------------------
+__device__ __forceinline__ uint32_t
+smem_u32(const void* p)
+{
+  return uint32_t(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void
+mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void
+fence_mbar_init()
+{
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void
+fence_proxy_async()
+{ // order this thread's earlier generic-proxy smem accesses before later async-proxy (bulk copy) writes
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void
+mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void
+bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{ // 16-byte aligned on both sides, bytes % 16 == 0
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void
+mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "WAIT_%=:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra DONE_%=;\n"
+               "bra WAIT_%=;\n"
+               "DONE_%=:\n"
+               "}" ::"r"(smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+
+// ---- 14-bit pair extraction ---------------------------------------------------------------------------------------
+// Lane l's pair occupies bits [28 l, 28 l + 28) of the 896-bit little-endian row (channel c at bits [14c, 14c+14):
+// fddetdataformats get_adc; reference unpack: wibeth/tpg/FrameExpand.hpp:84-186). Word index and shift are per-lane
+// constants; the second word is clamped so lane 31 (shift 4, bits 868..895 all in word 27) never reads past the row.
+struct PairPos
+{
+  uint32_t w0, w1, sh;
+};
+__device__ __forceinline__ PairPos
+pair_pos(uint32_t lane)
+{
+  PairPos p;
+  p.w0 = (28u * lane) >> 5;
+  p.sh = (28u * lane) & 31u;
+  p.w1 = p.w0 + 1u > 27u ? 27u : p.w0 + 1u;
+  return p;
+}
+__device__ __forceinline__ uint32_t
+extract_pair(const uint32_t* row, const PairPos& pp)
+{
+  const uint32_t x = __funnelshift_r(row[pp.w0], row[pp.w1], pp.sh); // 28 payload bits + 4 junk bits on top
+  return (x & 0x3FFFu) | ((x << 2) & 0x3FFF0000u);                   // -> u16x2 {adc(2l), adc(2l+1)}
+}
+
+// ---- TP emission -----------------------------------------------------------------------------------------------------
+struct TpSink
+{
+  swtpg_tp* buf;
+  unsigned int* count;
+  uint32_t cap;
+};
+// Appends one record. Device order is arbitrary (atomic cursor); the host sorts by (time_start, link, channel).
+__device__ __forceinline__ void
+emit_tp(const TpSink& k, uint64_t time_start, uint64_t time_peak, uint32_t tot, uint32_t integral, uint32_t peak, uint32_t chan,
+        uint32_t link)
+{
+  const unsigned idx = atomicAdd(k.count, 1u);
+  if (idx < k.cap) {
+    uint4* d = reinterpret_cast<uint4*>(k.buf + idx);
+    d[0] = make_uint4(uint32_t(time_start), uint32_t(time_start >> 32), uint32_t(time_peak), uint32_t(time_peak >> 32));
+    d[1] = make_uint4(tot, integral, (peak & 0xFFFFu) | (chan << 16), link);
+  }
+}
+// WIBEth TP fields: src/wibeth/WIBEthFrameProcessor.cpp:520-545 (accepted iff hit_charge != 0)
+__device__ __forceinline__ void
+emit_wibeth(const TpSink& k, uint64_t ts, int t_end, uint32_t charge, uint32_t tover, uint32_t peak_adc, uint32_t peak_time,
+            uint32_t chan, uint32_t link)
+{
+  if (charge == 0)
+    return;
+  const uint64_t t0 = ts + uint64_t(32ll * (int64_t(t_end) - int64_t(tover)));
+  emit_tp(k, t0, t0 + 32ull * peak_time, 32u * tover, charge, peak_adc, chan, link);
+}
+// WIB2 TP fields: src/wib2/WIB2FrameProcessor.cpp:429-455
+__device__ __forceinline__ void
+emit_wib2(const TpSink& k, uint64_t ts, int t_end, uint32_t charge, uint32_t tover, uint32_t chan, uint32_t link)
+{
+  if (charge == 0)
+    return;
+  const uint64_t t0 = ts + uint64_t(32ll * (int64_t(t_end) - int64_t(tover)));
+  const uint64_t t1 = ts + uint64_t(32ll * int64_t(t_end));
+  emit_tp(k, t0, (t0 + t1) / 2, uint32_t(int64_t(tover) * 32), charge, (charge / 20u) & 0xFFFFu, chan, link);
+}
+
+} // namespace swtpg

@@ -1,0 +1,476 @@
+// Fused SWTPG kernels for sm_100a: 14-bit unpack -> frugal pedestal -> [RS | FIR] -> threshold hit finding -> TP list.
+//
+// One warp owns one 64-channel group for the whole batch (time is a sequential recurrence per channel; parallelism
+// comes from channels and links only). Frame bytes reach the warp through a private ring of shared-
+// memory stages filled by the TMA engine (cp.async.bulk + mbarrier complete_tx), so no thread ever waits on a
+// global load inside the tick loop and no block-wide barrier exists.
+//
+// Algorithms are policy structs with the same shape:
+//   struct Algo { load(state, lane); seed(S); tick<...>(S, ctx, t); store(state, lane); }
+// `Scalar*` policies do the arithmetic one channel at a time in 32-bit registers, exactly as written in the
+// reference (any configuration); `Packed*` policies are the production fast paths on packed s16x2 registers and are
+// selected by the host only for configurations inside their documented validity range (swtpg_capi.cu: pick_kernel).
+#pragma once
+
+#include "swtpg_device.cuh"
+
+namespace swtpg {
+
+// ---- HBM-resident per-group state (struct of arrays: [group][var][lane], u32 = two packed channels) -------------
+enum StateVar
+{
+  SV_MEDIAN = 0,
+  SV_ACCUM,
+  SV_PREV,
+  SV_CHARGE,
+  SV_TOVER,
+  SV_PEAK_ADC,
+  SV_PEAK_TIME,
+  SV_Q25,
+  SV_Q75,
+  SV_A25,
+  SV_A75,
+  SV_RS,
+  SV_MED_RS,
+  SV_ACC_RS,
+  SV_RS_FACTOR,
+  SV_RING0, // .. SV_RING0 + 7
+  SV_COUNT = SV_RING0 + 8
+};
+constexpr uint32_t kStateWordsPerGroup = SV_COUNT * 32;
+constexpr uint32_t kFlagInitialized = 1u;
+
+struct KernelParams
+{
+  const uint8_t* frames;   // link-major units
+  const uint32_t* n_units; // per link, or nullptr = units_stride everywhere
+  uint32_t units_stride;
+  uint32_t n_links;
+  uint32_t* state;         // [n_groups][SV_COUNT][32]
+  uint32_t* group_flags;   // [n_groups]: bit 0 initialized, bits 8..10 FIR ring phase (absTimeModNTAPS)
+  TpSink sink;
+  int16_t* pedestal_out;   // debug dumps [link][unit][tick][channel] or nullptr
+  int16_t* waveform_out;
+  // configuration (swtpg_config)
+  uint32_t threshold;      // u16
+  int32_t acc_limit;       // i16
+  int32_t rs_scale;        // i16
+  int32_t tap_exponent;
+  int32_t taps[8];
+  uint32_t wib2_adc_offset;
+};
+
+struct TickCtx
+{
+  uint64_t ts;      // timestamp of the current unit
+  uint32_t tick_base; // ticks of this batch before the current unit (FIR ring phase)
+  uint32_t link;
+  uint32_t chan0;   // frame channel of this lane's low half
+  const KernelParams* p;
+};
+
+// =====================================================================================================================
+// Scalar policies: the reference arithmetic, one channel at a time. Used for configurations outside the packed fast
+// paths' validity range and as the in-kernel statement of the semantics (cf. oracle/swtpg_oracle.c).
+// =====================================================================================================================
+
+// wibeth/tpg/UtilsAVX2.hpp:24-74 for one lane; mask = lane participates
+__device__ __forceinline__ void
+frugal_scalar(int& median, int s, int& accum, int L, bool mask)
+{
+  int to_add = s > median ? 1 : (s == median ? 0 : -1);
+  if (!mask)
+    to_add = 0;
+  accum = wrap16(accum + to_add);
+  const bool is_gt = accum > L;
+  const int b = wrap16(-L); // _mm256_set1_epi16(-1 * acclimit)
+  const int sa = b < 0 ? wrap16(-accum) : (b == 0 ? 0 : accum); // _mm256_sign_epi16
+  const bool is_lt = sa > L;
+  int step = is_gt ? 1 : 0;
+  if (is_lt)
+    step = -1;
+  if (!mask)
+    step = 0;
+  median = sat16(median + step);
+  if ((is_gt || is_lt) && mask)
+    accum = 0;
+}
+
+struct ChanRegs
+{ // one channel, unpacked
+  int median, accum, prev, charge, tover, peak_adc, peak_time;
+  int q25, q75, a25, a75;
+  int rs, med_rs, acc_rs, rs_factor;
+  int ring[8];
+};
+
+template<int ALGO, bool WIB2>
+struct ScalarAlgo
+{
+  ChanRegs c[2];
+  uint32_t kphase; // FIR ring phase
+
+  __device__ __forceinline__ void load(const uint32_t* st, uint32_t lane, uint32_t flags)
+  {
+    auto ld = [&](int v) { return st[v * 32 + lane]; };
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      auto g = [&](int v) { uint32_t w = ld(v); return h ? hi16s(w) : lo16s(w); };
+      ChanRegs& r = c[h];
+      r.median = g(SV_MEDIAN); r.accum = g(SV_ACCUM); r.prev = g(SV_PREV) & 0xFFFF; r.charge = g(SV_CHARGE) & 0xFFFF;
+      r.tover = g(SV_TOVER) & 0xFFFF; r.peak_adc = g(SV_PEAK_ADC) & 0xFFFF; r.peak_time = g(SV_PEAK_TIME) & 0xFFFF;
+      r.q25 = g(SV_Q25); r.q75 = g(SV_Q75); r.a25 = g(SV_A25); r.a75 = g(SV_A75);
+      r.rs = g(SV_RS); r.med_rs = g(SV_MED_RS); r.acc_rs = g(SV_ACC_RS); r.rs_factor = g(SV_RS_FACTOR);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        r.ring[j] = g(SV_RING0 + j);
+    }
+    kphase = (flags >> 8) & 7u;
+  }
+  __device__ __forceinline__ void store(uint32_t* st, uint32_t lane) const
+  {
+    auto put = [&](int v, int lo, int hi) { st[v * 32 + lane] = pack2(lo, hi); };
+    put(SV_MEDIAN, c[0].median, c[1].median); put(SV_ACCUM, c[0].accum, c[1].accum); put(SV_PREV, c[0].prev, c[1].prev);
+    put(SV_CHARGE, c[0].charge, c[1].charge); put(SV_TOVER, c[0].tover, c[1].tover);
+    put(SV_PEAK_ADC, c[0].peak_adc, c[1].peak_adc); put(SV_PEAK_TIME, c[0].peak_time, c[1].peak_time);
+    put(SV_Q25, c[0].q25, c[1].q25); put(SV_Q75, c[0].q75, c[1].q75); put(SV_A25, c[0].a25, c[1].a25); put(SV_A75, c[0].a75, c[1].a75);
+    put(SV_RS, c[0].rs, c[1].rs); put(SV_MED_RS, c[0].med_rs, c[1].med_rs); put(SV_ACC_RS, c[0].acc_rs, c[1].acc_rs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      put(SV_RING0 + j, c[0].ring[j], c[1].ring[j]);
+  }
+  __device__ __forceinline__ uint32_t phase_after(uint32_t ticks) const { return (kphase + ticks) & 7u; }
+  __device__ __forceinline__ void configure(const KernelParams&) {}
+
+  // setState: pedestal = first sample, quartiles +-20 (wibeth/tpg/ProcessingInfo.hpp:116-144)
+  __device__ __forceinline__ void seed(uint32_t S)
+  {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int ped = h ? int(S >> 16) : int(S & 0xFFFFu);
+      c[h].median = ped;
+      c[h].q25 = wrap16(ped - 20);
+      c[h].q75 = wrap16(ped + 20);
+    }
+  }
+
+  // One tick for both channels of the lane. Returns {pedestal u16x2, waveform s16x2} through refs (debug dumps).
+  __device__ __forceinline__ void tick(uint32_t S, const TickCtx& ctx, int t, uint32_t lane, uint32_t& ped_out, uint32_t& wav_out)
+  {
+    const KernelParams& p = *ctx.p;
+    const int thr = int(int16_t(uint16_t(p.threshold)));
+    int ped[2], wav[2];
+    if constexpr (ALGO == SWTPG_ALGO_FIR_IQR) {
+      // wib2/tpg/ProcessAVX2FIR.hpp:103-283
+      const int multiplier = 1 << p.tap_exponent;
+      const int adc_max = 32767 / multiplier;
+      const int sigma_max = (1 << 15) / (multiplier * 5);
+      int sigma[2], filt[2];
+      const uint32_t kk = (kphase + ctx.tick_base + uint32_t(t)) & 7u; // absTimeModNTAPS at this tick
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        ChanRegs& r = c[h];
+        const int raw = h ? int(S >> 16) : int(S & 0xFFFFu);
+        const bool is_gt = raw > r.median, is_lt = raw < r.median;
+        frugal_scalar(r.q25, raw, r.a25, 10, is_lt);
+        frugal_scalar(r.q75, raw, r.a75, 10, is_gt);
+        frugal_scalar(r.median, raw, r.accum, 10, true);
+        int x = wrap16(raw - r.median);
+        int sg = wrap16(r.q75 - r.q25);
+        sg = sg > sigma_max ? sigma_max : sg;
+        sigma[h] = sg;
+        x = x > adc_max ? adc_max : x;
+        int f = 0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          int rv = 0; // ring[(j + kphase + t) & 7] without dynamic register indexing
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            rv = (((j + kk) & 7) == q) ? r.ring[q] : rv;
+          f = wrap16(f + wrap16(p.taps[j] * rv));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (kk == q)
+            r.ring[q] = x;
+        filt[h] = f;
+        ped[h] = r.median;
+        wav[h] = f;
+      }
+      // Threshold = 16-bit lane of a 64-bit-lane product over 4 adjacent AVX2 register POSITIONS.
+      // Position q of register r holds channel 16r + perm[q]; gather the 16 sigmas of this lane's register.
+      const uint32_t sig_packed = pack2(sigma[0], sigma[1]);
+      uint32_t sig8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sig8[j] = __shfl_sync(0xFFFFFFFFu, sig_packed, int((lane & ~7u) + j));
+      const uint64_t K = uint64_t(int64_t(int16_t(multiplier))) * uint64_t(p.threshold); // (sigma*mult)*thr mod 2^64
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ch16 = int(2 * (lane & 7u)) + h;                           // channel within the 16-channel register
+        const int pos = ch16 < 8 ? ch16 : (ch16 == 15 ? 8 : ch16 + 1);       // inverse of perm {0..7,15,8..14}
+        const int g = pos >> 2, jj = pos & 3;
+        uint64_t v = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int pp = 4 * g + i;
+          const int cc = pp < 8 ? pp : (pp == 8 ? 15 : pp - 1);              // perm
+          uint32_t w = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            w = (cc >> 1) == q ? sig8[q] : w;
+          const uint64_t s16 = (cc & 1) ? (w >> 16) : (w & 0xFFFFu);
+          v |= s16 << (16 * i);
+        }
+        v *= K;
+        const int th = int(int16_t(uint16_t(v >> (16 * jj))));
+        ChanRegs& r = c[h];
+        const bool over = filt[h] > th;
+        const bool left = r.prev && !over;
+        r.charge = sat16(int(int16_t(r.charge)) + ((over ? filt[h] : 0) >> p.tap_exponent)) & 0xFFFF;
+        r.tover = sat16(int(int16_t(r.tover)) + (over ? 1 : 0)) & 0xFFFF;
+        if (left) {
+          emit_wib2(p.sink, ctx.ts, t, uint32_t(r.charge), uint32_t(r.tover), ctx.chan0 + h, ctx.link);
+          r.charge = r.tover = 0;
+        }
+        r.prev = over ? 0xFFFF : 0;
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        ChanRegs& r = c[h];
+        const int raw = h ? int(S >> 16) : int(S & 0xFFFFu);
+        const int L = (WIB2 && ALGO == SWTPG_ALGO_SIMPLE_THRESHOLD) ? 10 : p.acc_limit; // wib2/tpg/ProcessAVX2.hpp:79
+        frugal_scalar(r.median, raw, r.accum, L, true);
+        const int x = wrap16(raw - r.median);
+        int level = x; // what the threshold sees
+        if constexpr (ALGO == SWTPG_ALGO_ABS_RS || ALGO == SWTPG_ALGO_STANDARD_RS) {
+          // wibeth/tpg/ProcessAbsRSAVX2.hpp:137-159, ProcessStandardRSAVX2.hpp:140-144
+          const int first = wrap16(r.rs * int(int16_t(r.rs_factor)));
+          const int ax = x < 0 ? wrap16(-x) : x;
+          const int sum = ALGO == SWTPG_ALGO_STANDARD_RS ? wrap16(first + x) : wrap16(first + wrap16(ax * p.rs_scale));
+          int rs = wrap16((((sum * 3276) >> 14) + 1) >> 1); // _mm256_mulhrs_epi16(sum, 32768/10)
+          frugal_scalar(r.med_rs, rs, r.acc_rs, p.acc_limit, true);
+          rs = wrap16(rs - r.med_rs);
+          r.rs = rs;
+          level = rs;
+        }
+        const bool over = level > thr;
+        const bool left = r.prev && !over;
+        if constexpr (WIB2) { // wib2/tpg/ProcessAVX2.hpp:104-121
+          r.charge = sat16(int(int16_t(r.charge)) + ((over ? x : 0) >> p.tap_exponent)) & 0xFFFF;
+          r.tover = sat16(int(int16_t(r.tover)) + (over ? 1 : 0)) & 0xFFFF;
+          if (left) {
+            emit_wib2(p.sink, ctx.ts, t, uint32_t(r.charge), uint32_t(r.tover), ctx.chan0 + h, ctx.link);
+            r.charge = r.tover = 0;
+          }
+        } else { // wibeth/tpg/ProcessAVX2.hpp:114-204
+          if constexpr (ALGO == SWTPG_ALGO_SIMPLE_THRESHOLD)
+            r.charge = wrap16(int(int16_t(r.charge)) + (over ? x : 0)) & 0xFFFF; // add_epi16 wraps (H3)
+          else
+            r.charge = sat16(int(int16_t(r.charge)) + (over ? x : 0)) & 0xFFFF;  // adds_epi16
+          if (x > int(int16_t(r.peak_adc))) { // not gated by `over` (H6)
+            r.peak_adc = x & 0xFFFF;
+            r.peak_time = r.tover;
+          }
+          r.tover = sat16(int(int16_t(r.tover)) + (over ? 1 : 0)) & 0xFFFF;
+          if (left) {
+            emit_wibeth(p.sink, ctx.ts, t, uint32_t(r.charge), uint32_t(r.tover), uint32_t(r.peak_adc), uint32_t(r.peak_time),
+                        ctx.chan0 + h, ctx.link);
+            r.charge = r.tover = r.peak_adc = r.peak_time = 0;
+          }
+        }
+        r.prev = over ? 0xFFFF : 0;
+        ped[h] = r.median;
+        wav[h] = level;
+      }
+    }
+    ped_out = pack2(ped[0], ped[1]);
+    wav_out = pack2(wav[0], wav[1]);
+  }
+};
+
+// =====================================================================================================================
+// Packed fast path: WIBEth SimpleThreshold (wibeth/tpg/ProcessAVX2.hpp:23-229), two channels per 32-bit register.
+// Validity (checked by the host before selecting it): 1 <= L <= 16000 and 0 <= threshold <= 32767.
+//   * median m stays in [0, 16383] (it only ever steps towards samples, which are 14-bit), so adds_epi16 on it never
+//     saturates, and -m fits a signed half;
+//   * with a constant L >= 1 the accumulator is in [-L, L] between ticks, so "acc > L" <=> acc == L+1 and
+//     "-acc > L" <=> acc == -(L+1): both become add+clamp (VIADDMNMX) results in {0,1} / {0,-1};
+//   * pedestal-subtracted samples s' are in [-16383, 16383] and threshold / peak_adc are non-negative, which is the
+//     operand range gt2_mask_nonneg requires.
+// Registers hold NEGATED median / tover / peak_time so that every update is an add (VIADD.16x2 has no subtract form).
+// =====================================================================================================================
+struct PackedSimpleWibEth
+{
+  uint32_t Mn, A, prev, C, Tn, PK, PTn;
+  uint32_t negL2, posL2, thr2;
+
+  __device__ __forceinline__ void configure(const KernelParams& p)
+  {
+    const uint32_t L = uint32_t(p.acc_limit) & 0xFFFFu;
+    posL2 = L | (L << 16);
+    negL2 = neg2(posL2);
+    uint32_t th = p.threshold > 16383u ? 16383u : p.threshold; // s' <= 16383: any larger threshold is never exceeded
+    thr2 = th | (th << 16);
+  }
+  __device__ __forceinline__ void load(const uint32_t* st, uint32_t lane, uint32_t)
+  {
+    Mn = neg2(st[SV_MEDIAN * 32 + lane]);
+    A = st[SV_ACCUM * 32 + lane];
+    prev = st[SV_PREV * 32 + lane];
+    C = st[SV_CHARGE * 32 + lane];
+    Tn = neg2(st[SV_TOVER * 32 + lane]);
+    PK = st[SV_PEAK_ADC * 32 + lane];
+    PTn = neg2(st[SV_PEAK_TIME * 32 + lane]);
+  }
+  __device__ __forceinline__ void store(uint32_t* st, uint32_t lane) const
+  {
+    st[SV_MEDIAN * 32 + lane] = neg2(Mn);
+    st[SV_ACCUM * 32 + lane] = A;
+    st[SV_PREV * 32 + lane] = prev;
+    st[SV_CHARGE * 32 + lane] = C;
+    st[SV_TOVER * 32 + lane] = neg2(Tn);
+    st[SV_PEAK_ADC * 32 + lane] = PK;
+    st[SV_PEAK_TIME * 32 + lane] = neg2(PTn);
+  }
+  __device__ __forceinline__ uint32_t phase_after(uint32_t) const { return 0; }
+  __device__ __forceinline__ void seed(uint32_t S) { Mn = neg2(S); }
+
+  __device__ __forceinline__ void tick(uint32_t S, const TickCtx& ctx, int t, uint32_t, uint32_t& ped_out, uint32_t& wav_out)
+  {
+    // frugal streaming median (wibeth/tpg/UtilsAVX2.hpp:38-73)
+    const uint32_t sg = min2(addmax2(S, Mn, 0xFFFFFFFFu), 0x00010001u); // sign(s - m) in {-1,0,1}
+    A = add2(A, sg);
+    const uint32_t up = addmax2(A, negL2, 0u);        // {0,1}: acc == L+1
+    const uint32_t dn = addmin2(A, posL2, 0u);        // {0,0xFFFF}: acc == -(L+1)
+    const uint32_t upm = up * 0xFFFFu;                // {0,0xFFFF} (no cross-half carry: halves are 0 or 1)
+    Mn = add2(Mn, upm | (dn & 0x00010001u));          // -m -= up ; -m += dn
+    A &= ~(upm | dn);                                 // reset where stepped
+    const uint32_t sp = add2(S, Mn);                  // s' = s - m                       (ProcessAVX2.hpp:85)
+    // hit finding
+    const uint32_t over = gt2_mask_nonneg(sp, thr2);  //                                  (:97-98)
+    const uint32_t left = prev & ~over;               //                                  (:102)
+    C = add2(C, sp & over);                           // wrapping charge                  (:114-118)
+    const uint32_t gtp = gt2_mask_nonneg(sp, PK);     // un-gated peak tracking           (:134-136)
+    PK = max2(PK, sp);
+    PTn = (Tn & gtp) | (PTn & ~gtp);                  // peak_time = tover BEFORE increment
+    Tn = addmax2(Tn, over, 0x80018001u);              // tover = adds(tover, 1): -tover >= -32767   (:139-140)
+    if (left) {                                       //                                  (:154-204)
+      const KernelParams& p = *ctx.p;
+      if (left & 0xFFFFu)
+        emit_wibeth(p.sink, ctx.ts, t, C & 0xFFFFu, uint32_t(-lo16s(Tn)) & 0xFFFFu, PK & 0xFFFFu, uint32_t(-lo16s(PTn)) & 0xFFFFu,
+                    ctx.chan0, ctx.link);
+      if (left >> 16)
+        emit_wibeth(p.sink, ctx.ts, t, C >> 16, uint32_t(-hi16s(Tn)) & 0xFFFFu, PK >> 16, uint32_t(-hi16s(PTn)) & 0xFFFFu,
+                    ctx.chan0 + 1, ctx.link);
+      C &= ~left;
+      Tn &= ~left;
+      PK &= ~left;
+      PTn &= ~left;
+    }
+    prev = over;
+    ped_out = neg2(Mn);
+    wav_out = sp;
+  }
+};
+
+// =====================================================================================================================
+// WIBEth kernel: one warp per link (64 channels), per-warp TMA ring of CHUNK_TICKS-tick stages.
+// =====================================================================================================================
+constexpr int kWibEthRowBytes = 112;
+
+template<class Algo, int WARPS, int NSTAGE, int CHUNK_TICKS, bool DUMP>
+__global__ void __launch_bounds__(WARPS * 32)
+wibeth_kernel(const KernelParams p)
+{
+  static_assert(64 % CHUNK_TICKS == 0, "chunk must divide the frame");
+  constexpr int kChunkBytes = kWibEthRowBytes * CHUNK_TICKS;
+  constexpr int kChunksPerUnit = 64 / CHUNK_TICKS;
+  extern __shared__ __align__(128) uint8_t smem[];
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t link = blockIdx.x * WARPS + warp;
+  if (link >= p.n_links)
+    return; // warps are fully independent: no block-level barrier anywhere below
+  const uint32_t n_units = p.n_units ? p.n_units[link] : p.units_stride;
+  if (n_units == 0)
+    return;
+
+  uint8_t* stages = smem + size_t(warp) * NSTAGE * kChunkBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(WARPS) * NSTAGE * kChunkBytes) + warp * NSTAGE;
+  const uint8_t* link_base = p.frames + size_t(link) * p.units_stride * SWTPG_WIBETH_FRAME_BYTES;
+  const uint32_t total_chunks = n_units * kChunksPerUnit;
+
+  auto issue = [&](uint32_t chunk) { // lane 0 only
+    const uint32_t st = chunk % NSTAGE;
+    const uint8_t* src = link_base + size_t(chunk / kChunksPerUnit) * SWTPG_WIBETH_FRAME_BYTES + 32 + size_t(chunk % kChunksPerUnit) * kChunkBytes;
+    mbar_arrive_expect_tx(&bars[st], kChunkBytes);
+    bulk_g2s(stages + size_t(st) * kChunkBytes, src, kChunkBytes, &bars[st]);
+  };
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s)
+      mbar_init(&bars[s], 1);
+    fence_mbar_init();
+    const uint32_t pre = total_chunks < uint32_t(NSTAGE) ? total_chunks : uint32_t(NSTAGE);
+    for (uint32_t c = 0; c < pre; ++c)
+      issue(c);
+  }
+  __syncwarp();
+
+  uint32_t* st = p.state + size_t(link) * kStateWordsPerGroup;
+  const uint32_t flags = p.group_flags[link];
+  Algo algo;
+  algo.configure(p);
+  algo.load(st, lane, flags);
+  bool need_seed = !(flags & kFlagInitialized);
+
+  const PairPos pp = pair_pos(lane);
+  TickCtx ctx;
+  ctx.p = &p;
+  ctx.link = link;
+  ctx.chan0 = 2 * lane;
+  ctx.ts = 0;
+  ctx.tick_base = 0;
+
+  for (uint32_t chunk = 0; chunk < total_chunks; ++chunk) {
+    const uint32_t stg = chunk % NSTAGE;
+    const uint32_t unit = chunk / kChunksPerUnit;
+    const int t0 = int(chunk % kChunksPerUnit) * CHUNK_TICKS;
+    ctx.tick_base = unit * 64u;
+    if (t0 == 0) // DAQEthHeader word 1 = timestamp (docs/README.md:81); consumed only when a hit ends
+      ctx.ts = *reinterpret_cast<const unsigned long long*>(link_base + size_t(unit) * SWTPG_WIBETH_FRAME_BYTES + 8);
+    mbar_wait(&bars[stg], (chunk / NSTAGE) & 1u);
+    const uint32_t* rows = reinterpret_cast<const uint32_t*>(stages + size_t(stg) * kChunkBytes);
+    if (need_seed) {
+      algo.seed(extract_pair(rows, pp));
+      need_seed = false;
+    }
+#pragma unroll 4
+    for (int tt = 0; tt < CHUNK_TICKS; ++tt) {
+      const uint32_t S = extract_pair(rows + tt * (kWibEthRowBytes / 4), pp);
+      uint32_t ped, wav;
+      algo.tick(S, ctx, t0 + tt, lane, ped, wav);
+      if constexpr (DUMP) {
+        const size_t o = ((size_t(link) * p.units_stride + unit) * 64 + size_t(t0 + tt)) * 32 + lane; // u32 = 2 channels
+        if (p.pedestal_out)
+          reinterpret_cast<uint32_t*>(p.pedestal_out)[o] = ped;
+        if (p.waveform_out)
+          reinterpret_cast<uint32_t*>(p.waveform_out)[o] = wav;
+      }
+    }
+    __syncwarp(); // every lane is done reading this stage
+    if (lane == 0 && chunk + NSTAGE < total_chunks) {
+      fence_proxy_async();
+      issue(chunk + NSTAGE);
+    }
+  }
+
+  algo.store(st, lane);
+  if (lane == 0)
+    p.group_flags[link] = kFlagInitialized | (algo.phase_after(n_units * 64u) << 8);
+}
+
+} // namespace swtpg

@@ -1,0 +1,214 @@
+/*
+ * swtpg.h — C ABI of the B200-native software trigger-primitive generator (libswtpg_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of DUNE-DAQ/fdreadoutlibs: what happens inside
+ * WIBEthFrameProcessor::find_hits / WIB2FrameProcessor::find_hits, i.e.
+ *   14-bit unpack -> frugal-streaming pedestal -> [running sum | FIR] -> threshold hit finding -> TriggerPrimitive fields.
+ * Every entry point names the reference interface it replaces (paths relative to the reference repository root).
+ * Plain C: POD structs, pointers and sizes, integer status codes; no exceptions cross this boundary and no
+ * torch / CUDA types appear in any signature (streams and device pointers travel as void*).
+ *
+ * There is no CPU fallback: every compute entry point fails with SWTPG_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef SWTPG_H_
+#define SWTPG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWTPG_ABI_VERSION 1u
+
+/* Frame geometry restated from the reference (sizes pinned by static_asserts there). */
+#define SWTPG_WIBETH_FRAME_BYTES 7200u /* include/fdreadoutlibs/DUNEWIBEthTypeAdapter.hpp:20-22,98 */
+#define SWTPG_WIBETH_CHANNELS 64u
+#define SWTPG_WIBETH_TICKS 64u        /* wibeth/tpg/TPGConstants_wibeth.hpp:22 (FRAMES_PER_MSG) */
+#define SWTPG_WIBETH_TS_PER_FRAME 2048u /* DUNEWIBEthTypeAdapter.hpp:93 */
+#define SWTPG_WIB2_FRAME_BYTES 472u
+#define SWTPG_WIB2_SUPERCHUNK_BYTES 5664u /* include/fdreadoutlibs/DUNEWIBSuperChunkTypeAdapter.hpp:18-22,100 */
+#define SWTPG_WIB2_CHANNELS 256u
+#define SWTPG_WIB2_TICKS 12u          /* wib2/tpg/TPGConstants_wib2.hpp:30 (FRAMES_PER_MSG) */
+#define SWTPG_TS_PER_TICK 32u         /* DUNEWIBEthTypeAdapter.hpp:95, DUNEWIBSuperChunkTypeAdapter.hpp:97 */
+#define SWTPG_MAX_TAPS 8u
+
+typedef enum swtpg_status
+{
+  SWTPG_OK = 0,
+  SWTPG_ERR_INVALID_ARG = 1,
+  SWTPG_ERR_CUDA = 2,       /* no usable device / CUDA runtime error; see swtpg_last_error() */
+  SWTPG_ERR_BUSY = 3,       /* back-pressure: staging ring full (reference: FailedToSendTP-style drop, never blocks) */
+  SWTPG_ERR_OVERFLOW = 4,   /* more TPs than the caller's / the device buffer's capacity; count is still reported */
+  SWTPG_ERR_STATE = 5,      /* call sequence violated (e.g. submit before start) */
+  SWTPG_ERR_UNSUPPORTED = 6 /* reference: TPGAlgorithmInexistent (include/fdreadoutlibs/FDReadoutIssues.hpp:27-31) */
+} swtpg_status;
+
+typedef enum swtpg_format
+{
+  SWTPG_FORMAT_WIBETH = 0, /* unit = one 7200-B WIBEthFrame: 64 channels x 64 ticks */
+  SWTPG_FORMAT_WIB2 = 1    /* unit = one 5664-B superchunk of 12 WIB2 frames: 256 channels x 12 ticks */
+} swtpg_format;
+
+/* tpg_algorithm strings of the reference (src/wibeth/WIBEthFrameProcessor.cpp:180-197) plus the FIR+IQR finder that
+ * the reference ships for WIB2/ProtoWIB (include/fdreadoutlibs/wib2/tpg/ProcessAVX2FIR.hpp). */
+typedef enum swtpg_algorithm
+{
+  SWTPG_ALGO_SIMPLE_THRESHOLD = 0, /* "SimpleThreshold": wibeth/tpg/ProcessAVX2.hpp, wib2/tpg/ProcessAVX2.hpp */
+  SWTPG_ALGO_ABS_RS = 1,           /* "AbsRS":      wibeth/tpg/ProcessAbsRSAVX2.hpp, wib2/tpg/ProcessRSAVX2.hpp */
+  SWTPG_ALGO_STANDARD_RS = 2,      /* "StandardRS": wibeth/tpg/ProcessStandardRSAVX2.hpp */
+  SWTPG_ALGO_FIR_IQR = 3           /* FIR matched filter + IQR threshold: wib2/tpg/ProcessAVX2FIR.hpp */
+} swtpg_algorithm;
+
+/* One trigger primitive as emitted by the device: the fields process_swtpg_hits derives per hit
+ * (src/wibeth/WIBEthFrameProcessor.cpp:523-545, src/wib2/WIB2FrameProcessor.cpp:431-455) BEFORE the
+ * register->offline-channel LUT, channel mask and tp_timeout filters, which stay on the host shim.
+ * `channel` is the frame channel (WIBEth 0..63, WIB2 0..255); see DESIGN.md "H2". 32 bytes. */
+typedef struct swtpg_tp
+{
+  uint64_t time_start;          /* 62.5 MHz ticks: ts(frame of hit end) + 32*(t_end - tover) */
+  uint64_t time_peak;
+  uint32_t time_over_threshold; /* 32 * samples over threshold */
+  uint32_t adc_integral;
+  uint16_t adc_peak;
+  uint16_t channel;
+  uint32_t link;                /* index of the link inside this handle (0..n_links-1) */
+} swtpg_tp;
+
+/* Mirrors the fields of readoutlibs' RawDataProcessorConf that the hot path consumes
+ * (src/wibeth/WIBEthFrameProcessor.cpp:175-230) and the handler constants
+ * (include/fdreadoutlibs/wibeth/WIBEthFrameProcessor.hpp:69, wib2/WIB2FrameProcessor.hpp:68-69). */
+typedef struct swtpg_config
+{
+  uint32_t struct_size;      /* = sizeof(swtpg_config); lets the ABI grow */
+  int32_t device;            /* CUDA device ordinal */
+  int32_t format;            /* swtpg_format */
+  int32_t algorithm;         /* swtpg_algorithm */
+  uint32_t n_links;          /* independent links owned by this handle (one reference FrameProcessor each) */
+  uint32_t max_units;        /* superchunk length: units (frames / WIB2 superchunks) per link per batch */
+  uint32_t tp_capacity;      /* device TP buffer, records per batch; 0 = sized for the worst case */
+  uint32_t n_slots;          /* staging-ring depth of the streaming path (>= 2); 0 = 3 */
+  uint16_t threshold;        /* tpg_threshold (ADC; sigma units for FIR_IQR) */
+  int16_t frugal_acc_limit;  /* tpg_frugal_streaming_accumulator_limit (WIB2 and FIR paths hard-wire 10) */
+  uint16_t rs_memory_factor; /* already x10, as conf() scales it (WIBEthFrameProcessor.cpp:202) */
+  uint16_t rs_scale_factor;  /* already 10/x (WIBEthFrameProcessor.cpp:206) */
+  int16_t fir_taps[SWTPG_MAX_TAPS]; /* FIR_IQR only; all-zero = firwin_int(7,0.1,64)+{0} = {1,6,15,20,15,6,1,0} */
+  uint8_t tap_exponent;      /* m_tpg_tap_exponent = 6 */
+  uint8_t reserved0[3];
+  uint32_t wib2_adc_offset;  /* byte offset of adc_words inside a WIB2 frame; 0 = 20 */
+  uint32_t flags;            /* SWTPG_FLAG_* */
+} swtpg_config;
+
+#define SWTPG_FLAG_NONE 0u
+
+/* Per-channel carried state, by frame channel: ChanState of wibeth/tpg/ProcessingInfo.hpp:20-66 and
+ * wib2/tpg/ProcessingInfo.hpp:20-68. Used for parity dumps only. */
+typedef struct swtpg_channel_state
+{
+  int16_t pedestal, accum;
+  int16_t quantile25, quantile75, accum25, accum75;
+  int16_t rs, pedestal_rs, accum_rs;
+  uint16_t rs_memory_factor;
+  uint16_t prev_was_over, hit_charge, hit_tover, hit_peak_adc, hit_peak_time;
+  uint16_t initialized; /* 0 until the first unit seeded the pedestal (setState) */
+  int16_t prev_samp[SWTPG_MAX_TAPS];
+} swtpg_channel_state;
+
+/* Counters behind the opmon fields of get_info (src/wibeth/WIBEthFrameProcessor.cpp:237-292). */
+typedef struct swtpg_counters
+{
+  uint64_t units_processed;  /* frames / superchunks */
+  uint64_t samples_processed;
+  uint64_t tps_emitted;
+  uint64_t tps_dropped_overflow;
+  uint64_t batches;
+  uint64_t submit_busy;      /* swtpg_submit calls refused with SWTPG_ERR_BUSY */
+  uint64_t h2d_bytes, d2h_bytes;
+} swtpg_counters;
+
+typedef struct swtpg_handle swtpg_handle;
+
+uint32_t swtpg_abi_version(void);
+const char* swtpg_status_string(swtpg_status s);
+/* Thread-local text of the last failure on this handle (NULL handle: last create failure). */
+const char* swtpg_last_error(const swtpg_handle* h);
+/* 1 if a CUDA device of compute capability 10.x is visible, else 0. Never throws, never initialises a context. */
+int swtpg_device_available(void);
+
+/* Replaces WIBEthFrameHandler::initialize / WIB2FrameHandler::initialize (buffers, taps, ProcessingInfo):
+ * src/wibeth/WIBEthFrameProcessor.cpp:74-91, src/wib2/WIB2FrameProcessor.cpp:90-120. */
+swtpg_status swtpg_create(const swtpg_config* cfg, swtpg_handle** out);
+void swtpg_destroy(swtpg_handle* h);
+
+/* Replaces the TPG part of FrameProcessor::start / ::stop: fresh zeroed ChanState, first_hit re-armed
+ * (src/wibeth/WIBEthFrameProcessor.cpp:111-154, 67-72). */
+swtpg_status swtpg_start(swtpg_handle* h);
+swtpg_status swtpg_stop(swtpg_handle* h);
+
+/* Per-position RS memory factor of AbsRS / StandardRS, by frame channel: [n_links][channels]
+ * (src/wibeth/WIBEthFrameProcessor.cpp:437-456). NULL = cfg.rs_memory_factor everywhere. Call before the first unit. */
+swtpg_status swtpg_set_rs_memory_factor(swtpg_handle* h, const uint16_t* by_link_channel);
+
+/*
+ * Batch entry points. `frames` is link-major: unit u of link l starts at ((l * units_stride) + u) * unit_bytes.
+ * n_units[l] <= units_stride <= cfg.max_units valid units for link l (ragged batches allowed; NULL = all links
+ * have units_stride units). State is carried from the previous batch per link, exactly as ProcessingInfo carries
+ * it from frame to frame. TPs come back unordered; sort with swtpg_sort_tps for (time_start, link, channel) order.
+ *
+ * Together these replace the body of find_hits: expand_wibeth_adcs + setState on the first frame +
+ * m_assigned_tpg_algorithm_function + process_swtpg_hits' field arithmetic
+ * (src/wibeth/WIBEthFrameProcessor.cpp:410-476,478-549; src/wib2/WIB2FrameProcessor.cpp:345-396,398-458).
+ */
+/* Host buffers (pageable or pinned): H2D copy, kernel, D2H of the TP list, all inside the call. */
+swtpg_status swtpg_process_host(swtpg_handle* h, const void* frames, const uint32_t* n_units, uint32_t units_stride,
+                                swtpg_tp* out, size_t cap, size_t* n_out);
+/* Frames already resident in HBM. `stream` is a cudaStream_t (NULL = the handle's own stream); asynchronous.
+ * TPs stay on the device until swtpg_fetch_tps. */
+swtpg_status swtpg_process_device(swtpg_handle* h, const void* d_frames, const uint32_t* n_units, uint32_t units_stride,
+                                  void* stream);
+/* Waits for the last swtpg_process_device, copies its TPs out. *n_out = TPs found (may exceed cap: OVERFLOW). */
+swtpg_status swtpg_fetch_tps(swtpg_handle* h, swtpg_tp* out, size_t cap, size_t* n_out);
+/* Device time of the last batch kernel in milliseconds (CUDA events on the launching stream); < 0 if none. */
+double swtpg_last_kernel_ms(swtpg_handle* h);
+
+/* Parity dump of the intermediate waveforms the reference can print (docs/README.md:31-36 "save-adc"):
+ * same as swtpg_process_host, plus per sample the pedestal AFTER its frugal update and the waveform the
+ * threshold is applied to (pedestal-subtracted ADC, running sum, or FIR output), both int16,
+ * laid out [link][unit][tick][channel] over units_stride units per link. Either may be NULL. */
+swtpg_status swtpg_process_host_debug(swtpg_handle* h, const void* frames, const uint32_t* n_units, uint32_t units_stride,
+                                      swtpg_tp* out, size_t cap, size_t* n_out, int16_t* pedestal_out, int16_t* waveform_out);
+
+/*
+ * Streaming entry points: what a FrameProcessor's post-processing thread calls once per payload.
+ * swtpg_submit copies one unit of `link` into the pinned staging slot being filled (the reference's constframeptr
+ * is only borrowed for the duration of find_hits). When every link of the handle has delivered cfg.max_units
+ * units — or on swtpg_flush — the slot is dispatched: async H2D, kernel, async D2H of the TP list, on the slot's
+ * stream. Never blocks: SWTPG_ERR_BUSY when all slots are in flight. One thread per link, any number of links
+ * concurrently. swtpg_poll hands back the TPs of completed batches, oldest first, without blocking; it replaces
+ * the per-hit m_tp_sink->try_send loop's source (src/wibeth/WIBEthFrameProcessor.cpp:555).
+ */
+swtpg_status swtpg_submit(swtpg_handle* h, uint32_t link, const void* unit, size_t bytes);
+swtpg_status swtpg_flush(swtpg_handle* h);
+swtpg_status swtpg_poll(swtpg_handle* h, swtpg_tp* out, size_t cap, size_t* n_out);
+/* Blocks until every dispatched batch has completed (used by stop and by tests). */
+swtpg_status swtpg_sync(swtpg_handle* h);
+
+/* Carried state of one link, by frame channel (ChanState parity). out has SWTPG_*_CHANNELS entries. */
+swtpg_status swtpg_dump_state(swtpg_handle* h, uint32_t link, swtpg_channel_state* out);
+swtpg_status swtpg_get_counters(swtpg_handle* h, swtpg_counters* out);
+
+/* Host-side ordering of a TP list by (time_start, link, channel): the order TriggerPrimitiveTypeAdapter::operator<
+ * imposes downstream (include/fdreadoutlibs/TriggerPrimitiveTypeAdapter.hpp:26-29). In place. */
+void swtpg_sort_tps(swtpg_tp* tps, size_t n);
+/* k-way merge of already sorted per-GPU TP lists into `out` (capacity sum of n[i]): the host-side time-ordered
+ * merge that follows link sharding across GPUs. */
+void swtpg_merge_sorted(const swtpg_tp* const* lists, const size_t* n, size_t k, swtpg_tp* out);
+
+/* firwin_int of src/wib2/tpg/DesignFIR.cpp:57-68 (host, double precision): taps[n]. Returns n. */
+int swtpg_firwin_int(int n, double cutoff, int multiplier, int16_t* taps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWTPG_H_ */
