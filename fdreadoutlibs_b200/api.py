@@ -149,9 +149,12 @@ class TPGenerator:
         self._check(st)
         return out[: n.value].copy()
 
-    def process_device(self, d_frames_ptr: int, units_stride: int, n_units=None, stream: int = 0):
+    def process_device(self, d_frames_ptr: int, units_stride: int, n_units=None, stream: Optional[int] = None):
+        """stream: a cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream) or None for the handle's own
+        stream. Handle value 0 (the legacy default stream, torch's default) is passed as cudaStreamLegacy."""
         nu = self._nunits(n_units)
-        self._check(lib.swtpg_process_device(self._h, C.c_void_p(d_frames_ptr), _ptr(nu), units_stride, C.c_void_p(stream)))
+        sp = None if stream is None else C.c_void_p(stream if stream != 0 else 1)
+        self._check(lib.swtpg_process_device(self._h, C.c_void_p(d_frames_ptr), _ptr(nu), units_stride, sp))
 
     def fetch_tps(self, cap: int = 1 << 20) -> np.ndarray:
         out = np.zeros(cap, dtype=F.TP_DTYPE)

@@ -17,6 +17,12 @@
 
 using namespace swtpg;
 
+// Layouts the ctypes binding (fdreadoutlibs_b200/_lib.py, frames.py) relies on.
+static_assert(sizeof(swtpg_tp) == 32, "swtpg_tp must stay 32 bytes (two 16-byte device stores)");
+static_assert(sizeof(swtpg_config) == 68, "swtpg_config layout changed: bump SWTPG_ABI_VERSION and the bindings");
+static_assert(sizeof(swtpg_channel_state) == 48, "swtpg_channel_state layout changed");
+static_assert(sizeof(swtpg_counters) == 64, "swtpg_counters layout changed");
+
 namespace {
 
 thread_local std::string g_create_error;

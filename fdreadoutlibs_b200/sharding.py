@@ -1,0 +1,57 @@
+"""Link sharding across GPUs and the host-side time-ordered TP merge.
+
+Every link is an independent recurrence with private state (the reference already runs one thread per link with no
+sharing: src/wibeth/WIBEthFrameProcessor.cpp:231), so links partition across GPUs as contiguous blocks with NO data-path
+collective. The only cross-GPU step is host-side: per-GPU TP lists, each sorted by (time_start, link, channel), are
+k-way merged — the order TriggerPrimitiveTypeAdapter::operator< imposes downstream
+(include/fdreadoutlibs/TriggerPrimitiveTypeAdapter.hpp:26-29, consumed by src/TPCTPRequestHandler.cpp:99-193).
+torch.distributed is used only as the transport that brings the lists to rank 0 (gloo on CPU, NCCL-initialised
+process groups fall back to their CPU object path for this host-side step).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import frames as F
+from .api import merge_sorted
+
+LINKS_PER_APA = 40  # 2560 channels / 64 channels per WIBEth link
+
+
+def shard_links(n_links: int, world_size: int, rank: int, keep_together: int = LINKS_PER_APA) -> Tuple[int, int]:
+    """Contiguous block [link0, link0 + n) of rank `rank`. Blocks are aligned to `keep_together` links (one APA stays on one
+    GPU) whenever there are at least as many such groups as ranks; otherwise links are split evenly."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError("bad world_size / rank")
+    groups = n_links // keep_together if keep_together > 0 else 0
+    if keep_together > 0 and groups >= world_size and n_links % keep_together == 0:
+        g0 = groups * rank // world_size
+        g1 = groups * (rank + 1) // world_size
+        return g0 * keep_together, (g1 - g0) * keep_together
+    l0 = n_links * rank // world_size
+    l1 = n_links * (rank + 1) // world_size
+    return l0, l1 - l0
+
+
+def globalise(tps: np.ndarray, link0: int) -> np.ndarray:
+    """Local link indices (0..n-1 inside one handle) -> global link numbers."""
+    out = tps.copy()
+    out["link"] = out["link"] + np.uint32(link0)
+    return out
+
+
+def gather_and_merge(local_sorted: np.ndarray, group=None, dst: int = 0) -> Optional[np.ndarray]:
+    """Rank `dst` receives every rank's sorted TP list and returns the merged list; other ranks return None."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    payload = np.ascontiguousarray(local_sorted, dtype=F.TP_DTYPE).tobytes()
+    gathered: Optional[List[bytes]] = [None] * world if rank == dst else None  # type: ignore[list-item]
+    dist.gather_object(payload, gathered, dst=dst, group=group)
+    if rank != dst:
+        return None
+    lists = [np.frombuffer(b, dtype=F.TP_DTYPE) for b in gathered]  # type: ignore[union-attr]
+    return merge_sorted(lists)

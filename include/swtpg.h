@@ -163,8 +163,9 @@ swtpg_status swtpg_set_rs_memory_factor(swtpg_handle* h, const uint16_t* by_link
 /* Host buffers (pageable or pinned): H2D copy, kernel, D2H of the TP list, all inside the call. */
 swtpg_status swtpg_process_host(swtpg_handle* h, const void* frames, const uint32_t* n_units, uint32_t units_stride,
                                 swtpg_tp* out, size_t cap, size_t* n_out);
-/* Frames already resident in HBM. `stream` is a cudaStream_t (NULL = the handle's own stream); asynchronous.
- * TPs stay on the device until swtpg_fetch_tps. */
+/* Frames already resident in HBM. `stream` is a cudaStream_t; NULL = the handle's own (non-blocking) stream — to run on
+ * the legacy default stream pass cudaStreamLegacy, i.e. (void*)1. Asynchronous: the caller orders the producer of
+ * d_frames before this call on that stream. TPs stay on the device until swtpg_fetch_tps. */
 swtpg_status swtpg_process_device(swtpg_handle* h, const void* d_frames, const uint32_t* n_units, uint32_t units_stride,
                                   void* stream);
 /* Waits for the last swtpg_process_device, copies its TPs out. *n_out = TPs found (may exceed cap: OVERFLOW). */

@@ -1,0 +1,112 @@
+"""CPU: the C-ABI shared library loads, exports every symbol the headers declare, has the documented record layouts,
+and refuses to compute without a GPU (no CPU fallback). Host-only helpers (generator, sort, merge, taps) are exercised."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fdreadoutlibs_b200 as S
+from fdreadoutlibs_b200 import _lib
+from fdreadoutlibs_b200 import frames as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for hdr in ("swtpg.h", "swtpg_framegen.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(swtpg_[a-z0-9_]+)\s*\(", text))
+    return names
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in sorted(names):
+        assert hasattr(_lib.lib, n), f"{n} declared in include/ but not exported by libswtpg_b200.so"
+    assert names == set(_lib.EXPORTS), f"binding and headers differ: {names ^ set(_lib.EXPORTS)}"
+
+
+def test_abi_version_and_layouts():
+    assert _lib.lib.swtpg_abi_version() == 1
+    assert F.TP_DTYPE.itemsize == 32
+    assert C.sizeof(_lib.SwtpgConfig) == 68  # static_assert'ed on the C side (swtpg_capi.cu)
+    assert C.sizeof(_lib.GenParams) == 32
+    assert F.STATE_DTYPE.itemsize == 48
+    assert _lib.lib.swtpg_status_string(3) == b"busy (back-pressure)"
+
+
+@pytest.mark.skipif(S.device_available(), reason="this check is for GPU-less hosts")
+def test_no_cpu_fallback():
+    with pytest.raises(S.SwtpgError) as e:
+        S.TPGenerator(1, 4)
+    assert e.value.status == _lib.SWTPG_ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_create_rejects_bad_config():
+    cfg = _lib.SwtpgConfig()
+    h = C.c_void_p()
+    assert _lib.lib.swtpg_create(C.byref(cfg), C.byref(h)) == _lib.SWTPG_ERR_INVALID_ARG  # struct_size == 0
+    cfg.struct_size = C.sizeof(cfg)
+    assert _lib.lib.swtpg_create(C.byref(cfg), C.byref(h)) == _lib.SWTPG_ERR_INVALID_ARG  # n_links == 0
+    cfg.n_links, cfg.max_units, cfg.algorithm = 1, 1, 17
+    assert _lib.lib.swtpg_create(C.byref(cfg), C.byref(h)) == _lib.SWTPG_ERR_UNSUPPORTED  # TPGAlgorithmInexistent
+    with pytest.raises(S.TPGAlgorithmInexistent):
+        S.TPGenerator(1, 1, algorithm="NoSuchAlgo")
+
+
+def test_generator_is_deterministic_and_sharding_invariant():
+    p = S.gen_params(7, 0.1)
+    a = S.gen_wibeth_host(p, 6, 5, n_threads=1)
+    b = S.gen_wibeth_host(p, 6, 5, n_threads=4)
+    assert (a == b).all()
+    part = S.gen_wibeth_host(p, 2, 3, link0=3, unit0=2)
+    assert (part == a[3:5, 2:5]).all()  # any (link, unit) window reproduces the same bytes
+    adc, ts = F.unpack_wibeth_frames(a[1])
+    assert list(ts) == [(1 << 40) + 2048 * i for i in range(5)]
+    assert 850 < adc.mean() < 1700 and adc.max() <= 16383
+    w = S.gen_wib2_host(p, 2, 4)
+    adc2, ts2 = F.unpack_wib2_superchunks(w[1])
+    assert list(ts2[:3]) == [1 << 40, (1 << 40) + 32, (1 << 40) + 64] and adc2.shape == (48, 256)
+    # WIB2 link l channel c tick t is the same waveform as global channel 256 l + c
+    assert (S.gen_wib2_host(p, 1, 4, link0=1)[0] == w[1]).all()
+
+
+def test_pack_unpack_roundtrip():
+    rng = np.random.default_rng(0)
+    adc = rng.integers(0, 16384, size=(3, 64, 64), dtype=np.uint16)
+    fr = F.pack_wibeth_frames(adc, 12345)
+    back, ts = F.unpack_wibeth_frames(fr)
+    assert (back == adc).all() and list(ts) == [12345, 12345 + 2048, 12345 + 4096]
+    adc2 = rng.integers(0, 16384, size=(24, 256), dtype=np.uint16)
+    sc = F.pack_wib2_superchunks(adc2, 99)
+    back2, ts2 = F.unpack_wib2_superchunks(sc)
+    assert (back2 == adc2).all() and ts2[13] == 99 + 32 * 13
+
+
+def test_sort_and_merge():
+    rng = np.random.default_rng(1)
+    tps = np.zeros(5000, dtype=F.TP_DTYPE)
+    tps["time_start"] = rng.integers(0, 400, 5000)
+    tps["link"] = rng.integers(0, 8, 5000)
+    tps["channel"] = rng.integers(0, 64, 5000)
+    tps["adc_integral"] = rng.integers(1, 60000, 5000)
+    s = S.sort_tps(tps)
+    key = list(zip(s["time_start"].tolist(), s["link"].tolist(), s["channel"].tolist()))
+    assert key == sorted(key)
+    parts = [S.sort_tps(tps[tps["link"] % 3 == r]) for r in range(3)]
+    merged = S.merge_sorted(parts)
+    assert merged.size == tps.size
+    assert (F.sort_tps(merged) == F.sort_tps(tps)).all()
+    mk = list(zip(merged["time_start"].tolist(), merged["link"].tolist(), merged["channel"].tolist()))
+    assert mk == sorted(mk)
+    assert S.merge_sorted([np.zeros(0, dtype=F.TP_DTYPE), parts[0]]).size == parts[0].size
+
+
+def test_firwin_int_host():
+    assert list(S.firwin_int(7, 0.1, 64)) == [1, 6, 15, 20, 15, 6, 1]

@@ -1,0 +1,253 @@
+"""GPU (B200): parity of the CUDA path — always called through the C ABI (include/swtpg.h) — against the CPU oracle and the
+reference-generated golden vectors. Bit-exact: TP field tuples, carried state, pedestal and waveform dumps."""
+import numpy as np
+import pytest
+
+import cases
+import fdreadoutlibs_b200 as S
+from fdreadoutlibs_b200 import frames as F
+from oracle import binding as B
+from util import assert_same_tps, oracle_config
+
+pytestmark = pytest.mark.gpu
+
+WIBETH_CASES = sorted(n for n, c in cases.GOLDEN_CASES.items() if c["fmt"] == "wibeth" and c["flavour"] == 0)
+
+
+def run_gpu(case, units, max_units=None, **kw):
+    n_links, n_units = units.shape[0], units.shape[1]
+    with S.TPGenerator(n_links, max_units or n_units, fmt=case["fmt"], algorithm=case["algorithm"], threshold=case["threshold"],
+                       acc_limit=case.get("acc_limit", 10), rs_memory_factor=case.get("rs_memory_factor", 8),
+                       rs_scale_factor=case.get("rs_scale_factor", 5), **kw) as g:
+        g.start()
+        step = max_units or n_units
+        parts = [g.process_host(np.ascontiguousarray(units[:, u:u + step])) for u in range(0, n_units, step)]
+        ped = np.stack([g.dump_state(l)["pedestal"] for l in range(n_links)])
+        return np.concatenate(parts), ped
+
+
+@pytest.mark.parametrize("name", WIBETH_CASES)
+def test_golden_cases(name, golden):
+    """Same inputs as tests/golden/make_golden.py fed the reference with: TPs and final pedestals must be identical."""
+    case = cases.GOLDEN_CASES[name]
+    units = cases.make_input(case)
+    tps, ped = run_gpu(case, units)
+    assert_same_tps(tps, golden[name + "__tps"], name)
+    assert (ped == golden[name + "__pedestal"]).all()
+
+
+@pytest.mark.parametrize("name", ["noise_simple_thr60", "dense_simple_thr8", "noise_absrs_thr30"])
+@pytest.mark.parametrize("max_units", [1, 7, 32])
+def test_batching_does_not_change_results(name, max_units, golden):
+    """Superchunk length is an implementation choice: state carried across batches must make it invisible."""
+    case = cases.GOLDEN_CASES[name]
+    tps, ped = run_gpu(case, cases.make_input(case), max_units=max_units)
+    assert_same_tps(tps, golden[name + "__tps"], f"{name} max_units={max_units}")
+    assert (ped == golden[name + "__pedestal"]).all()
+
+
+@pytest.mark.parametrize("algorithm,thr,L", [("SimpleThreshold", 25, 10), ("SimpleThreshold", 0, 1), ("SimpleThreshold", 25, 0),
+                                              ("SimpleThreshold", 40000, 10), ("SimpleThreshold", 25, -3), ("SimpleThreshold", 12, 300),
+                                              ("AbsRS", 30, 10), ("StandardRS", 30, 4), ("FIR", 5, 10), ("FIR", 40, 10)])
+def test_against_oracle_with_state_and_dumps(algorithm, thr, L):
+    """Random waveforms, several links, 3 batches (last one short): TPs, every carried state field, and the per-sample
+    pedestal / filtered-waveform dumps equal the oracle's. Covers the packed fast path (L >= 1, thr <= 32767) and the
+    scalar path (degenerate accumulator limits, thresholds >= 2^15 that the reference compares as negative int16)."""
+    n_links, n_units = 5, 20
+    units = S.gen_wibeth_host(S.gen_params(41, 0.4), n_links, n_units)
+    cfg = B.make_config(algorithm=S.ALGORITHMS[algorithm], threshold=thr, acc_limit=L)
+    oracles = [B.Oracle(cfg, link_id=l) for l in range(n_links)]
+    want, peds, wavs = [], [], []
+    for l in range(n_links):
+        t, p, w = oracles[l].process(units[l], dump=True, cap=1 << 20)
+        want.append(t), peds.append(p), wavs.append(w)
+    got, gp, gw = [], [], []
+    with S.TPGenerator(n_links, 8, algorithm=algorithm, threshold=thr, acc_limit=L, tp_capacity=1 << 21) as g:
+        g.start()
+        for u in range(0, n_units, 8):
+            t, p, w = g.process_host(np.ascontiguousarray(units[:, u:u + 8]), debug=True, cap=1 << 21)
+            got.append(t), gp.append(p), gw.append(w)
+        assert_same_tps(np.concatenate(got), np.concatenate(want), algorithm)
+        assert (np.concatenate(gp, axis=1) == np.stack(peds)).all(), "pedestal dump"
+        assert (np.concatenate(gw, axis=1) == np.stack(wavs)).all(), "waveform dump"
+        fields = ["pedestal", "accum", "prev_was_over", "hit_charge", "hit_tover", "initialized"]
+        if algorithm in ("SimpleThreshold", "AbsRS", "StandardRS"):
+            fields += ["hit_peak_adc", "hit_peak_time"]
+        if algorithm in ("AbsRS", "StandardRS"):
+            fields += ["rs", "pedestal_rs", "accum_rs", "rs_memory_factor"]
+        if algorithm == "FIR":
+            fields += ["quantile25", "quantile75", "accum25", "accum75", "prev_samp"]
+        for l in range(n_links):
+            sg, so = g.dump_state(l), oracles[l].state()
+            for f in fields:
+                assert (sg[f] == so[f]).all(), f"link {l} state field {f}"
+
+
+def test_ragged_and_empty_batches():
+    """n_units per link: 0, 1, full and in between; an all-empty batch is a no-op."""
+    n_links, stride = 6, 10
+    units = S.gen_wibeth_host(S.gen_params(43, 0.5), n_links, 2 * stride)
+    nu1 = np.array([0, 1, 10, 3, 10, 7], dtype=np.uint32)
+    nu2 = np.array([10, 0, 5, 10, 2, 9], dtype=np.uint32)
+    cfg = B.make_config(threshold=20)
+    want = []
+    for l in range(n_links):
+        o = B.Oracle(cfg, link_id=l)
+        want += [o.process(units[l, : nu1[l]]), o.process(units[l, stride: stride + nu2[l]])]
+    with S.TPGenerator(n_links, stride, threshold=20) as g:
+        g.start()
+        a = g.process_host(np.ascontiguousarray(units[:, :stride]), n_units=nu1)
+        e = g.process_host(np.ascontiguousarray(units[:, :stride]), n_units=np.zeros(n_links, dtype=np.uint32))
+        z = g.process_host(np.zeros((n_links, 0, 7200), dtype=np.uint8), units_stride=0)
+        b = g.process_host(np.ascontiguousarray(units[:, stride:]), n_units=nu2)
+        assert e.size == 0 and z.size == 0
+        assert_same_tps(np.concatenate([a, b]), np.concatenate(want), "ragged")
+        assert g.counters()["units_processed"] == int(nu1.sum() + nu2.sum())
+
+
+def test_restart_resets_state():
+    """start() = fresh ChanState + first_hit re-armed (src/wibeth/WIBEthFrameProcessor.cpp:111-154, 67-72)."""
+    units = S.gen_wibeth_host(S.gen_params(44, 0.5), 2, 12)
+    with S.TPGenerator(2, 12, threshold=20) as g:
+        g.start()
+        a = g.process_host(units)
+        g.stop()
+        g.start()
+        b = g.process_host(units)
+        assert_same_tps(a, b, "restart")
+        with pytest.raises(S.SwtpgError):
+            g.stop()
+            g.process_host(units)  # not started
+
+
+def test_streaming_submit_poll_equals_batch():
+    """The drop-in path: per-link submit of single frames, auto-dispatch of full superchunks on the staging ring,
+    poll; then flush of the ragged tail. Equals the batch entry point and the oracle."""
+    n_links, n_units, sc = 7, 23, 4
+    units = S.gen_wibeth_host(S.gen_params(45, 0.5), n_links, n_units)
+    want, _ = B.oracle_process_links(B.make_config(threshold=20), units)
+    got = []
+    with S.TPGenerator(n_links, sc, threshold=20, n_slots=3) as g:
+        g.start()
+        busy = 0
+        for u in range(n_units):
+            for l in range(n_links):
+                while not g.submit(l, units[l, u]):
+                    busy += 1
+                    got.append(g.poll())  # back-pressure: drain completed batches, then retry
+            got.append(g.poll())
+        g.flush()
+        g.sync()
+        for _ in range(8):
+            got.append(g.poll())
+        c = g.counters()
+        assert c["units_processed"] == n_links * n_units
+        assert c["h2d_bytes"] == n_links * n_units * 7200
+    assert_same_tps(np.concatenate(got), want, "streaming")
+
+
+def test_streaming_links_out_of_step():
+    """Links are fed by independent threads: one link may run a whole superchunk ahead of the others."""
+    n_links, n_units, sc = 3, 8, 4
+    units = S.gen_wibeth_host(S.gen_params(46, 0.5), n_links, n_units)
+    want, _ = B.oracle_process_links(B.make_config(threshold=20), units)
+    got = []
+    with S.TPGenerator(n_links, sc, threshold=20, n_slots=2) as g:
+        g.start()
+        for u in range(n_units):  # link 0 first, all of it
+            assert g.submit(0, units[0, u])
+        assert not g.submit(0, units[0, 0])  # third superchunk of link 0: both slots still filling -> BUSY, not blocked
+        for l in (1, 2):
+            for u in range(n_units):
+                assert g.submit(l, units[l, u])
+        g.sync()
+        for _ in range(4):
+            got.append(g.poll())
+        assert g.counters()["submit_busy"] == 1
+    assert_same_tps(np.concatenate(got), want, "out of step")
+
+
+def test_tp_buffer_overflow_is_reported():
+    units = S.gen_wibeth_host(S.gen_params(47, 0.9), 2, 8)
+    with S.TPGenerator(2, 8, threshold=5, tp_capacity=16) as g:
+        g.start()
+        with pytest.raises(S.SwtpgError) as e:
+            g.process_host(units)
+        assert e.value.status == 4  # SWTPG_ERR_OVERFLOW
+        c = g.counters()
+        assert c["tps_emitted"] > 16 and c["tps_dropped_overflow"] == c["tps_emitted"] - 16
+
+
+def test_device_generator_matches_host_generator():
+    import torch
+
+    p = S.gen_params(48, 0.3)
+    n_links, n_units = 9, 5
+    buf = torch.empty(n_links * n_units * 7200, dtype=torch.uint8, device="cuda")
+    S.gen_wibeth_device(p, buf.data_ptr(), n_links, n_units, link0=4, unit0=3)
+    torch.cuda.synchronize()
+    host = S.gen_wibeth_host(p, n_links, n_units, link0=4, unit0=3)
+    assert (buf.cpu().numpy().reshape(host.shape) == host).all()
+    buf2 = torch.empty(3 * 4 * 5664, dtype=torch.uint8, device="cuda")
+    S.gen_wib2_device(p, buf2.data_ptr(), 3, 4, link0=2)
+    torch.cuda.synchronize()
+    host2 = S.gen_wib2_host(p, 3, 4, link0=2)
+    assert (buf2.cpu().numpy().reshape(host2.shape) == host2).all()
+
+
+def test_sharded_equals_unsharded():
+    """Links split over two handles (as over two GPUs) + host merge == one handle over all links."""
+    from fdreadoutlibs_b200 import sharding
+
+    n_links, n_units = 80, 6
+    p = S.gen_params(49, 0.3)
+    with S.TPGenerator(n_links, n_units, threshold=30) as g:
+        g.start()
+        full = S.sort_tps(g.process_host(S.gen_wibeth_host(p, n_links, n_units)))
+    parts = []
+    for rank in range(2):
+        l0, n = sharding.shard_links(n_links, 2, rank)
+        with S.TPGenerator(n, n_units, threshold=30) as g:
+            g.start()
+            parts.append(S.sort_tps(sharding.globalise(g.process_host(S.gen_wibeth_host(p, n, n_units, link0=l0)), l0)))
+    merged = S.merge_sorted(parts)
+    assert merged.size == full.size and (merged == full).all()
+
+
+def test_full_size_one_apa_properties():
+    """BASELINE config 2 at full size — 40 links x 8192 frames (2.36 GB, 1.34 G samples), resident in HBM.
+    Size-independent properties: (1) one 8192-frame batch and 16 batches of 512 give the identical TP multiset;
+    (2) two complete links agree with the CPU oracle tuple for tuple; (3) a second start() reproduces the same list."""
+    import torch
+
+    n_links, n_units = 40, 8192
+    p = S.gen_params(2, 0.02)
+    buf = torch.empty(n_links * n_units * 7200, dtype=torch.uint8, device="cuda")
+    S.gen_wibeth_device(p, buf.data_ptr(), n_links, n_units)
+    torch.cuda.synchronize()
+    with S.TPGenerator(n_links, n_units, threshold=60, tp_capacity=1 << 22) as g:
+        g.start()
+        g.process_device(buf.data_ptr(), n_units)
+        one = g.fetch_tps(cap=1 << 22)
+        g.stop()
+        g.start()
+        g.process_device(buf.data_ptr(), n_units)
+        again = g.fetch_tps(cap=1 << 22)
+    assert one.size > 10000
+    assert_same_tps(one, again, "restart determinism")
+    # batched: link-major layout with stride 8192 -> batches address sub-ranges by offsetting the base pointer
+    parts = []
+    with S.TPGenerator(n_links, n_units, threshold=60, tp_capacity=1 << 22) as g:
+        g.start()
+        view = buf.view(n_links, n_units, 7200)
+        ts = torch.cuda.current_stream().cuda_stream  # run on torch's stream: ordered after the .contiguous() copy
+        for b in range(16):
+            chunk = view[:, b * 512:(b + 1) * 512].contiguous()
+            g.process_device(chunk.data_ptr(), 512, stream=ts)
+            parts.append(g.fetch_tps(cap=1 << 22))
+    assert_same_tps(np.concatenate(parts), one, "batch split")
+    cfg = B.make_config(threshold=60)
+    for l in (0, 39):
+        host = buf.view(n_links, n_units, 7200)[l].cpu().numpy()
+        want = B.Oracle(cfg, link_id=l).process(host, cap=1 << 20)
+        assert_same_tps(one[one["link"] == l], want, f"link {l} vs oracle")

@@ -1,0 +1,73 @@
+"""CPU: differential test of the C restatement against the reference's own headers compiled in this container
+(oracle/_ref/libswtpg_ref.so). Skipped where that library was not built (it needs /root/reference at build time)."""
+import numpy as np
+import pytest
+
+import fdreadoutlibs_b200 as S
+from oracle import binding as B
+from util import assert_same_tps
+
+pytestmark = pytest.mark.skipif(not B.reference_available(), reason="oracle/_ref/libswtpg_ref.so not built")
+
+
+@pytest.mark.parametrize("seed,rate,thr", [(11, 0.02, 60), (12, 0.3, 20), (13, 0.9, 8), (14, 0.9, 0), (15, 0.05, 3)])
+@pytest.mark.parametrize("algo,impl,flav", [(0, B.REF_ETH_SIMPLE_AVX2, 0), (0, B.REF_ETH_SIMPLE_NAIVE, 1), (1, B.REF_ETH_ABSRS_AVX2, 0),
+                                            (2, B.REF_ETH_STDRS_AVX2, 0)])
+def test_wibeth_matches_reference(seed, rate, thr, algo, impl, flav):
+    fr = S.gen_wibeth_host(S.gen_params(seed, rate), 1, 150)[0]
+    cfg = B.make_config(algorithm=algo, threshold=thr, rs_memory_factor=8, rs_scale_factor=5)
+    o = B.Oracle(cfg, flav)
+    r = B.ReferenceWibEth(impl, thr, 10, 8, 5)
+    to, ped, _ = o.process(fr, dump=True)
+    tr, pr = r.process(fr, dump=True)
+    assert_same_tps(to, tr, f"algo {algo} impl {impl}")
+    assert (ped[:, 63, :] == pr[:, 0, :]).all()          # pedestal after every frame
+    assert (o.state()["accum"] == pr[-1, 1, :]).all()
+
+
+@pytest.mark.parametrize("L", [1, 3, 10, 50, 0, -2])
+def test_wibeth_accumulator_limits(L):
+    """AVX2 SimpleThreshold honours the configured limit, including the degenerate L <= 0 cases of SURVEY A5."""
+    fr = S.gen_wibeth_host(S.gen_params(21, 0.2), 1, 60)[0]
+    o = B.Oracle(B.make_config(threshold=25, acc_limit=L))
+    r = B.ReferenceWibEth(B.REF_ETH_SIMPLE_AVX2, 25, L, 8, 5)
+    to, ped, _ = o.process(fr, dump=True)
+    tr, pr = r.process(fr, dump=True)
+    assert_same_tps(to, tr, f"L={L}")
+    assert (ped[:, 63, :] == pr[:, 0, :]).all()
+
+
+def test_wibeth_rs_memory_factor_per_channel():
+    """Collection channels get R = 0 under enable_simple_threshold_on_collection (src/wibeth/WIBEthFrameProcessor.cpp:441-450)."""
+    fr = S.gen_wibeth_host(S.gen_params(22, 0.2), 1, 80)[0]
+    fac = np.where(np.arange(64) % 3 == 0, 0, 8).astype(np.uint16)
+    o = B.Oracle(B.make_config(algorithm=1, threshold=30))
+    o.set_memory_factor(fac)
+    r = B.ReferenceWibEth(B.REF_ETH_ABSRS_AVX2, 30, 10, 8, 5)
+    r.set_memory_factor(fac)
+    assert_same_tps(o.process(fr), r.process(fr), "per-channel R")
+
+
+@pytest.mark.parametrize("seed,rate", [(31, 0.05), (32, 0.6)])
+@pytest.mark.parametrize("algo,impl,flav,thr", [(0, B.REF_WIB2_SIMPLE_AVX2, 0, 100), (0, B.REF_WIB2_SIMPLE_AVX2, 0, 30),
+                                                (3, B.REF_WIB2_FIR_AVX2, 0, 5), (3, B.REF_WIB2_FIR_NAIVE, 1, 5), (3, B.REF_WIB2_FIR_AVX2, 0, 2)])
+def test_wib2_matches_reference(seed, rate, algo, impl, flav, thr):
+    sc = S.gen_wib2_host(S.gen_params(seed, rate), 1, 250)[0]
+    o = B.Oracle(B.make_config(fmt="wib2", algorithm=algo, threshold=thr), flav)
+    r = B.ReferenceWib2(impl, thr)
+    tr, sd = r.process(sc, dump=True)
+    assert_same_tps(o.process(sc), tr, f"wib2 algo {algo} impl {impl} thr {thr}")
+    st = o.state()
+    assert (st["pedestal"] == sd[-1, 0]).all()
+    if algo == 3:
+        assert (st["quantile25"] == sd[-1, 1]).all() and (st["quantile75"] == sd[-1, 2]).all()
+
+
+def test_fir_threshold_64bit_lane_product():
+    """`sigma * multiplier * threshold` is a 4 x int64 multiply; with a large threshold the product of one
+    16-bit lane carries into its neighbour. The oracle must follow the AVX2 code there too."""
+    sc = S.gen_wib2_host(S.gen_params(33, 0.4, noise_q8=40 * 256), 1, 200)[0]  # wide noise -> sigma at its clamp of 102
+    for thr in (11, 40, 700):  # 102*64*11 = 71808 > 65535: lanes overflow into each other
+        o = B.Oracle(B.make_config(fmt="wib2", algorithm=3, threshold=thr))
+        r = B.ReferenceWib2(B.REF_WIB2_FIR_AVX2, thr)
+        assert_same_tps(o.process(sc), r.process(sc), f"thr {thr}")
