@@ -7,12 +7,14 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <memory>
 #include <mutex>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 using namespace swtpg;
@@ -122,24 +124,71 @@ fail(swtpg_handle* h, swtpg_status s, const char* msg)
 }
 
 // ---- kernel launch table ------------------------------------------------------------------------------------------
-constexpr int kWarps = 4, kStages = 3, kChunkTicks = 32;
-constexpr size_t kWibEthSmem = size_t(kWarps) * kStages * (112 * kChunkTicks) + size_t(kWarps) * kStages * 8;
+// Geometry of the WIBEth kernel: WARPS links per CTA, per-warp ring of NSTAGE stages of CHUNK ticks (112 B each).
+template<int WARPS, int NSTAGE, int CHUNK, int MIN_CTAS = 1>
+struct Geo
+{
+  static constexpr int warps = WARPS, stages = NSTAGE, chunk = CHUNK, min_ctas = MIN_CTAS;
+  static constexpr size_t smem = size_t(WARPS) * NSTAGE * (112 * CHUNK) + size_t(WARPS) * NSTAGE * 8 + size_t(WARPS) * HitStage::kCap * 16;
+};
+// Default: 2 stages x 32 ticks (7 KB) + 1.5 KB hit staging per warp, 4 links per CTA. Measured best of the geometries below
+// on B200 (profiles/r01_geometry_sweep.txt): the kernel is ALU-pipe/issue bound, so deeper rings or more resident warps
+// do not help, while 72 registers per thread (unconstrained allocation) do.
+using GeoDefault = Geo<4, 2, 32>;
+
+template<class Algo, bool DUMP, class G>
+cudaError_t
+launch_wibeth_geo(const KernelParams& kp, cudaStream_t s)
+{
+  auto k = wibeth_kernel<Algo, G::warps, G::stages, G::chunk, DUMP, G::min_ctas>;
+  static bool attr_done = false; // per instantiation
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(G::smem));
+    if (e != cudaSuccess)
+      return e;
+    attr_done = true;
+  }
+  const unsigned grid = (kp.n_links + G::warps - 1) / G::warps;
+  k<<<grid, G::warps * 32, G::smem, s>>>(kp);
+  return cudaGetLastError();
+}
+
+// SWTPG_GEO=<n> selects an alternative geometry for the packed fast path (tuning aid; default 0).
+int
+geo_choice()
+{
+  static int g = [] {
+    const char* e = getenv("SWTPG_GEO");
+    return e ? atoi(e) : 0;
+  }();
+  return g;
+}
 
 template<class Algo, bool DUMP>
 cudaError_t
 launch_wibeth(const KernelParams& kp, cudaStream_t s)
 {
-  auto k = wibeth_kernel<Algo, kWarps, kStages, kChunkTicks, DUMP>;
-  static bool attr_done = false; // per instantiation
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWibEthSmem));
-    if (e != cudaSuccess)
-      return e;
-    attr_done = true;
+  if constexpr (std::is_same<Algo, PackedSimpleWibEth>::value && !DUMP) {
+    switch (geo_choice()) {
+      case 1: return launch_wibeth_geo<Algo, DUMP, Geo<4, 3, 32>>(kp, s);
+      case 2: return launch_wibeth_geo<Algo, DUMP, Geo<4, 2, 32>>(kp, s);
+      case 3: return launch_wibeth_geo<Algo, DUMP, Geo<8, 3, 16>>(kp, s);
+      case 4: return launch_wibeth_geo<Algo, DUMP, Geo<4, 4, 16>>(kp, s);
+      case 5: return launch_wibeth_geo<Algo, DUMP, Geo<2, 3, 16>>(kp, s);
+      case 6: return launch_wibeth_geo<Algo, DUMP, Geo<4, 4, 8>>(kp, s);
+      case 7: return launch_wibeth_geo<Algo, DUMP, Geo<4, 3, 16, 10>>(kp, s);
+      case 8: return launch_wibeth_geo<Algo, DUMP, Geo<8, 3, 16, 5>>(kp, s);
+      case 9: return launch_wibeth_geo<Algo, DUMP, Geo<4, 2, 16, 10>>(kp, s);
+      case 10: return launch_wibeth_geo<Algo, DUMP, Geo<4, 2, 32, 5>>(kp, s);
+      case 11: return launch_wibeth_geo<Algo, DUMP, Geo<2, 2, 32, 20>>(kp, s);
+      case 12: return launch_wibeth_geo<Algo, DUMP, Geo<4, 4, 16, 10>>(kp, s);
+      case 13: return launch_wibeth_geo<Algo, DUMP, Geo<1, 2, 32>>(kp, s);
+      case 14: return launch_wibeth_geo<Algo, DUMP, Geo<2, 2, 32>>(kp, s);
+      case 15: return launch_wibeth_geo<Algo, DUMP, Geo<1, 3, 16>>(kp, s);
+      default: break;
+    }
   }
-  const unsigned grid = (kp.n_links + kWarps - 1) / kWarps;
-  k<<<grid, kWarps * 32, kWibEthSmem, s>>>(kp);
-  return cudaGetLastError();
+  return launch_wibeth_geo<Algo, DUMP, GeoDefault>(kp, s);
 }
 
 template<bool DUMP>

@@ -12,6 +12,10 @@
 
 #include "../../include/swtpg.h"
 
+#ifndef SWTPG_EXTRACT_IMAD
+#define SWTPG_EXTRACT_IMAD 0
+#endif
+
 namespace swtpg {
 
 // ---- packed 16x2 primitives ------------------------------------------------------------------------------------
@@ -161,7 +165,14 @@ __device__ __forceinline__ uint32_t
 extract_pair(const uint32_t* row, const PairPos& pp)
 {
   const uint32_t x = __funnelshift_r(row[pp.w0], row[pp.w1], pp.sh); // 28 payload bits + 4 junk bits on top
+#if SWTPG_EXTRACT_IMAD
+  // Same result with one ALU-pipe op fewer (the ALU pipe is the kernel's bottleneck, profiles/r01_*): z = f0 + f1*2^14;
+  // f1 = z >> 14 as a high multiply (IMAD.HI, FMA pipe), then z + f1*(2^16 - 2^14) = f0 + f1*2^16 (IMAD, FMA pipe).
+  const uint32_t z = x & 0x0FFFFFFFu;
+  return __umulhi(z, 1u << 18) * 0xC000u + z;
+#else
   return (x & 0x3FFFu) | ((x << 2) & 0x3FFF0000u);                   // -> u16x2 {adc(2l), adc(2l+1)}
+#endif
 }
 
 // ---- TP emission -----------------------------------------------------------------------------------------------------
@@ -203,5 +214,58 @@ emit_wib2(const TpSink& k, uint64_t ts, int t_end, uint32_t charge, uint32_t tov
   const uint64_t t1 = ts + uint64_t(32ll * int64_t(t_end));
   emit_tp(k, t0, (t0 + t1) / 2, uint32_t(int64_t(tover) * 32), charge, (charge / 20u) & 0xFFFFu, chan, link);
 }
+
+// ---- per-warp hit staging -----------------------------------------------------------------------------------------
+// The tick loop only parks raw hit words in a warp-private shared-memory buffer (one 16-byte store per ended hit, slot
+// from a warp ballot); the 64-bit TP arithmetic, the global cursor atomic (one per flush, not per hit) and the coalesced
+// 32-byte record stores happen in flush(), with all 32 lanes converting one record each.
+struct HitStage
+{
+  static constexpr uint32_t kCap = 96;        // records; flushed whenever fewer than 64 slots (one tick's worst case) remain
+  uint4* buf;                                 // warp-private, kCap entries
+  uint32_t cnt;                               // warp-uniform
+
+  // lo/hi: this lane's low/high channel ended a hit (with non-zero charge) at tick t_end of unit `unit`. Whole warp calls.
+  __device__ __forceinline__ void push(bool lo, bool hi, uint32_t lane, uint32_t unit, uint32_t t_end, uint32_t C, uint32_t T, uint32_t PK,
+                                       uint32_t PT)
+  {
+    const uint32_t mlo = __ballot_sync(0xFFFFFFFFu, lo), mhi = __ballot_sync(0xFFFFFFFFu, hi);
+    const uint32_t below = (1u << lane) - 1u;
+    if (lo)
+      buf[cnt + __popc(mlo & below)] = make_uint4((2u * lane) | (t_end << 8), unit, (C & 0xFFFFu) | (T << 16), (PK & 0xFFFFu) | (PT << 16));
+    if (hi)
+      buf[cnt + __popc(mlo) + __popc(mhi & below)] =
+        make_uint4((2u * lane + 1u) | (t_end << 8), unit, (C >> 16) | (T & 0xFFFF0000u), (PK >> 16) | (PT & 0xFFFF0000u));
+    cnt += __popc(mlo) + __popc(mhi);
+  }
+  __device__ __forceinline__ bool nearly_full() const { return cnt > kCap - 64u; }
+
+  // Converts and writes out everything staged. WIBEth TP fields: src/wibeth/WIBEthFrameProcessor.cpp:520-545.
+  __device__ __forceinline__ void flush_wibeth(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane)
+  {
+    if (cnt == 0)
+      return;
+    __syncwarp();
+    unsigned base = 0;
+    if (lane == 0)
+      base = atomicAdd(k.count, cnt);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    for (uint32_t i = lane; i < cnt; i += 32) {
+      const uint4 r = buf[i];
+      const uint32_t chan = r.x & 0xFFu, t_end = r.x >> 8, charge = r.z & 0xFFFFu, tover = r.z >> 16, peak = r.w & 0xFFFFu, ptime = r.w >> 16;
+      const uint64_t ts = *reinterpret_cast<const unsigned long long*>(link_base + size_t(r.y) * SWTPG_WIBETH_FRAME_BYTES + 8);
+      const uint64_t t0 = ts + uint64_t(32ll * (int64_t(t_end) - int64_t(tover)));
+      const unsigned idx = base + i;
+      if (idx < k.cap) {
+        uint4* d = reinterpret_cast<uint4*>(k.buf + idx);
+        const uint64_t tp = t0 + 32ull * ptime;
+        d[0] = make_uint4(uint32_t(t0), uint32_t(t0 >> 32), uint32_t(tp), uint32_t(tp >> 32));
+        d[1] = make_uint4(32u * tover, charge, peak | (chan << 16), link);
+      }
+    }
+    __syncwarp();
+    cnt = 0;
+  }
+};
 
 } // namespace swtpg

@@ -14,6 +14,10 @@
 
 #include "swtpg_device.cuh"
 
+#ifndef SWTPG_GROUP_UNROLL
+#define SWTPG_GROUP_UNROLL 4
+#endif
+
 namespace swtpg {
 
 // ---- HBM-resident per-group state (struct of arrays: [group][var][lane], u32 = two packed channels) -------------
@@ -66,6 +70,9 @@ struct TickCtx
   uint32_t tick_base; // ticks of this batch before the current unit (FIR ring phase)
   uint32_t link;
   uint32_t chan0;   // frame channel of this lane's low half
+  uint32_t unit;    // index of the current unit inside the batch
+  const uint8_t* link_base;
+  HitStage* stage;  // warp-private hit staging (packed policies)
   const KernelParams* p;
 };
 
@@ -151,6 +158,21 @@ struct ScalarAlgo
       c[h].median = ped;
       c[h].q25 = wrap16(ped - 20);
       c[h].q75 = wrap16(ped + 20);
+    }
+  }
+
+  template<int G, bool DUMP>
+  __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
+                                        uint32_t* wav_out)
+  {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      uint32_t ped, wav;
+      tick(extract_pair(rows + g * (112 / 4), pp), ctx, t0 + g, ctx.chan0 >> 1, ped, wav);
+      if constexpr (DUMP) {
+        ped_out[g] = ped;
+        wav_out[g] = wav;
+      }
     }
   }
 
@@ -337,9 +359,9 @@ struct PackedSimpleWibEth
   __device__ __forceinline__ uint32_t phase_after(uint32_t) const { return 0; }
   __device__ __forceinline__ void seed(uint32_t S) { Mn = neg2(S); }
 
-  __device__ __forceinline__ void tick(uint32_t S, const TickCtx& ctx, int t, uint32_t, uint32_t& ped_out, uint32_t& wav_out)
+  // frugal streaming median (wibeth/tpg/UtilsAVX2.hpp:38-73) + pedestal subtraction (ProcessAVX2.hpp:85): S -> s'
+  __device__ __forceinline__ uint32_t pedestal_step(uint32_t S)
   {
-    // frugal streaming median (wibeth/tpg/UtilsAVX2.hpp:38-73)
     const uint32_t sg = min2(addmax2(S, Mn, 0xFFFFFFFFu), 0x00010001u); // sign(s - m) in {-1,0,1}
     A = add2(A, sg);
     const uint32_t up = addmax2(A, negL2, 0u);        // {0,1}: acc == L+1
@@ -347,31 +369,90 @@ struct PackedSimpleWibEth
     const uint32_t upm = up * 0xFFFFu;                // {0,0xFFFF} (no cross-half carry: halves are 0 or 1)
     Mn = add2(Mn, upm | (dn & 0x00010001u));          // -m -= up ; -m += dn
     A &= ~(upm | dn);                                 // reset where stepped
-    const uint32_t sp = add2(S, Mn);                  // s' = s - m                       (ProcessAVX2.hpp:85)
-    // hit finding
-    const uint32_t over = gt2_mask_nonneg(sp, thr2);  //                                  (:97-98)
-    const uint32_t left = prev & ~over;               //                                  (:102)
+    return add2(S, Mn);                               // s' = s - m
+  }
+  __device__ __forceinline__ uint32_t over_mask(uint32_t sp) const { return gt2_mask_nonneg(sp, thr2); } // (:97-98)
+
+  // Hit bookkeeping of one tick when NO channel of the warp ends a hit in this group of ticks: no emission, no reset.
+  __device__ __forceinline__ void hit_update(uint32_t sp, uint32_t over)
+  {
     C = add2(C, sp & over);                           // wrapping charge                  (:114-118)
     const uint32_t gtp = gt2_mask_nonneg(sp, PK);     // un-gated peak tracking           (:134-136)
     PK = max2(PK, sp);
     PTn = (Tn & gtp) | (PTn & ~gtp);                  // peak_time = tover BEFORE increment
     Tn = addmax2(Tn, over, 0x80018001u);              // tover = adds(tover, 1): -tover >= -32767   (:139-140)
-    if (left) {                                       //                                  (:154-204)
-      const KernelParams& p = *ctx.p;
-      if (left & 0xFFFFu)
-        emit_wibeth(p.sink, ctx.ts, t, C & 0xFFFFu, uint32_t(-lo16s(Tn)) & 0xFFFFu, PK & 0xFFFFu, uint32_t(-lo16s(PTn)) & 0xFFFFu,
-                    ctx.chan0, ctx.link);
-      if (left >> 16)
-        emit_wibeth(p.sink, ctx.ts, t, C >> 16, uint32_t(-hi16s(Tn)) & 0xFFFFu, PK >> 16, uint32_t(-hi16s(PTn)) & 0xFFFFu,
-                    ctx.chan0 + 1, ctx.link);
-      C &= ~left;
-      Tn &= ~left;
-      PK &= ~left;
-      PTn &= ~left;
-    }
+  }
+  // Same, plus hand-off + reset of the lanes whose hit ends at this tick (:154-204). Whole warp calls (ballots inside).
+  __device__ __forceinline__ void hit_update_emit(uint32_t sp, uint32_t over, const TickCtx& ctx, int t)
+  {
+    const uint32_t left = prev & ~over;               //                                  (:102)
+    hit_update(sp, over);
+    // accepted iff hit_charge != 0 (src/wibeth/WIBEthFrameProcessor.cpp:520)
+    ctx.stage->push((left & 0xFFFFu) && (C & 0xFFFFu), (left >> 16) && (C >> 16), ctx.chan0 >> 1, ctx.unit, uint32_t(t), C, neg2(Tn), PK,
+                    neg2(PTn));
+    C &= ~left;
+    Tn &= ~left;
+    PK &= ~left;
+    PTn &= ~left;
     prev = over;
-    ped_out = neg2(Mn);
-    wav_out = sp;
+    if (ctx.stage->nearly_full())
+      ctx.stage->flush_wibeth(ctx.p->sink, ctx.link_base, ctx.link, ctx.chan0 >> 1);
+  }
+
+  // G consecutive ticks, three-tier (results identical in every tier):
+  //  1. The pedestal recurrence runs first for all G ticks. It never reads hit state, so it is one branch-free block
+  //     the scheduler can interleave with the 14-bit extraction of later ticks.
+  //  2. QUIET tier — no channel of the warp is inside a hit and none goes over threshold in the group (by far the most
+  //     common case on physical noise): per channel charge = tover = peak_time = 0 stay 0 and only the un-gated peak
+  //     tracker moves, peak_adc = max(peak_adc, max_g s'_g), because with tover == 0 every peak update writes
+  //     peak_time = 0 again (ProcessAVX2.hpp:134-136). One max tree + one compare per group instead of per tick.
+  //  3. Otherwise per-tick bookkeeping; a second vote selects the emitting variant only when some channel of the warp
+  //     has a falling edge inside the group.
+  template<int G, bool DUMP>
+  __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
+                                        uint32_t* wav_out)
+  {
+    static_assert(G == 4, "max tree below is written for 4 ticks");
+    uint32_t sp[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const uint32_t S = extract_pair(rows + g * (112 / 4), pp);
+      sp[g] = pedestal_step(S);
+      if constexpr (DUMP) {
+        ped_out[g] = neg2(Mn);
+        wav_out[g] = sp[g];
+      }
+    }
+    const uint32_t mx = max2(max2(sp[0], sp[1]), max2(sp[2], sp[3]));
+    const uint32_t busy = over_mask(mx) | prev; // some tick of the group over threshold, or still inside a hit
+    if (__builtin_expect(!__any_sync(0xFFFFFFFFu, busy != 0u), 1)) {
+      PK = max2(PK, mx);
+      return;
+    }
+    uint32_t over[G], edge[G];
+    uint32_t pv = prev;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      over[g] = over_mask(sp[g]);
+      edge[g] = pv & ~over[g];
+      pv = over[g];
+    }
+    if (!__any_sync(0xFFFFFFFFu, (edge[0] | edge[1] | edge[2] | edge[3]) != 0u)) {
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        hit_update(sp[g], over[g]);
+      prev = pv;
+    } else {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (__any_sync(0xFFFFFFFFu, edge[g] != 0u)) {
+          hit_update_emit(sp[g], over[g], ctx, t0 + g);
+        } else {
+          hit_update(sp[g], over[g]);
+          prev = over[g];
+        }
+      }
+    }
   }
 };
 
@@ -380,8 +461,8 @@ struct PackedSimpleWibEth
 // =====================================================================================================================
 constexpr int kWibEthRowBytes = 112;
 
-template<class Algo, int WARPS, int NSTAGE, int CHUNK_TICKS, bool DUMP>
-__global__ void __launch_bounds__(WARPS * 32)
+template<class Algo, int WARPS, int NSTAGE, int CHUNK_TICKS, bool DUMP, int MIN_CTAS = 1>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 wibeth_kernel(const KernelParams p)
 {
   static_assert(64 % CHUNK_TICKS == 0, "chunk must divide the frame");
@@ -399,6 +480,9 @@ wibeth_kernel(const KernelParams p)
 
   uint8_t* stages = smem + size_t(warp) * NSTAGE * kChunkBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(WARPS) * NSTAGE * kChunkBytes) + warp * NSTAGE;
+  HitStage hits;
+  hits.buf = reinterpret_cast<uint4*>(smem + size_t(WARPS) * NSTAGE * (kChunkBytes + 8)) + size_t(warp) * HitStage::kCap;
+  hits.cnt = 0;
   const uint8_t* link_base = p.frames + size_t(link) * p.units_stride * SWTPG_WIBETH_FRAME_BYTES;
   const uint32_t total_chunks = n_units * kChunksPerUnit;
 
@@ -434,12 +518,16 @@ wibeth_kernel(const KernelParams p)
   ctx.chan0 = 2 * lane;
   ctx.ts = 0;
   ctx.tick_base = 0;
+  ctx.unit = 0;
+  ctx.link_base = link_base;
+  ctx.stage = &hits;
 
   for (uint32_t chunk = 0; chunk < total_chunks; ++chunk) {
     const uint32_t stg = chunk % NSTAGE;
     const uint32_t unit = chunk / kChunksPerUnit;
     const int t0 = int(chunk % kChunksPerUnit) * CHUNK_TICKS;
     ctx.tick_base = unit * 64u;
+    ctx.unit = unit;
     if (t0 == 0) // DAQEthHeader word 1 = timestamp (docs/README.md:81); consumed only when a hit ends
       ctx.ts = *reinterpret_cast<const unsigned long long*>(link_base + size_t(unit) * SWTPG_WIBETH_FRAME_BYTES + 8);
     mbar_wait(&bars[stg], (chunk / NSTAGE) & 1u);
@@ -448,17 +536,22 @@ wibeth_kernel(const KernelParams p)
       algo.seed(extract_pair(rows, pp));
       need_seed = false;
     }
-#pragma unroll 4
-    for (int tt = 0; tt < CHUNK_TICKS; ++tt) {
-      const uint32_t S = extract_pair(rows + tt * (kWibEthRowBytes / 4), pp);
-      uint32_t ped, wav;
-      algo.tick(S, ctx, t0 + tt, lane, ped, wav);
+    constexpr int G = 4;
+    static_assert(CHUNK_TICKS % G == 0, "group must divide the chunk");
+    constexpr int kGroupUnroll = SWTPG_GROUP_UNROLL;
+#pragma unroll kGroupUnroll
+    for (int tt = 0; tt < CHUNK_TICKS; tt += G) {
+      uint32_t ped[G], wav[G];
+      algo.template group<G, DUMP>(rows + tt * (kWibEthRowBytes / 4), pp, ctx, t0 + tt, ped, wav);
       if constexpr (DUMP) {
-        const size_t o = ((size_t(link) * p.units_stride + unit) * 64 + size_t(t0 + tt)) * 32 + lane; // u32 = 2 channels
-        if (p.pedestal_out)
-          reinterpret_cast<uint32_t*>(p.pedestal_out)[o] = ped;
-        if (p.waveform_out)
-          reinterpret_cast<uint32_t*>(p.waveform_out)[o] = wav;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const size_t o = ((size_t(link) * p.units_stride + unit) * 64 + size_t(t0 + tt + g)) * 32 + lane; // u32 = 2 channels
+          if (p.pedestal_out)
+            reinterpret_cast<uint32_t*>(p.pedestal_out)[o] = ped[g];
+          if (p.waveform_out)
+            reinterpret_cast<uint32_t*>(p.waveform_out)[o] = wav[g];
+        }
       }
     }
     __syncwarp(); // every lane is done reading this stage
@@ -468,6 +561,7 @@ wibeth_kernel(const KernelParams p)
     }
   }
 
+  hits.flush_wibeth(p.sink, link_base, link, lane);
   algo.store(st, lane);
   if (lane == 0)
     p.group_flags[link] = kFlagInitialized | (algo.phase_after(n_units * 64u) << 8);

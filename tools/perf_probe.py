@@ -1,0 +1,24 @@
+"""Kernel-time probe for the fused WIBEth kernel on HBM-resident frames (tuning aid).
+usage: python tools/perf_probe.py [links] [frames] [algorithm] [threshold]"""
+import sys
+sys.path.insert(0, '.')
+import torch
+import fdreadoutlibs_b200 as S
+n_links = int(sys.argv[1]) if len(sys.argv) > 1 else 5920
+n_units = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+algo = sys.argv[3] if len(sys.argv) > 3 else "SimpleThreshold"
+thr = int(sys.argv[4]) if len(sys.argv) > 4 else 60
+buf = torch.empty(n_links * n_units * 7200, dtype=torch.uint8, device='cuda')
+S.gen_wibeth_device(S.gen_params(2, 0.02), buf.data_ptr(), n_links, n_units)
+torch.cuda.synchronize()
+with S.TPGenerator(n_links, n_units, algorithm=algo, threshold=thr, tp_capacity=1 << 22) as g:
+    g.start()
+    ms = []
+    for i in range(8):
+        g.process_device(buf.data_ptr(), n_units)
+        n = g.fetch_count()
+        ms.append(g.last_kernel_ms())
+    best = min(ms[2:]); avg = sum(ms[2:]) / len(ms[2:])
+    samples = n_links * n_units * 4096
+    print(f"{algo} links={n_links} frames={n_units}: best {best:.3f} ms avg {avg:.3f} ms  {samples/best/1e6:.0f} Gsamples/s  "
+          f"{n_links*n_units*7200/best/1e6:.0f} GB/s ({n_links*n_units*7200/best/1e6/6452.5*100:.1f}% of 6452.5)  tps={n}", flush=True)

@@ -53,6 +53,15 @@ DEFK(k_dp2a,   1, asm volatile("dp2a.lo.s32.s32 %0, %1, %2, %0;" : "+r"(r[i]) : 
 DEFK(k_dp4a,   1, asm volatile("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(r[i]) : "r"(x), "r"(y));)
 DEFK(k_setp_selp, 2, asm volatile("{.reg .pred p; setp.gt.s32 p, %0, %1; selp.b32 %0, %2, %0, p;}" : "+r"(r[i]) : "r"(x), "r"(y));)
 DEFK(k_max32,  1, asm volatile("max.s32 %0, %0, %1;" : "+r"(r[i]) : "r"(r[(i + 1) % CHAINS]));)
+DEFK(k_mulhi,  1, asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(x));)
+DEFK(k_madhi,  1, asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(x), "r"(y));)
+DEFK(k_mix_mulhi_lop, 2, asm volatile("mul.hi.u32 %0, %0, %1; lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[i]) : "r"(x), "r"(y));)
+DEFK(k_mix_mulhi_imad, 2, asm volatile("mul.hi.u32 %0, %0, %1; mad.lo.s32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(x), "r"(y));)
+DEFK(k_mulwide, 1, asm volatile("{.reg .b64 t; mul.wide.u32 t, %0, %1; cvt.u32.u64 %0, t;}" : "+r"(r[i]) : "r"(x));)
+DEFK(k_mulwide_hi, 1, asm volatile("{.reg .b64 t; .reg .b32 lo; mul.wide.u32 t, %0, %1; mov.b64 {lo, %0}, t;}" : "+r"(r[i]) : "r"(x));)
+DEFK(k_shr,    1, asm volatile("shr.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(y));)
+DEFK(k_bfe,    1, asm volatile("bfe.u32 %0, %0, %1, 14;" : "+r"(r[i]) : "r"(y));)
+DEFK(k_mix_lds_lop, 2, { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((r[i] & 0xFFCu))); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[i]) : "r"(v), "r"(y)); })
 DEFK(k_ffma,   1, asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(*(float*)&r[i]) : "f"(1.0001f), "f"(0.5f));)
 // two-op mixes: is issue shared or are there two independent pipes?
 DEFK(k_mix_lop_imad, 2, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96; mad.lo.s32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(x), "r"(y));)
@@ -134,7 +143,7 @@ int main() {
   { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a); for (int i = 0; i < 400; ++i) k_ffma<<<grid, threads>>>(out, 3, 5, cyc); cudaEventRecord(b); CHECK(cudaDeviceSynchronize()); float ms; cudaEventElapsedTime(&ms, a, b); printf("clock warm-up: %.1f ms\n", ms); }
 #define E(n) { #n, n, n##_ops }
   Entry es[] = { E(k_iadd), E(k_lop3), E(k_shf), E(k_prmt), E(k_imad), E(k_shl), E(k_add16x2), E(k_max16x2), E(k_addmax16x2),
-                 E(k_min3_16x2), E(k_hset2), E(k_hfma2), E(k_hadd2), E(k_vimnmx_pred), E(k_dp2a), E(k_dp4a), E(k_setp_selp), E(k_max32), E(k_ffma),
+                 E(k_min3_16x2), E(k_hset2), E(k_hfma2), E(k_hadd2), E(k_vimnmx_pred), E(k_dp2a), E(k_dp4a), E(k_setp_selp), E(k_max32), E(k_mulhi), E(k_madhi), E(k_mix_mulhi_lop), E(k_mix_mulhi_imad), E(k_mulwide), E(k_mulwide_hi), E(k_shr), E(k_bfe), E(k_ffma),
                  E(k_mix_lop_imad), E(k_mix_add16_hfma2), E(k_mix_add16_lop), E(k_mix_max16_imad), E(k_mix_max16_lop),
                  E(k_mix_hset2_lop), E(k_mix_hset2_hfma2), E(k_mix_shf_imad), E(k_mix_iadd_imad), E(k_mix_add16_max16),
                  E(k_lds32), E(k_lds128), E(k_lds_row14) };
