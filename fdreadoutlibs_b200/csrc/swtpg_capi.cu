@@ -129,7 +129,7 @@ template<int WARPS, int NSTAGE, int CHUNK, int MIN_CTAS = 1>
 struct Geo
 {
   static constexpr int warps = WARPS, stages = NSTAGE, chunk = CHUNK, min_ctas = MIN_CTAS;
-  static constexpr size_t smem = size_t(WARPS) * NSTAGE * (112 * CHUNK) + size_t(WARPS) * NSTAGE * 8 + size_t(WARPS) * HitStage::kCap * 16;
+  static constexpr size_t smem = WibEthSmem<WARPS, NSTAGE, CHUNK>::total;
 };
 // Default: 2 stages x 32 ticks (7 KB) + 1.5 KB hit staging per warp, 4 links per CTA. Measured best of the geometries below
 // on B200 (profiles/r01_geometry_sweep.txt): the kernel is ALU-pipe/issue bound, so deeper rings or more resident warps
@@ -141,14 +141,31 @@ cudaError_t
 launch_wibeth_geo(const KernelParams& kp, cudaStream_t s)
 {
   auto k = wibeth_kernel<Algo, G::warps, G::stages, G::chunk, DUMP, G::min_ctas>;
-  static bool attr_done = false; // per instantiation
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(G::smem));
+  // Persistent grid: as many CTAs as the device holds at once (SMs x resident CTAs per SM); warps walk the links.
+  static int resident[64]; // per instantiation and device: CTAs the whole GPU can hold, 0 = not queried yet
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess)
+    return e;
+  if (dev < 0 || dev >= 64)
+    return cudaErrorInvalidDevice;
+  if (resident[dev] == 0) {
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(G::smem));
     if (e != cudaSuccess)
       return e;
-    attr_done = true;
+    int per_sm = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, G::warps * 32, G::smem);
+    if (e != cudaSuccess)
+      return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess)
+      return e;
+    if (const char* cap = getenv("SWTPG_CTAS_PER_SM")) // tuning aid
+      per_sm = std::min(per_sm, std::max(1, atoi(cap)));
+    resident[dev] = std::max(1, per_sm * sms);
   }
-  const unsigned grid = (kp.n_links + G::warps - 1) / G::warps;
+  const unsigned want = (kp.n_links + G::warps - 1) / G::warps;
+  const unsigned grid = std::min<unsigned>(want, unsigned(resident[dev]));
   k<<<grid, G::warps * 32, G::smem, s>>>(kp);
   return cudaGetLastError();
 }
@@ -557,7 +574,7 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
   h->tp_capacity = uint32_t(cap);
   // Packed fast path validity (see PackedSimpleWibEth)
   h->fast_simple = !wib2 && cfg->algorithm == SWTPG_ALGO_SIMPLE_THRESHOLD && cfg->frugal_acc_limit >= 1 &&
-                   cfg->frugal_acc_limit <= 16000 && cfg->threshold <= 32767;
+                   cfg->frugal_acc_limit <= 1000 && cfg->threshold <= 32767;
 
   swtpg_handle* hp = h.get();
   SW_CUDA(hp, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));

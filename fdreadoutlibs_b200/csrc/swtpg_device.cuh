@@ -12,6 +12,9 @@
 
 #include "../../include/swtpg.h"
 
+#ifndef SWTPG_HIT_CAP
+#define SWTPG_HIT_CAP 160
+#endif
 #ifndef SWTPG_EXTRACT_IMAD
 #define SWTPG_EXTRACT_IMAD 0
 #endif
@@ -55,6 +58,11 @@ addmin2(uint32_t a, uint32_t b, uint32_t c)
   return r;
 }
 __device__ __forceinline__ uint32_t
+addclamp2(uint32_t a, uint32_t b, uint32_t hi)
+{ // clamp(a + b, 0, hi) per signed half in ONE instruction (DPX: VIADDMNMX.S16x2.RELU)
+  return __viaddmin_s16x2_relu(a, b, hi);
+}
+__device__ __forceinline__ uint32_t
 neg2(uint32_t a)
 { // per-half two's complement negate
   return add2(~a, 0x00010001u);
@@ -68,6 +76,46 @@ gt2_mask_nonneg(uint32_t a, uint32_t b)
 {
   uint32_t r;
   asm("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+// fp16x2 add on raw bit patterns. On subnormal operands (|pattern & 0x7FFF| <= 0x3FF) this is exact sign-magnitude integer
+// arithmetic executed by the FMA pipe (HADD2/HFMA2, denormals are not flushed).
+__device__ __forceinline__ uint32_t
+hadd2_bits(uint32_t a, uint32_t b)
+{
+  uint32_t r;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+// Per-half fp16 "a == b" as 0xFFFF / 0x0000 (HSET2.EQ); on subnormal patterns an integer equality test (+0 == -0).
+__device__ __forceinline__ uint32_t
+eq2_mask(uint32_t a, uint32_t b)
+{
+  uint32_t r;
+  asm("set.eq.u32.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+// fp16x2 fused multiply-add on raw bit patterns (no flush-to-zero), and its [0, 1]-saturating form.
+__device__ __forceinline__ uint32_t
+hfma2_bits(uint32_t a, uint32_t b, uint32_t c)
+{
+  uint32_t r;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t
+hfma2_sat_bits(uint32_t a, uint32_t b, uint32_t c)
+{
+  uint32_t r;
+  asm("fma.rn.sat.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+// Per half: 1.0 (0x3C00) where |a| != b, else 0.0 — one HSET2.BF with the |.| operand modifier.
+__device__ __forceinline__ uint32_t
+ne2_abs_one(uint32_t a, uint32_t b)
+{
+  uint32_t r;
+  asm("{.reg .b32 t; abs.f16x2 t, %1; set.ne.f16x2.f16x2 %0, t, %2;}" : "=r"(r) : "r"(a), "r"(b));
   return r;
 }
 __device__ __forceinline__ uint32_t
@@ -216,56 +264,68 @@ emit_wib2(const TpSink& k, uint64_t ts, int t_end, uint32_t charge, uint32_t tov
 }
 
 // ---- per-warp hit staging -----------------------------------------------------------------------------------------
-// The tick loop only parks raw hit words in a warp-private shared-memory buffer (one 16-byte store per ended hit, slot
-// from a warp ballot); the 64-bit TP arithmetic, the global cursor atomic (one per flush, not per hit) and the coalesced
+// The tick loop only parks raw hit words in a warp-private shared-memory buffer: a lane whose channel ends a hit takes a
+// slot with a shared-memory atomic (lane-divergent code, executed once per hit, no warp-wide ballots) and writes one
+// 16-byte record. The 64-bit TP arithmetic, the global cursor atomic (one per flush, not per hit) and the coalesced
 // 32-byte record stores happen in flush(), with all 32 lanes converting one record each.
 struct HitStage
 {
-  static constexpr uint32_t kCap = 96;        // records; flushed whenever fewer than 64 slots (one tick's worst case) remain
+  static constexpr uint32_t kCap = SWTPG_HIT_CAP;     // records; a 4-tick group ends at most 2 hits per channel = 128 records,
+  static constexpr uint32_t kFlushAbove = kCap - 128; // so checking once per group with <= kCap-128 parked never overflows
   uint4* buf;                                 // warp-private, kCap entries
-  uint32_t cnt;                               // warp-uniform
+  uint32_t* cnt;                              // warp-private counter in shared memory
 
-  // lo/hi: this lane's low/high channel ended a hit (with non-zero charge) at tick t_end of unit `unit`. Whole warp calls.
-  __device__ __forceinline__ void push(bool lo, bool hi, uint32_t lane, uint32_t unit, uint32_t t_end, uint32_t C, uint32_t T, uint32_t PK,
-                                       uint32_t PT)
+  // One record: a hit of frame channel `chan` ended at tick t_end of unit `unit`. Any subset of lanes may call.
+  __device__ __forceinline__ void push(uint32_t chan, uint32_t unit, uint32_t t_end, uint32_t charge, uint32_t tover, uint32_t peak,
+                                       uint32_t ptime)
   {
-    const uint32_t mlo = __ballot_sync(0xFFFFFFFFu, lo), mhi = __ballot_sync(0xFFFFFFFFu, hi);
-    const uint32_t below = (1u << lane) - 1u;
-    if (lo)
-      buf[cnt + __popc(mlo & below)] = make_uint4((2u * lane) | (t_end << 8), unit, (C & 0xFFFFu) | (T << 16), (PK & 0xFFFFu) | (PT << 16));
-    if (hi)
-      buf[cnt + __popc(mlo) + __popc(mhi & below)] =
-        make_uint4((2u * lane + 1u) | (t_end << 8), unit, (C >> 16) | (T & 0xFFFF0000u), (PK >> 16) | (PT & 0xFFFF0000u));
-    cnt += __popc(mlo) + __popc(mhi);
+    const uint32_t slot = atomicAdd(cnt, 1u);
+    buf[slot] = make_uint4(chan | (t_end << 8), unit, (charge & 0xFFFFu) | (tover << 16), (peak & 0xFFFFu) | (ptime << 16));
   }
-  __device__ __forceinline__ bool nearly_full() const { return cnt > kCap - 64u; }
+  // Warp-uniform (every lane reads the same word); call after __syncwarp().
+  __device__ __forceinline__ bool nearly_full() const { return *reinterpret_cast<volatile uint32_t*>(cnt) > kFlushAbove; }
 
-  // Converts and writes out everything staged. WIBEth TP fields: src/wibeth/WIBEthFrameProcessor.cpp:520-545.
-  __device__ __forceinline__ void flush_wibeth(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane)
-  {
-    if (cnt == 0)
-      return;
-    __syncwarp();
-    unsigned base = 0;
-    if (lane == 0)
-      base = atomicAdd(k.count, cnt);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    for (uint32_t i = lane; i < cnt; i += 32) {
-      const uint4 r = buf[i];
-      const uint32_t chan = r.x & 0xFFu, t_end = r.x >> 8, charge = r.z & 0xFFFFu, tover = r.z >> 16, peak = r.w & 0xFFFFu, ptime = r.w >> 16;
-      const uint64_t ts = *reinterpret_cast<const unsigned long long*>(link_base + size_t(r.y) * SWTPG_WIBETH_FRAME_BYTES + 8);
-      const uint64_t t0 = ts + uint64_t(32ll * (int64_t(t_end) - int64_t(tover)));
-      const unsigned idx = base + i;
-      if (idx < k.cap) {
-        uint4* d = reinterpret_cast<uint4*>(k.buf + idx);
-        const uint64_t tp = t0 + 32ull * ptime;
-        d[0] = make_uint4(uint32_t(t0), uint32_t(t0 >> 32), uint32_t(tp), uint32_t(tp >> 32));
-        d[1] = make_uint4(32u * tover, charge, peak | (chan << 16), link);
-      }
-    }
-    __syncwarp();
-    cnt = 0;
-  }
+  // Converts and writes out everything staged (see flush_hits_wibeth). Whole warp calls, converged.
+  __device__ __forceinline__ void flush_wibeth(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const;
 };
+
+// WIBEth TP fields: src/wibeth/WIBEthFrameProcessor.cpp:520-545. Out of line (cold: once per ~32 hits) and all-by-value, so
+// the caller keeps its state in registers.
+__device__ __noinline__ void
+flush_hits_wibeth(uint4* buf, uint32_t* cnt, swtpg_tp* out, unsigned int* out_count, uint32_t out_cap, const uint8_t* link_base, uint32_t link,
+                  uint32_t lane)
+{
+  __syncwarp();
+  const uint32_t n = *reinterpret_cast<volatile uint32_t*>(cnt);
+  if (n == 0)
+    return;
+  unsigned base = 0;
+  if (lane == 0)
+    base = atomicAdd(out_count, n);
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  for (uint32_t i = lane; i < n; i += 32) {
+    const uint4 r = buf[i];
+    const uint32_t chan = r.x & 0xFFu, t_end = r.x >> 8, charge = r.z & 0xFFFFu, tover = r.z >> 16, peak = r.w & 0xFFFFu, ptime = r.w >> 16;
+    const uint64_t ts = *reinterpret_cast<const unsigned long long*>(link_base + size_t(r.y) * SWTPG_WIBETH_FRAME_BYTES + 8);
+    const uint64_t t0 = ts + uint64_t(32ll * (int64_t(t_end) - int64_t(tover)));
+    const unsigned idx = base + i;
+    if (idx < out_cap) {
+      uint4* d = reinterpret_cast<uint4*>(out + idx);
+      const uint64_t tp = t0 + 32ull * ptime;
+      d[0] = make_uint4(uint32_t(t0), uint32_t(t0 >> 32), uint32_t(tp), uint32_t(tp >> 32));
+      d[1] = make_uint4(32u * tover, charge, peak | (chan << 16), link);
+    }
+  }
+  __syncwarp();
+  if (lane == 0)
+    *reinterpret_cast<volatile uint32_t*>(cnt) = 0u;
+  __syncwarp();
+}
+
+__device__ __forceinline__ void
+HitStage::flush_wibeth(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const
+{
+  flush_hits_wibeth(buf, cnt, k.buf, k.count, k.cap, link_base, link, lane);
+}
 
 } // namespace swtpg

@@ -14,8 +14,13 @@
 
 #include "swtpg_device.cuh"
 
+#include <type_traits>
+
 #ifndef SWTPG_GROUP_UNROLL
 #define SWTPG_GROUP_UNROLL 4
+#endif
+#ifndef SWTPG_FLOAT_ACC
+#define SWTPG_FLOAT_ACC 1
 #endif
 
 namespace swtpg {
@@ -314,100 +319,143 @@ struct ScalarAlgo
 
 // =====================================================================================================================
 // Packed fast path: WIBEth SimpleThreshold (wibeth/tpg/ProcessAVX2.hpp:23-229), two channels per 32-bit register.
-// Validity (checked by the host before selecting it): 1 <= L <= 16000 and 0 <= threshold <= 32767.
+// Validity (checked by the host before selecting it): 1 <= L <= 1000 and 0 <= threshold <= 32767.
 //   * median m stays in [0, 16383] (it only ever steps towards samples, which are 14-bit), so adds_epi16 on it never
-//     saturates, and -m fits a signed half;
+//     saturates;
 //   * with a constant L >= 1 the accumulator is in [-L, L] between ticks, so "acc > L" <=> acc == L+1 and
 //     "-acc > L" <=> acc == -(L+1): both become add+clamp (VIADDMNMX) results in {0,1} / {0,-1};
 //   * pedestal-subtracted samples s' are in [-16383, 16383] and threshold / peak_adc are non-negative, which is the
 //     operand range gt2_mask_nonneg requires.
-// Registers hold NEGATED median / tover / peak_time so that every update is an add (VIADD.16x2 has no subtract form).
+// Register forms (every update is an add: VIADD.16x2 has no subtract form):
+//   Mq  = 1 - median         so that  S + Mq = s' + 1  ("sp1": the pedestal-subtracted sample, biased by one) and
+//                            clamp(S + Mq, 0, 2) = sign(s - m) + 1 is a single VIADDMNMX.S16x2.RELU;
+//   PK1 = peak_adc + 1       compared against sp1;   thr1 = threshold + 1 likewise;
+//   Tn  = -tover, PTn = -peak_time.
 // =====================================================================================================================
 struct PackedSimpleWibEth
 {
-  uint32_t Mn, A, prev, C, Tn, PK, PTn;
-  uint32_t negL2, posL2, thr2;
+  uint32_t Mq, A, prev, C, Tn, PK1, PTn;
+  uint32_t cUp, cDn, thr1;
 
   __device__ __forceinline__ void configure(const KernelParams& p)
   {
     const uint32_t L = uint32_t(p.acc_limit) & 0xFFFFu;
-    posL2 = L | (L << 16);
-    negL2 = neg2(posL2);
+#if SWTPG_FLOAT_ACC
+    const uint32_t up = L + 1u;            // acc == L + 1       (as an fp16 subnormal: value * 2^-24 == bit pattern)
+    const uint32_t dn = 0x8000u | L;       // -L: addend of the "acc == -(L+1)" test (sign-magnitude)
+#else
+    const uint32_t up = (0x10000u - (L + 1u)) & 0xFFFFu; // -(L+1): T - (L+1) = acc - L
+    const uint32_t dn = L - 1u;
+#endif
+    cUp = up | (up << 16);
+    cDn = dn | (dn << 16);
     uint32_t th = p.threshold > 16383u ? 16383u : p.threshold; // s' <= 16383: any larger threshold is never exceeded
-    thr2 = th | (th << 16);
+    th += 1u;
+    thr1 = th | (th << 16);
   }
+#if SWTPG_FLOAT_ACC
+  // Register form of the accumulator: (acc - 1) as the bit pattern of an fp16x2 subnormal (value * 2^-24, sign-magnitude).
+  static __device__ __forceinline__ uint32_t acc_to_reg(uint32_t v)
+  {
+    v = add2(v, 0xFFFFFFFFu);
+    const uint32_t neg = (v & 0x80008000u) >> 15; // 1 per negative half
+    const uint32_t m = neg * 0xFFFFu;             // 0xFFFF per negative half
+    return (add2(v ^ m, neg) & 0x7FFF7FFFu) | (m & 0x80008000u);
+  }
+  static __device__ __forceinline__ uint32_t acc_from_reg(uint32_t v)
+  {
+    const uint32_t neg = (v & 0x80008000u) >> 15;
+    const uint32_t m = neg * 0xFFFFu;
+    return add2(add2((v & 0x7FFF7FFFu) ^ m, neg), 0x00010001u);
+  }
+#else
+  static __device__ __forceinline__ uint32_t acc_to_reg(uint32_t v) { return v; }
+  static __device__ __forceinline__ uint32_t acc_from_reg(uint32_t v) { return v; }
+#endif
   __device__ __forceinline__ void load(const uint32_t* st, uint32_t lane, uint32_t)
   {
-    Mn = neg2(st[SV_MEDIAN * 32 + lane]);
-    A = st[SV_ACCUM * 32 + lane];
+    Mq = add2(~st[SV_MEDIAN * 32 + lane], 0x00020002u); // ~m = -m - 1
+    A = acc_to_reg(st[SV_ACCUM * 32 + lane]);
     prev = st[SV_PREV * 32 + lane];
     C = st[SV_CHARGE * 32 + lane];
     Tn = neg2(st[SV_TOVER * 32 + lane]);
-    PK = st[SV_PEAK_ADC * 32 + lane];
+    PK1 = add2(st[SV_PEAK_ADC * 32 + lane], 0x00010001u);
     PTn = neg2(st[SV_PEAK_TIME * 32 + lane]);
   }
+  __device__ __forceinline__ uint32_t median() const { return add2(~Mq, 0x00020002u); } // 1 - Mq
   __device__ __forceinline__ void store(uint32_t* st, uint32_t lane) const
   {
-    st[SV_MEDIAN * 32 + lane] = neg2(Mn);
-    st[SV_ACCUM * 32 + lane] = A;
+    st[SV_MEDIAN * 32 + lane] = median();
+    st[SV_ACCUM * 32 + lane] = acc_from_reg(A);
     st[SV_PREV * 32 + lane] = prev;
     st[SV_CHARGE * 32 + lane] = C;
     st[SV_TOVER * 32 + lane] = neg2(Tn);
-    st[SV_PEAK_ADC * 32 + lane] = PK;
+    st[SV_PEAK_ADC * 32 + lane] = add2(PK1, 0xFFFFFFFFu);
     st[SV_PEAK_TIME * 32 + lane] = neg2(PTn);
   }
   __device__ __forceinline__ uint32_t phase_after(uint32_t) const { return 0; }
-  __device__ __forceinline__ void seed(uint32_t S) { Mn = neg2(S); }
+  __device__ __forceinline__ void seed(uint32_t S) { Mq = add2(~S, 0x00020002u); }
 
-  // frugal streaming median (wibeth/tpg/UtilsAVX2.hpp:38-73) + pedestal subtraction (ProcessAVX2.hpp:85): S -> s'
+  // frugal streaming median (wibeth/tpg/UtilsAVX2.hpp:38-73) + pedestal subtraction (ProcessAVX2.hpp:85): S -> s' + 1
   __device__ __forceinline__ uint32_t pedestal_step(uint32_t S)
   {
-    const uint32_t sg = min2(addmax2(S, Mn, 0xFFFFFFFFu), 0x00010001u); // sign(s - m) in {-1,0,1}
-    A = add2(A, sg);
-    const uint32_t up = addmax2(A, negL2, 0u);        // {0,1}: acc == L+1
-    const uint32_t dn = addmin2(A, posL2, 0u);        // {0,0xFFFF}: acc == -(L+1)
-    const uint32_t upm = up * 0xFFFFu;                // {0,0xFFFF} (no cross-half carry: halves are 0 or 1)
-    Mn = add2(Mn, upm | (dn & 0x00010001u));          // -m -= up ; -m += dn
-    A &= ~(upm | dn);                                 // reset where stepped
-    return add2(S, Mn);                               // s' = s - m
+    const uint32_t sg1 = addclamp2(S, Mq, 0x00020002u); // sign(s - m) + 1 in {0,1,2}
+#if SWTPG_FLOAT_ACC
+    // The accumulator lives as an fp16x2 subnormal (value * 2^-24: exact integer arithmetic for |v| <= 1023, executed by
+    // the FMA pipe), stored minus one so that adding sign+1 lands on the new accumulator value. The ALU pipe only does the
+    // two compares; the down-step flag, the reset and the re-bias are three fp16 FMAs.
+    const uint32_t T = hadd2_bits(A, sg1);              // acc after this sample, in [-(L+1), L+1]
+    const uint32_t upm = eq2_mask(T, cUp);              // 0xFFFF: acc == L+1
+    const uint32_t dn1 = hfma2_sat_bits(T, 0xBC00BC00u, cDn); // sat(-acc - L) -> bit pattern 1: acc == -(L+1)
+    const uint32_t keep = ne2_abs_one(T, cUp);          // 1.0 unless |acc| == L+1
+    A = hfma2_bits(keep, T, 0x80018001u);               // (stepped ? 0 : acc) - 1
+    Mq = add2(add2(Mq, upm), dn1);                      // m += up - down
+#else
+    const uint32_t T = add2(A, sg1);                    // acc + 1, acc in [-(L+1), L+1]
+    const uint32_t up = addmax2(T, cUp, 0u);            // {0,1}:      acc == L+1
+    const uint32_t dn = addmin2(T, cDn, 0u);            // {0,0xFFFF}: acc == -(L+1)
+    const uint32_t upm = up * 0xFFFFu;                  // {0,0xFFFF} (no cross-half carry: halves are 0 or 1)
+    A = add2(T, 0xFFFFFFFFu) & ~(upm | dn);             // reset where stepped
+    Mq = add2(Mq, upm | (dn & 0x00010001u));            // m += up - down
+#endif
+    return add2(S, Mq);                                 // s' + 1 with the UPDATED median
   }
-  __device__ __forceinline__ uint32_t over_mask(uint32_t sp) const { return gt2_mask_nonneg(sp, thr2); } // (:97-98)
+  __device__ __forceinline__ uint32_t over_mask(uint32_t sp1) const { return gt2_mask_nonneg(sp1, thr1); } // (:97-98)
 
-  // Hit bookkeeping of one tick when NO channel of the warp ends a hit in this group of ticks: no emission, no reset.
-  __device__ __forceinline__ void hit_update(uint32_t sp, uint32_t over)
+  // Hit bookkeeping of one tick (:102-207). Lanes whose channel ends a hit hand it to the warp's staging buffer and
+  // reset (lane-divergent, once per hit); accepted iff hit_charge != 0 (src/wibeth/WIBEthFrameProcessor.cpp:520).
+  __device__ __forceinline__ void hit_update(uint32_t sp1, const TickCtx& ctx, int t)
   {
-    C = add2(C, sp & over);                           // wrapping charge                  (:114-118)
-    const uint32_t gtp = gt2_mask_nonneg(sp, PK);     // un-gated peak tracking           (:134-136)
-    PK = max2(PK, sp);
-    PTn = (Tn & gtp) | (PTn & ~gtp);                  // peak_time = tover BEFORE increment
-    Tn = addmax2(Tn, over, 0x80018001u);              // tover = adds(tover, 1): -tover >= -32767   (:139-140)
-  }
-  // Same, plus hand-off + reset of the lanes whose hit ends at this tick (:154-204). Whole warp calls (ballots inside).
-  __device__ __forceinline__ void hit_update_emit(uint32_t sp, uint32_t over, const TickCtx& ctx, int t)
-  {
-    const uint32_t left = prev & ~over;               //                                  (:102)
-    hit_update(sp, over);
-    // accepted iff hit_charge != 0 (src/wibeth/WIBEthFrameProcessor.cpp:520)
-    ctx.stage->push((left & 0xFFFFu) && (C & 0xFFFFu), (left >> 16) && (C >> 16), ctx.chan0 >> 1, ctx.unit, uint32_t(t), C, neg2(Tn), PK,
-                    neg2(PTn));
-    C &= ~left;
-    Tn &= ~left;
-    PK &= ~left;
-    PTn &= ~left;
+    const uint32_t over = over_mask(sp1);
+    const uint32_t left = prev & ~over;                 //                                  (:102)
+    C = add2(C, add2(sp1, 0xFFFFFFFFu) & over);         // wrapping charge                  (:114-118)
+    const uint32_t gtp = gt2_mask_nonneg(sp1, PK1);     // un-gated peak tracking           (:134-136)
+    PK1 = max2(PK1, sp1);
+    PTn = (Tn & gtp) | (PTn & ~gtp);                    // peak_time = tover BEFORE increment
+    Tn = addmax2(Tn, over, 0x80018001u);                // tover = adds(tover, 1): -tover >= -32767   (:139-140)
     prev = over;
-    if (ctx.stage->nearly_full())
-      ctx.stage->flush_wibeth(ctx.p->sink, ctx.link_base, ctx.link, ctx.chan0 >> 1);
+    if (left != 0u) {                                   //                                  (:154-204)
+      const uint32_t T = neg2(Tn), PK = add2(PK1, 0xFFFFFFFFu), PT = neg2(PTn);
+      if ((left & 0xFFFFu) && (C & 0xFFFFu))
+        ctx.stage->push(ctx.chan0, ctx.unit, uint32_t(t), C & 0xFFFFu, T & 0xFFFFu, PK & 0xFFFFu, PT & 0xFFFFu);
+      if ((left >> 16) && (C >> 16))
+        ctx.stage->push(ctx.chan0 + 1u, ctx.unit, uint32_t(t), C >> 16, T >> 16, PK >> 16, PT >> 16);
+      C &= ~left;
+      Tn &= ~left;
+      PK1 = (PK1 & ~left) | (left & 0x00010001u);
+      PTn &= ~left;
+    }
   }
 
-  // G consecutive ticks, three-tier (results identical in every tier):
+  // G consecutive ticks, two tiers (results identical in both):
   //  1. The pedestal recurrence runs first for all G ticks. It never reads hit state, so it is one branch-free block
   //     the scheduler can interleave with the 14-bit extraction of later ticks.
   //  2. QUIET tier — no channel of the warp is inside a hit and none goes over threshold in the group (by far the most
   //     common case on physical noise): per channel charge = tover = peak_time = 0 stay 0 and only the un-gated peak
   //     tracker moves, peak_adc = max(peak_adc, max_g s'_g), because with tover == 0 every peak update writes
-  //     peak_time = 0 again (ProcessAVX2.hpp:134-136). One max tree + one compare per group instead of per tick.
-  //  3. Otherwise per-tick bookkeeping; a second vote selects the emitting variant only when some channel of the warp
-  //     has a falling edge inside the group.
+  //     peak_time = 0 again (ProcessAVX2.hpp:134-136). Outside a hit peak_adc <= threshold (it restarts from 0 when a
+  //     hit ends and every sample since was not over), so "new peak > threshold" <=> "some sample of the group is over".
+  //  3. Otherwise per-tick bookkeeping for the whole warp.
   template<int G, bool DUMP>
   __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
                                         uint32_t* wav_out)
@@ -419,47 +467,43 @@ struct PackedSimpleWibEth
       const uint32_t S = extract_pair(rows + g * (112 / 4), pp);
       sp[g] = pedestal_step(S);
       if constexpr (DUMP) {
-        ped_out[g] = neg2(Mn);
-        wav_out[g] = sp[g];
+        ped_out[g] = median();
+        wav_out[g] = add2(sp[g], 0xFFFFFFFFu);
       }
     }
-    const uint32_t mx = max2(max2(sp[0], sp[1]), max2(sp[2], sp[3]));
-    const uint32_t busy = over_mask(mx) | prev; // some tick of the group over threshold, or still inside a hit
+    const uint32_t pk = __vimax3_s16x2(__vimax3_s16x2(sp[0], sp[1], sp[2]), sp[3], PK1);
+    const uint32_t busy = over_mask(pk) | prev; // some tick of the group over threshold, or still inside a hit
     if (__builtin_expect(!__any_sync(0xFFFFFFFFu, busy != 0u), 1)) {
-      PK = max2(PK, mx);
+      PK1 = pk;
       return;
     }
-    uint32_t over[G], edge[G];
-    uint32_t pv = prev;
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      over[g] = over_mask(sp[g]);
-      edge[g] = pv & ~over[g];
-      pv = over[g];
-    }
-    if (!__any_sync(0xFFFFFFFFu, (edge[0] | edge[1] | edge[2] | edge[3]) != 0u)) {
-#pragma unroll
-      for (int g = 0; g < G; ++g)
-        hit_update(sp[g], over[g]);
-      prev = pv;
-    } else {
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        if (__any_sync(0xFFFFFFFFu, edge[g] != 0u)) {
-          hit_update_emit(sp[g], over[g], ctx, t0 + g);
-        } else {
-          hit_update(sp[g], over[g]);
-          prev = over[g];
-        }
-      }
-    }
+    for (int g = 0; g < G; ++g)
+      hit_update(sp[g], ctx, t0 + g);
+    __syncwarp();
+    if (ctx.stage->nearly_full())
+      ctx.stage->flush_wibeth(ctx.p->sink, ctx.link_base, ctx.link, ctx.chan0 >> 1);
   }
 };
 
 // =====================================================================================================================
-// WIBEth kernel: one warp per link (64 channels), per-warp TMA ring of CHUNK_TICKS-tick stages.
+// WIBEth kernel: persistent warps, one link (64 channels) at a time per warp, per-warp TMA ring of CHUNK_TICKS-tick stages.
+// Warp w of the grid walks links w, w + W, w + 2W, ... (W = warps in the grid). The ring is refilled by lane 0 from a
+// producer cursor that runs NSTAGE chunks ahead of the consumer ACROSS link boundaries, so a warp never drains its
+// pipeline between links.
 // =====================================================================================================================
 constexpr int kWibEthRowBytes = 112;
+
+// Dynamic shared memory of one CTA: [stages | mbarriers | hit staging | hit counters], each 16-byte aligned.
+template<int WARPS, int NSTAGE, int CHUNK_TICKS>
+struct WibEthSmem
+{
+  static constexpr size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+  static constexpr size_t bars = align16(size_t(WARPS) * NSTAGE * kWibEthRowBytes * CHUNK_TICKS);
+  static constexpr size_t hits = align16(bars + size_t(WARPS) * NSTAGE * 8);
+  static constexpr size_t counts = hits + size_t(WARPS) * HitStage::kCap * 16;
+  static constexpr size_t total = align16(counts + size_t(WARPS) * 4);
+};
 
 template<class Algo, int WARPS, int NSTAGE, int CHUNK_TICKS, bool DUMP, int MIN_CTAS = 1>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
@@ -470,101 +514,131 @@ wibeth_kernel(const KernelParams p)
   constexpr int kChunksPerUnit = 64 / CHUNK_TICKS;
   extern __shared__ __align__(128) uint8_t smem[];
 
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  const uint32_t link = blockIdx.x * WARPS + warp;
-  if (link >= p.n_links)
+  // warp index through a shuffle: tells the compiler it is warp-uniform, so the ring bookkeeping runs on the uniform datapath
+  const uint32_t warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31u;
+  const uint32_t warps_total = gridDim.x * WARPS;
+  const uint32_t first_link = blockIdx.x * WARPS + warp;
+  if (first_link >= p.n_links)
     return; // warps are fully independent: no block-level barrier anywhere below
-  const uint32_t n_units = p.n_units ? p.n_units[link] : p.units_stride;
-  if (n_units == 0)
-    return;
 
+  using L = WibEthSmem<WARPS, NSTAGE, CHUNK_TICKS>;
   uint8_t* stages = smem + size_t(warp) * NSTAGE * kChunkBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(WARPS) * NSTAGE * kChunkBytes) + warp * NSTAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars) + warp * NSTAGE;
   HitStage hits;
-  hits.buf = reinterpret_cast<uint4*>(smem + size_t(WARPS) * NSTAGE * (kChunkBytes + 8)) + size_t(warp) * HitStage::kCap;
-  hits.cnt = 0;
-  const uint8_t* link_base = p.frames + size_t(link) * p.units_stride * SWTPG_WIBETH_FRAME_BYTES;
-  const uint32_t total_chunks = n_units * kChunksPerUnit;
+  hits.buf = reinterpret_cast<uint4*>(smem + L::hits) + size_t(warp) * HitStage::kCap;
+  hits.cnt = reinterpret_cast<uint32_t*>(smem + L::counts) + warp;
 
-  auto issue = [&](uint32_t chunk) { // lane 0 only
-    const uint32_t st = chunk % NSTAGE;
-    const uint8_t* src = link_base + size_t(chunk / kChunksPerUnit) * SWTPG_WIBETH_FRAME_BYTES + 32 + size_t(chunk % kChunksPerUnit) * kChunkBytes;
-    mbar_arrive_expect_tx(&bars[st], kChunkBytes);
-    bulk_g2s(stages + size_t(st) * kChunkBytes, src, kChunkBytes, &bars[st]);
+  auto units_of = [&](uint32_t link) -> uint32_t { return p.n_units ? p.n_units[link] : p.units_stride; };
+  auto base_of = [&](uint32_t link) -> const uint8_t* { return p.frames + size_t(link) * p.units_stride * SWTPG_WIBETH_FRAME_BYTES; };
+
+  // Producer cursor (meaningful in lane 0 only): the next chunk to request is pr_src; pr_left chunks remain in link pr_link.
+  uint32_t pr_link = first_link, pr_left = units_of(first_link) * kChunksPerUnit, pr_in_unit = 0, pr_slot = 0;
+  const uint8_t* pr_src = base_of(first_link) + 32;
+  auto produce = [&]() { // lane 0: request one more chunk, if any link of this warp has one left
+    if (pr_left == 0) {  // link exhausted (or empty): next link of this warp that has data
+      do {
+        pr_link += warps_total;
+        if (pr_link >= p.n_links)
+          return;
+        pr_left = units_of(pr_link) * kChunksPerUnit;
+      } while (pr_left == 0);
+      pr_src = base_of(pr_link) + 32;
+      pr_in_unit = 0;
+    }
+    mbar_arrive_expect_tx(&bars[pr_slot], kChunkBytes);
+    bulk_g2s(stages + pr_slot * kChunkBytes, pr_src, kChunkBytes, &bars[pr_slot]);
+    pr_slot = pr_slot + 1 == NSTAGE ? 0 : pr_slot + 1;
+    pr_src += kChunkBytes;
+    if (++pr_in_unit == kChunksPerUnit) { // skip the 32 header bytes of the next frame
+      pr_in_unit = 0;
+      pr_src += 32;
+    }
+    --pr_left;
   };
 
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s)
       mbar_init(&bars[s], 1);
+    *hits.cnt = 0u;
     fence_mbar_init();
-    const uint32_t pre = total_chunks < uint32_t(NSTAGE) ? total_chunks : uint32_t(NSTAGE);
-    for (uint32_t c = 0; c < pre; ++c)
-      issue(c);
+    for (int s = 0; s < NSTAGE; ++s)
+      produce();
   }
   __syncwarp();
 
-  uint32_t* st = p.state + size_t(link) * kStateWordsPerGroup;
-  const uint32_t flags = p.group_flags[link];
   Algo algo;
   algo.configure(p);
-  algo.load(st, lane, flags);
-  bool need_seed = !(flags & kFlagInitialized);
-
   const PairPos pp = pair_pos(lane);
   TickCtx ctx;
   ctx.p = &p;
-  ctx.link = link;
   ctx.chan0 = 2 * lane;
   ctx.ts = 0;
-  ctx.tick_base = 0;
-  ctx.unit = 0;
-  ctx.link_base = link_base;
   ctx.stage = &hits;
 
-  for (uint32_t chunk = 0; chunk < total_chunks; ++chunk) {
-    const uint32_t stg = chunk % NSTAGE;
-    const uint32_t unit = chunk / kChunksPerUnit;
-    const int t0 = int(chunk % kChunksPerUnit) * CHUNK_TICKS;
-    ctx.tick_base = unit * 64u;
-    ctx.unit = unit;
-    if (t0 == 0) // DAQEthHeader word 1 = timestamp (docs/README.md:81); consumed only when a hit ends
-      ctx.ts = *reinterpret_cast<const unsigned long long*>(link_base + size_t(unit) * SWTPG_WIBETH_FRAME_BYTES + 8);
-    mbar_wait(&bars[stg], (chunk / NSTAGE) & 1u);
-    const uint32_t* rows = reinterpret_cast<const uint32_t*>(stages + size_t(stg) * kChunkBytes);
-    if (need_seed) {
-      algo.seed(extract_pair(rows, pp));
-      need_seed = false;
-    }
-    constexpr int G = 4;
-    static_assert(CHUNK_TICKS % G == 0, "group must divide the chunk");
-    constexpr int kGroupUnroll = SWTPG_GROUP_UNROLL;
+  uint32_t stg = 0, phase = 0; // consumer position in the ring and its mbarrier phase
+  for (uint32_t link = first_link; link < p.n_links; link += warps_total) {
+    const uint32_t n_units = units_of(link);
+    if (n_units == 0)
+      continue;
+    const uint8_t* link_base = base_of(link);
+    uint32_t* st = p.state + size_t(link) * kStateWordsPerGroup;
+    const uint32_t flags = p.group_flags[link];
+    algo.load(st, lane, flags);
+    bool need_seed = !(flags & kFlagInitialized);
+    ctx.link = link;
+    ctx.link_base = link_base;
+
+    for (uint32_t unit = 0; unit < n_units; ++unit) {
+      ctx.tick_base = unit * 64u;
+      ctx.unit = unit;
+      if constexpr (!std::is_same<Algo, PackedSimpleWibEth>::value) {
+        // DAQEthHeader word 1 = timestamp (docs/README.md:81); the packed path reads it when it flushes hits
+        ctx.ts = *reinterpret_cast<const unsigned long long*>(link_base + size_t(unit) * SWTPG_WIBETH_FRAME_BYTES + 8);
+      }
+#pragma unroll 1
+      for (int t0 = 0; t0 < 64; t0 += CHUNK_TICKS) {
+        mbar_wait(&bars[stg], phase);
+        const uint32_t* rows = reinterpret_cast<const uint32_t*>(stages + stg * kChunkBytes);
+        if (need_seed) {
+          algo.seed(extract_pair(rows, pp));
+          need_seed = false;
+        }
+        constexpr int G = 4;
+        static_assert(CHUNK_TICKS % G == 0, "group must divide the chunk");
+        constexpr int kGroupUnroll = SWTPG_GROUP_UNROLL;
 #pragma unroll kGroupUnroll
-    for (int tt = 0; tt < CHUNK_TICKS; tt += G) {
-      uint32_t ped[G], wav[G];
-      algo.template group<G, DUMP>(rows + tt * (kWibEthRowBytes / 4), pp, ctx, t0 + tt, ped, wav);
-      if constexpr (DUMP) {
+        for (int tt = 0; tt < CHUNK_TICKS; tt += G) {
+          uint32_t ped[G], wav[G];
+          algo.template group<G, DUMP>(rows + tt * (kWibEthRowBytes / 4), pp, ctx, t0 + tt, ped, wav);
+          if constexpr (DUMP) {
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const size_t o = ((size_t(link) * p.units_stride + unit) * 64 + size_t(t0 + tt + g)) * 32 + lane; // u32 = 2 channels
-          if (p.pedestal_out)
-            reinterpret_cast<uint32_t*>(p.pedestal_out)[o] = ped[g];
-          if (p.waveform_out)
-            reinterpret_cast<uint32_t*>(p.waveform_out)[o] = wav[g];
+            for (int g = 0; g < G; ++g) {
+              const size_t o = ((size_t(link) * p.units_stride + unit) * 64 + size_t(t0 + tt + g)) * 32 + lane; // u32 = 2 channels
+              if (p.pedestal_out)
+                reinterpret_cast<uint32_t*>(p.pedestal_out)[o] = ped[g];
+              if (p.waveform_out)
+                reinterpret_cast<uint32_t*>(p.waveform_out)[o] = wav[g];
+            }
+          }
+        }
+        // Every lane's loads from this stage have completed (their values were consumed above), so after the warp barrier
+        // the stage can be handed back to the copy engine: a read-then-async-write hand-off needs no proxy fence.
+        __syncwarp();
+        if (lane == 0)
+          produce();
+        if (++stg == NSTAGE) {
+          stg = 0;
+          phase ^= 1u;
         }
       }
     }
-    __syncwarp(); // every lane is done reading this stage
-    if (lane == 0 && chunk + NSTAGE < total_chunks) {
-      fence_proxy_async();
-      issue(chunk + NSTAGE);
-    }
-  }
 
-  hits.flush_wibeth(p.sink, link_base, link, lane);
-  algo.store(st, lane);
-  if (lane == 0)
-    p.group_flags[link] = kFlagInitialized | (algo.phase_after(n_units * 64u) << 8);
+    hits.flush_wibeth(p.sink, link_base, link, lane); // records carry unit indices of THIS link
+    algo.store(st, lane);
+    if (lane == 0)
+      p.group_flags[link] = kFlagInitialized | (algo.phase_after(n_units * 64u) << 8);
+  }
 }
 
 } // namespace swtpg
