@@ -128,14 +128,22 @@ class TPGenerator:
         assert a.size == self.n_links
         return a
 
-    def process_host(self, frames: np.ndarray, n_units=None, units_stride: Optional[int] = None, cap: int = 1 << 20, debug: bool = False):
-        """frames: uint8 [n_links, units_stride, unit_bytes]. Returns TPs (unsorted) and, if debug, (tps, pedestal, waveform)."""
+    def process_host(self, frames: np.ndarray, n_units=None, units_stride: Optional[int] = None, cap: int = 1 << 20, debug: bool = False,
+                     out: Optional[np.ndarray] = None):
+        """frames: uint8 [n_links, units_stride, unit_bytes]. Returns TPs (unsorted) and, if debug, (tps, pedestal, waveform).
+        `out`: optional caller-owned TP_DTYPE array (pinned memory makes the D2H copy asynchronous-capable and avoids a
+        staging copy); the result is then a view of its first n records instead of a fresh array."""
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         if units_stride is None:
             units_stride = frames.size // (self.n_links * self.unit_bytes)
         assert frames.size == self.n_links * units_stride * self.unit_bytes, "frames must be [n_links, units_stride, unit_bytes]"
         nu = self._nunits(n_units)
-        out = np.zeros(cap, dtype=F.TP_DTYPE)
+        if out is None:
+            out = np.empty(cap, dtype=F.TP_DTYPE)
+            own = True
+        else:
+            assert out.dtype == F.TP_DTYPE and out.flags["C_CONTIGUOUS"]
+            cap, own = out.size, False
         n = C.c_size_t(0)
         if debug:
             shape = (self.n_links, units_stride, self.ticks, self.channels)
@@ -147,7 +155,7 @@ class TPGenerator:
             return out[: n.value].copy(), ped, wav
         st = lib.swtpg_process_host(self._h, frames.ctypes.data, _ptr(nu), units_stride, out.ctypes.data, cap, C.byref(n))
         self._check(st)
-        return out[: n.value].copy()
+        return out[: n.value].copy() if own else out[: n.value]
 
     def process_device(self, d_frames_ptr: int, units_stride: int, n_units=None, stream: Optional[int] = None):
         """stream: a cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream) or None for the handle's own

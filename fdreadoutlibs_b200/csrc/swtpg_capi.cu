@@ -131,10 +131,10 @@ struct Geo
   static constexpr int warps = WARPS, stages = NSTAGE, chunk = CHUNK, min_ctas = MIN_CTAS;
   static constexpr size_t smem = WibEthSmem<WARPS, NSTAGE, CHUNK>::total;
 };
-// Default: 2 stages x 32 ticks (7 KB) + 1.5 KB hit staging per warp, 4 links per CTA. Measured best of the geometries below
-// on B200 (profiles/r01_geometry_sweep.txt): the kernel is ALU-pipe/issue bound, so deeper rings or more resident warps
-// do not help, while 72 registers per thread (unconstrained allocation) do.
-using GeoDefault = Geo<4, 2, 32>;
+// Default: one link-warp per CTA with a ring of 2 stages x 32 ticks (7 KB) + 2.5 KB hit staging. Measured best of the
+// geometries below on B200 (profiles/r01_geometry_sweep.txt): the kernel is issue-bound, so deeper rings do not help, and
+// single-warp CTAs let the block scheduler spread the 20 resident warps per SM evenly over the four sub-partitions.
+using GeoDefault = Geo<1, 2, 32>;
 
 template<class Algo, bool DUMP, class G>
 cudaError_t
@@ -164,8 +164,12 @@ launch_wibeth_geo(const KernelParams& kp, cudaStream_t s)
       per_sm = std::min(per_sm, std::max(1, atoi(cap)));
     resident[dev] = std::max(1, per_sm * sms);
   }
-  const unsigned want = (kp.n_links + G::warps - 1) / G::warps;
-  const unsigned grid = std::min<unsigned>(want, unsigned(resident[dev]));
+  // Balanced grid: with R = ceil(links / resident warps) rounds, use just enough warps that every warp walks R links (+-1).
+  // 5920 links on 148 SMs x 5 CTAs x 4 warps -> 2960 warps x 2 links, no partially filled last round.
+  const unsigned max_warps = unsigned(resident[dev]) * G::warps;
+  const unsigned rounds = (kp.n_links + max_warps - 1) / max_warps;
+  const unsigned warps = (kp.n_links + rounds - 1) / rounds;
+  const unsigned grid = std::min<unsigned>((warps + G::warps - 1) / G::warps, unsigned(resident[dev]));
   k<<<grid, G::warps * 32, G::smem, s>>>(kp);
   return cudaGetLastError();
 }
@@ -199,7 +203,7 @@ launch_wibeth(const KernelParams& kp, cudaStream_t s)
       case 10: return launch_wibeth_geo<Algo, DUMP, Geo<4, 2, 32, 5>>(kp, s);
       case 11: return launch_wibeth_geo<Algo, DUMP, Geo<2, 2, 32, 20>>(kp, s);
       case 12: return launch_wibeth_geo<Algo, DUMP, Geo<4, 4, 16, 10>>(kp, s);
-      case 13: return launch_wibeth_geo<Algo, DUMP, Geo<1, 2, 32>>(kp, s);
+      case 13: return launch_wibeth_geo<Algo, DUMP, Geo<4, 2, 32>>(kp, s);
       case 14: return launch_wibeth_geo<Algo, DUMP, Geo<2, 2, 32>>(kp, s);
       case 15: return launch_wibeth_geo<Algo, DUMP, Geo<1, 3, 16>>(kp, s);
       default: break;
@@ -208,10 +212,54 @@ launch_wibeth(const KernelParams& kp, cudaStream_t s)
   return launch_wibeth_geo<Algo, DUMP, GeoDefault>(kp, s);
 }
 
+// WIB2: one 4-warp CTA per link at a time, ring of 4 superchunks; persistent over links.
+template<class Algo, bool DUMP>
+cudaError_t
+launch_wib2(const KernelParams& kp, cudaStream_t s)
+{
+  constexpr int kStages = 4;
+  auto k = wib2_kernel<Algo, kStages, DUMP>;
+  constexpr size_t smem = Wib2Smem<kStages>::total;
+  static int resident[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess)
+    return e;
+  if (dev < 0 || dev >= 64)
+    return cudaErrorInvalidDevice;
+  if (resident[dev] == 0) {
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess)
+      return e;
+    int per_sm = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kWib2Warps * 32, smem);
+    if (e != cudaSuccess)
+      return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess)
+      return e;
+    resident[dev] = std::max(1, per_sm * sms);
+  }
+  const unsigned max_ctas = unsigned(resident[dev]);
+  const unsigned rounds = (kp.n_links + max_ctas - 1) / max_ctas;
+  const unsigned grid = (kp.n_links + rounds - 1) / rounds; // every CTA walks `rounds` links (+-1)
+  k<<<grid, kWib2Warps * 32, smem, s>>>(kp);
+  return cudaGetLastError();
+}
+
 template<bool DUMP>
 cudaError_t
 launch(const swtpg_handle* h, const KernelParams& kp, cudaStream_t s)
 {
+  if (h->cfg.format == SWTPG_FORMAT_WIB2) {
+    switch (h->cfg.algorithm) {
+      case SWTPG_ALGO_SIMPLE_THRESHOLD:
+        return h->fast_simple ? launch_wib2<PackedSimpleWib2, DUMP>(kp, s)
+                              : launch_wib2<ScalarAlgo<SWTPG_ALGO_SIMPLE_THRESHOLD, true>, DUMP>(kp, s);
+      case SWTPG_ALGO_FIR_IQR: return launch_wib2<ScalarAlgo<SWTPG_ALGO_FIR_IQR, true>, DUMP>(kp, s);
+      default: return cudaErrorNotSupported;
+    }
+  }
   if (h->cfg.format == SWTPG_FORMAT_WIBETH) {
     switch (h->cfg.algorithm) {
       case SWTPG_ALGO_SIMPLE_THRESHOLD:
@@ -523,8 +571,10 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
     return fail(nullptr, SWTPG_ERR_UNSUPPORTED, "unknown frame format");
   if (cfg->algorithm < SWTPG_ALGO_SIMPLE_THRESHOLD || cfg->algorithm > SWTPG_ALGO_FIR_IQR)
     return fail(nullptr, SWTPG_ERR_UNSUPPORTED, "unknown tpg_algorithm (reference: TPGAlgorithmInexistent)");
-  if (cfg->format == SWTPG_FORMAT_WIB2)
-    return fail(nullptr, SWTPG_ERR_UNSUPPORTED, "WIB2 kernels are not built yet");
+  if (cfg->format == SWTPG_FORMAT_WIB2 && (cfg->algorithm == SWTPG_ALGO_ABS_RS || cfg->algorithm == SWTPG_ALGO_STANDARD_RS))
+    return fail(nullptr, SWTPG_ERR_UNSUPPORTED, "running-sum algorithms are only built for the WIBEth format");
+  if (cfg->wib2_adc_offset % 4 != 0 || cfg->wib2_adc_offset > SWTPG_WIB2_FRAME_BYTES - 448)
+    return fail(nullptr, SWTPG_ERR_INVALID_ARG, "wib2_adc_offset must be a multiple of 4 and leave room for the 448-byte ADC block");
   if (cfg->tap_exponent > 14)
     return fail(nullptr, SWTPG_ERR_INVALID_ARG, "tap_exponent out of range");
 
@@ -573,8 +623,8 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
   cap = std::min<uint64_t>(cap, std::max<uint64_t>(samples / 2, 1));
   h->tp_capacity = uint32_t(cap);
   // Packed fast path validity (see PackedSimpleWibEth)
-  h->fast_simple = !wib2 && cfg->algorithm == SWTPG_ALGO_SIMPLE_THRESHOLD && cfg->frugal_acc_limit >= 1 &&
-                   cfg->frugal_acc_limit <= 1000 && cfg->threshold <= 32767;
+  h->fast_simple = cfg->algorithm == SWTPG_ALGO_SIMPLE_THRESHOLD && cfg->threshold <= 32767 &&
+                   (wib2 || (cfg->frugal_acc_limit >= 1 && cfg->frugal_acc_limit <= 1000));
 
   swtpg_handle* hp = h.get();
   SW_CUDA(hp, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));

@@ -44,6 +44,13 @@ min2(uint32_t a, uint32_t b)
   return r;
 }
 __device__ __forceinline__ uint32_t
+minu2(uint32_t a, uint32_t b)
+{ // per-half UNSIGNED min
+  uint32_t r;
+  asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t
 addmax2(uint32_t a, uint32_t b, uint32_t c)
 { // max(a + b, c) per signed half: one VIADDMNMX.S16x2
   uint32_t r;
@@ -171,6 +178,11 @@ mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void
+mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void
 bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 { // 16-byte aligned on both sides, bytes % 16 == 0
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
@@ -268,6 +280,21 @@ emit_wib2(const TpSink& k, uint64_t ts, int t_end, uint32_t charge, uint32_t tov
 // slot with a shared-memory atomic (lane-divergent code, executed once per hit, no warp-wide ballots) and writes one
 // 16-byte record. The 64-bit TP arithmetic, the global cursor atomic (one per flush, not per hit) and the coalesced
 // 32-byte record stores happen in flush(), with all 32 lanes converting one record each.
+// SWTPG_PUSH_NOINLINE=1 moves this cold path out of line (the tick loop carries 32 copies of it otherwise).
+#ifndef SWTPG_PUSH_NOINLINE
+#define SWTPG_PUSH_NOINLINE 0
+#endif
+#if SWTPG_PUSH_NOINLINE
+__device__ __noinline__ void
+#else
+__device__ __forceinline__ void
+#endif
+push_hit(uint4* buf, uint32_t* cnt, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3)
+{
+  const uint32_t slot = atomicAdd(cnt, 1u);
+  buf[slot] = make_uint4(w0, w1, w2, w3);
+}
+
 struct HitStage
 {
   static constexpr uint32_t kCap = SWTPG_HIT_CAP;     // records; a 4-tick group ends at most 2 hits per channel = 128 records,
@@ -277,16 +304,16 @@ struct HitStage
 
   // One record: a hit of frame channel `chan` ended at tick t_end of unit `unit`. Any subset of lanes may call.
   __device__ __forceinline__ void push(uint32_t chan, uint32_t unit, uint32_t t_end, uint32_t charge, uint32_t tover, uint32_t peak,
-                                       uint32_t ptime)
+                                       uint32_t ptime) const
   {
-    const uint32_t slot = atomicAdd(cnt, 1u);
-    buf[slot] = make_uint4(chan | (t_end << 8), unit, (charge & 0xFFFFu) | (tover << 16), (peak & 0xFFFFu) | (ptime << 16));
+    push_hit(buf, cnt, chan | (t_end << 8), unit, (charge & 0xFFFFu) | (tover << 16), (peak & 0xFFFFu) | (ptime << 16));
   }
   // Warp-uniform (every lane reads the same word); call after __syncwarp().
   __device__ __forceinline__ bool nearly_full() const { return *reinterpret_cast<volatile uint32_t*>(cnt) > kFlushAbove; }
 
   // Converts and writes out everything staged (see flush_hits_wibeth). Whole warp calls, converged.
   __device__ __forceinline__ void flush_wibeth(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const;
+  __device__ __forceinline__ void flush_wib2(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const;
 };
 
 // WIBEth TP fields: src/wibeth/WIBEthFrameProcessor.cpp:520-545. Out of line (cold: once per ~32 hits) and all-by-value, so
@@ -322,10 +349,51 @@ flush_hits_wibeth(uint4* buf, uint32_t* cnt, swtpg_tp* out, unsigned int* out_co
   __syncwarp();
 }
 
+// WIB2 TP fields: src/wib2/WIB2FrameProcessor.cpp:429-455 (time_peak = middle of the hit, adc_peak = integral / 20).
+// The unit's timestamp is WIB2Frame::get_timestamp of the superchunk's first frame (bytes 4..11, :350-351).
+__device__ __noinline__ void
+flush_hits_wib2(uint4* buf, uint32_t* cnt, swtpg_tp* out, unsigned int* out_count, uint32_t out_cap, const uint8_t* link_base, uint32_t link,
+                uint32_t lane)
+{
+  __syncwarp();
+  const uint32_t n = *reinterpret_cast<volatile uint32_t*>(cnt);
+  if (n == 0)
+    return;
+  unsigned base = 0;
+  if (lane == 0)
+    base = atomicAdd(out_count, n);
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  for (uint32_t i = lane; i < n; i += 32) {
+    const uint4 r = buf[i];
+    const uint32_t chan = r.x & 0xFFu, t_end = r.x >> 8, charge = r.z & 0xFFFFu, tover = r.z >> 16;
+    const uint32_t* hdr = reinterpret_cast<const uint32_t*>(link_base + size_t(r.y) * SWTPG_WIB2_SUPERCHUNK_BYTES + 4);
+    const uint64_t ts = uint64_t(hdr[0]) | (uint64_t(hdr[1]) << 32);
+    const uint64_t t0 = ts + uint64_t(32ll * (int64_t(t_end) - int64_t(tover)));
+    const uint64_t t1 = ts + uint64_t(32ll * int64_t(t_end));
+    const unsigned idx = base + i;
+    if (idx < out_cap) {
+      uint4* d = reinterpret_cast<uint4*>(out + idx);
+      const uint64_t tp = (t0 + t1) / 2;
+      d[0] = make_uint4(uint32_t(t0), uint32_t(t0 >> 32), uint32_t(tp), uint32_t(tp >> 32));
+      d[1] = make_uint4(32u * tover, charge, ((charge / 20u) & 0xFFFFu) | (chan << 16), link);
+    }
+  }
+  __syncwarp();
+  if (lane == 0)
+    *reinterpret_cast<volatile uint32_t*>(cnt) = 0u;
+  __syncwarp();
+}
+
 __device__ __forceinline__ void
 HitStage::flush_wibeth(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const
 {
   flush_hits_wibeth(buf, cnt, k.buf, k.count, k.cap, link_base, link, lane);
+}
+
+__device__ __forceinline__ void
+HitStage::flush_wib2(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const
+{
+  flush_hits_wib2(buf, cnt, k.buf, k.count, k.cap, link_base, link, lane);
 }
 
 } // namespace swtpg

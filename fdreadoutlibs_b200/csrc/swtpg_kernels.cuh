@@ -166,14 +166,14 @@ struct ScalarAlgo
     }
   }
 
-  template<int G, bool DUMP>
+  template<int G, bool DUMP, int ROW_WORDS = 28>
   __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
                                         uint32_t* wav_out)
   {
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       uint32_t ped, wav;
-      tick(extract_pair(rows + g * (112 / 4), pp), ctx, t0 + g, ctx.chan0 >> 1, ped, wav);
+      tick(extract_pair(rows + g * ROW_WORDS, pp), ctx, t0 + g, (ctx.chan0 >> 1) & 31u, ped, wav);
       if constexpr (DUMP) {
         ped_out[g] = ped;
         wav_out[g] = wav;
@@ -456,7 +456,7 @@ struct PackedSimpleWibEth
   //     peak_time = 0 again (ProcessAVX2.hpp:134-136). Outside a hit peak_adc <= threshold (it restarts from 0 when a
   //     hit ends and every sample since was not over), so "new peak > threshold" <=> "some sample of the group is over".
   //  3. Otherwise per-tick bookkeeping for the whole warp.
-  template<int G, bool DUMP>
+  template<int G, bool DUMP, int ROW_WORDS = 28>
   __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
                                         uint32_t* wav_out)
   {
@@ -464,7 +464,7 @@ struct PackedSimpleWibEth
     uint32_t sp[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const uint32_t S = extract_pair(rows + g * (112 / 4), pp);
+      const uint32_t S = extract_pair(rows + g * ROW_WORDS, pp);
       sp[g] = pedestal_step(S);
       if constexpr (DUMP) {
         ped_out[g] = median();
@@ -483,6 +483,71 @@ struct PackedSimpleWibEth
     __syncwarp();
     if (ctx.stage->nearly_full())
       ctx.stage->flush_wibeth(ctx.p->sink, ctx.link_base, ctx.link, ctx.chan0 >> 1);
+  }
+};
+
+// =====================================================================================================================
+// Packed fast path: WIB2 SimpleThreshold (wib2/tpg/ProcessAVX2.hpp:24-200). Same pedestal recurrence with the limit fixed
+// at 10 (:79); charge accumulates (over ? s' : 0) >> tap_exponent with signed saturation (:110-112), no peak tracking,
+// hit block = {chan, t, charge, tover}. Validity: 0 <= threshold <= 32767.
+// =====================================================================================================================
+struct PackedSimpleWib2 : PackedSimpleWibEth
+{
+  uint32_t shift, shmask;
+
+  __device__ __forceinline__ void configure(const KernelParams& p)
+  {
+    KernelParams q = p;
+    q.acc_limit = 10; // wib2/tpg/ProcessAVX2.hpp:79
+    PackedSimpleWibEth::configure(q);
+    shift = uint32_t(p.tap_exponent);
+    const uint32_t m = 0xFFFFu >> shift;
+    shmask = m | (m << 16);
+  }
+  __device__ __forceinline__ void hit_update(uint32_t sp1, const TickCtx& ctx, int t)
+  {
+    const uint32_t over = over_mask(sp1);
+    const uint32_t left = prev & ~over;
+    // over => s' > threshold >= 0: both halves of the masked value are non-negative, so the arithmetic shift is a logical one
+    const uint32_t add = ((add2(sp1, 0xFFFFFFFFu) & over) >> shift) & shmask;
+    C = minu2(add2(C, add), 0x7FFF7FFFu);               // adds_epi16 of two non-negative halves
+    Tn = addmax2(Tn, over, 0x80018001u);                // tover = adds(tover, 1)
+    prev = over;
+    if (left != 0u) {
+      const uint32_t T = neg2(Tn);
+      if ((left & 0xFFFFu) && (C & 0xFFFFu)) // accepted iff hit_charge != 0 (src/wib2/WIB2FrameProcessor.cpp:429)
+        ctx.stage->push(ctx.chan0, ctx.unit, uint32_t(t), C & 0xFFFFu, T & 0xFFFFu, 0u, 0u);
+      if ((left >> 16) && (C >> 16))
+        ctx.stage->push(ctx.chan0 + 1u, ctx.unit, uint32_t(t), C >> 16, T >> 16, 0u, 0u);
+      C &= ~left;
+      Tn &= ~left;
+    }
+  }
+  template<int G, bool DUMP, int ROW_WORDS>
+  __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
+                                        uint32_t* wav_out)
+  {
+    static_assert(G == 4, "max tree below is written for 4 ticks");
+    uint32_t sp[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const uint32_t S = extract_pair(rows + g * ROW_WORDS, pp);
+      sp[g] = pedestal_step(S);
+      if constexpr (DUMP) {
+        ped_out[g] = median();
+        wav_out[g] = add2(sp[g], 0xFFFFFFFFu);
+      }
+    }
+    const uint32_t mx = __vimax3_s16x2(__vimax3_s16x2(sp[0], sp[1], sp[2]), sp[3], sp[3]);
+    const uint32_t busy = over_mask(mx) | prev;
+    if (__builtin_expect(!__any_sync(0xFFFFFFFFu, busy != 0u), 1))
+      return; // nothing but the pedestal moves outside hits
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      hit_update(sp[g], ctx, t0 + g);
+    __syncwarp();
+    if (ctx.stage->nearly_full())
+      ctx.stage->flush_wib2(ctx.p->sink, ctx.link_base, ctx.link, ctx.chan0 >> 1 & 31u);
   }
 };
 
@@ -638,6 +703,160 @@ wibeth_kernel(const KernelParams p)
     algo.store(st, lane);
     if (lane == 0)
       p.group_flags[link] = kFlagInitialized | (algo.phase_after(n_units * 64u) << 8);
+  }
+}
+
+// =====================================================================================================================
+// WIB2 kernel: one CTA of 4 warps per link (256 channels), persistent over links. A superchunk (12 frames x 472 B) is one
+// 5664-byte bulk copy into a CTA-wide ring; warp w consumes channels 64w..64w+63 (112 bytes of every frame's ADC block).
+// full[s]: the copy engine's complete_tx; empty[s]: one arrival per warp. Warp 0 refills, one iteration behind its own
+// consumption so it does not wait for the slowest warp.
+// =====================================================================================================================
+constexpr int kWib2FrameWords = SWTPG_WIB2_FRAME_BYTES / 4; // 118
+constexpr int kWib2Warps = 4;
+
+template<int NSTAGE>
+struct Wib2Smem
+{
+  static constexpr size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+  static constexpr size_t bars = align16(size_t(NSTAGE) * SWTPG_WIB2_SUPERCHUNK_BYTES);
+  static constexpr size_t hits = align16(bars + size_t(NSTAGE) * 16);
+  static constexpr size_t counts = hits + size_t(kWib2Warps) * HitStage::kCap * 16;
+  static constexpr size_t total = align16(counts + size_t(kWib2Warps) * 4);
+};
+
+template<class Algo, int NSTAGE, bool DUMP>
+__global__ void __launch_bounds__(kWib2Warps * 32)
+wib2_kernel(const KernelParams p)
+{
+  constexpr uint32_t kUnit = SWTPG_WIB2_SUPERCHUNK_BYTES;
+  extern __shared__ __align__(128) uint8_t smem[];
+  using L = Wib2Smem<NSTAGE>;
+  const uint32_t warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31u;
+  uint8_t* stages = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::bars);
+  uint64_t* empty = full + NSTAGE;
+  HitStage hits;
+  hits.buf = reinterpret_cast<uint4*>(smem + L::hits) + size_t(warp) * HitStage::kCap;
+  hits.cnt = reinterpret_cast<uint32_t*>(smem + L::counts) + warp;
+
+  auto units_of = [&](uint32_t link) -> uint32_t { return p.n_units ? p.n_units[link] : p.units_stride; };
+  auto base_of = [&](uint32_t link) -> const uint8_t* { return p.frames + size_t(link) * p.units_stride * kUnit; };
+
+  // producer cursor (thread 0 only)
+  uint32_t pr_link = blockIdx.x, pr_left = pr_link < p.n_links ? units_of(pr_link) : 0, pr_slot = 0;
+  const uint8_t* pr_src = pr_link < p.n_links ? base_of(pr_link) : nullptr;
+  auto produce = [&]() -> bool {
+    if (pr_left == 0) {
+      do {
+        pr_link += gridDim.x;
+        if (pr_link >= p.n_links)
+          return false;
+        pr_left = units_of(pr_link);
+      } while (pr_left == 0);
+      pr_src = base_of(pr_link);
+    }
+    mbar_arrive_expect_tx(&full[pr_slot], kUnit);
+    bulk_g2s(stages + pr_slot * kUnit, pr_src, kUnit, &full[pr_slot]);
+    pr_slot = pr_slot + 1 == NSTAGE ? 0 : pr_slot + 1;
+    pr_src += kUnit;
+    --pr_left;
+    return true;
+  };
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kWib2Warps);
+    }
+    fence_mbar_init();
+  }
+  if (lane == 0)
+    *hits.cnt = 0u;
+  __syncthreads(); // the only CTA-wide barrier: mbarriers visible before anyone waits on them
+  if (threadIdx.x == 0 && blockIdx.x < p.n_links)
+    for (int s = 0; s < NSTAGE; ++s)
+      if (!produce())
+        break;
+
+  Algo algo;
+  algo.configure(p);
+  const PairPos pp = pair_pos(lane);
+  TickCtx ctx;
+  ctx.p = &p;
+  ctx.chan0 = 64 * warp + 2 * lane;
+  ctx.ts = 0;
+  ctx.stage = &hits;
+  const uint32_t row0 = p.wib2_adc_offset / 4 + warp * 28; // word offset of this warp's 112 bytes inside a frame
+
+  uint32_t stg = 0, phase = 0;       // consumer ring position / full-barrier phase
+  uint32_t prev_stg = 0, prev_phase = 0;
+  bool have_prev = false;
+  for (uint32_t link = blockIdx.x; link < p.n_links; link += gridDim.x) {
+    const uint32_t n_units = units_of(link);
+    if (n_units == 0)
+      continue;
+    const uint8_t* link_base = base_of(link);
+    const uint32_t group = link * kWib2Warps + warp;
+    uint32_t* st = p.state + size_t(group) * kStateWordsPerGroup;
+    const uint32_t flags = p.group_flags[group];
+    algo.load(st, lane, flags);
+    bool need_seed = !(flags & kFlagInitialized);
+    ctx.link = link;
+    ctx.link_base = link_base;
+
+    for (uint32_t unit = 0; unit < n_units; ++unit) {
+      ctx.tick_base = unit * 12u;
+      ctx.unit = unit;
+      mbar_wait(&full[stg], phase);
+      const uint32_t* sc = reinterpret_cast<const uint32_t*>(stages + stg * kUnit);
+      if constexpr (!std::is_same<Algo, PackedSimpleWib2>::value)
+        ctx.ts = uint64_t(sc[1]) | (uint64_t(sc[2]) << 32); // WIB2Frame::get_timestamp, first frame (:350-351)
+      const uint32_t* rows = sc + row0;
+      if (need_seed) {
+        algo.seed(extract_pair(rows, pp));
+        need_seed = false;
+      }
+      constexpr int G = 4;
+#pragma unroll
+      for (int tt = 0; tt < 12; tt += G) {
+        uint32_t ped[G], wav[G];
+        algo.template group<G, DUMP, kWib2FrameWords>(rows + tt * kWib2FrameWords, pp, ctx, tt, ped, wav);
+        if constexpr (DUMP) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const size_t o = ((size_t(link) * p.units_stride + unit) * 12 + size_t(tt + g)) * 128 + warp * 32 + lane; // u32 = 2 channels
+            if (p.pedestal_out)
+              reinterpret_cast<uint32_t*>(p.pedestal_out)[o] = ped[g];
+            if (p.waveform_out)
+              reinterpret_cast<uint32_t*>(p.waveform_out)[o] = wav[g];
+          }
+        }
+      }
+      __syncwarp(); // this warp is done with the stage
+      if (lane == 0)
+        mbar_arrive(&empty[stg]);
+      if (threadIdx.x == 0) { // refill the stage every warp left one iteration ago
+        if (have_prev) {
+          mbar_wait(&empty[prev_stg], prev_phase);
+          produce();
+        }
+        have_prev = true;
+        prev_stg = stg;
+        prev_phase = phase;
+      }
+      if (++stg == NSTAGE) {
+        stg = 0;
+        phase ^= 1u;
+      }
+    }
+
+    if constexpr (std::is_same<Algo, PackedSimpleWib2>::value)
+      hits.flush_wib2(p.sink, link_base, link, lane);
+    algo.store(st, lane);
+    if (lane == 0)
+      p.group_flags[group] = kFlagInitialized | (algo.phase_after(n_units * 12u) << 8);
   }
 }
 

@@ -12,6 +12,7 @@ from util import assert_same_tps, oracle_config
 pytestmark = pytest.mark.gpu
 
 WIBETH_CASES = sorted(n for n, c in cases.GOLDEN_CASES.items() if c["fmt"] == "wibeth" and c["flavour"] == 0)
+WIB2_CASES = sorted(n for n, c in cases.GOLDEN_CASES.items() if c["fmt"] == "wib2" and c["flavour"] == 0)
 
 
 def run_gpu(case, units, max_units=None, **kw):
@@ -26,7 +27,7 @@ def run_gpu(case, units, max_units=None, **kw):
         return np.concatenate(parts), ped
 
 
-@pytest.mark.parametrize("name", WIBETH_CASES)
+@pytest.mark.parametrize("name", WIBETH_CASES + WIB2_CASES)
 def test_golden_cases(name, golden):
     """Same inputs as tests/golden/make_golden.py fed the reference with: TPs and final pedestals must be identical."""
     case = cases.GOLDEN_CASES[name]
@@ -36,7 +37,7 @@ def test_golden_cases(name, golden):
     assert (ped == golden[name + "__pedestal"]).all()
 
 
-@pytest.mark.parametrize("name", ["noise_simple_thr60", "dense_simple_thr8", "noise_absrs_thr30"])
+@pytest.mark.parametrize("name", ["noise_simple_thr60", "dense_simple_thr8", "noise_absrs_thr30", "wib2_simple_thr100", "wib2_fir_thr5"])
 @pytest.mark.parametrize("max_units", [1, 7, 32])
 def test_batching_does_not_change_results(name, max_units, golden):
     """Superchunk length is an implementation choice: state carried across batches must make it invisible."""
@@ -81,6 +82,74 @@ def test_against_oracle_with_state_and_dumps(algorithm, thr, L):
             sg, so = g.dump_state(l), oracles[l].state()
             for f in fields:
                 assert (sg[f] == so[f]).all(), f"link {l} state field {f}"
+
+
+@pytest.mark.parametrize("algorithm,thr", [("SimpleThreshold", 30), ("SimpleThreshold", 2), ("SimpleThreshold", 40000), ("FIR", 5), ("FIR", 2)])
+def test_wib2_against_oracle_with_state_and_dumps(algorithm, thr):
+    """BASELINE config 5: WIB2 superchunks (256 channels x 12 ticks) through the same fused kernels — SimpleThreshold with the
+    >>6 charge (wib2/tpg/ProcessAVX2.hpp) and the FIR + IQR finder (wib2/tpg/ProcessAVX2FIR.hpp). Ragged batches, several
+    links; TPs, carried state and per-sample pedestal / waveform dumps equal the oracle's."""
+    n_links, n_units, step = 3, 50, 16
+    units = S.gen_wib2_host(S.gen_params(51, 0.5), n_links, n_units)
+    cfg = B.make_config(fmt="wib2", algorithm=S.ALGORITHMS[algorithm], threshold=thr)
+    oracles = [B.Oracle(cfg, link_id=l) for l in range(n_links)]
+    want, peds, wavs = [], [], []
+    for l in range(n_links):
+        t, p, w = oracles[l].process(units[l], dump=True, cap=1 << 20)
+        want.append(t), peds.append(p), wavs.append(w)
+    got, gp, gw = [], [], []
+    with S.TPGenerator(n_links, step, fmt="wib2", algorithm=algorithm, threshold=thr, tp_capacity=1 << 21) as g:
+        g.start()
+        for u in range(0, n_units, step):
+            t, p, w = g.process_host(np.ascontiguousarray(units[:, u:u + step]), debug=True, cap=1 << 21)
+            got.append(t), gp.append(p), gw.append(w)
+        assert_same_tps(np.concatenate(got), np.concatenate(want), f"wib2 {algorithm}")
+        assert (np.concatenate(gp, axis=1) == np.stack(peds)).all(), "pedestal dump"
+        assert (np.concatenate(gw, axis=1) == np.stack(wavs)).all(), "waveform dump"
+        fields = ["pedestal", "accum", "prev_was_over", "hit_charge", "hit_tover", "initialized"]
+        if algorithm == "FIR":
+            fields += ["quantile25", "quantile75", "accum25", "accum75", "prev_samp"]
+        for l in range(n_links):
+            sg, so = g.dump_state(l), oracles[l].state()
+            for f in fields:
+                assert (sg[f] == so[f]).all(), f"link {l} state field {f}"
+
+
+def test_wib2_many_links_ragged_and_streaming():
+    """More links than one wave of CTAs would be on a small grid, ragged unit counts, then the streaming entry points."""
+    n_links, stride = 9, 8
+    units = S.gen_wib2_host(S.gen_params(52, 0.4), n_links, 2 * stride)
+    nu = np.array([8, 0, 3, 8, 1, 8, 5, 8, 2], dtype=np.uint32)
+    cfg = B.make_config(fmt="wib2", threshold=25)
+    want = []
+    for l in range(n_links):
+        o = B.Oracle(cfg, link_id=l)
+        want += [o.process(units[l, : nu[l]]), o.process(units[l, stride:])]
+    with S.TPGenerator(n_links, stride, fmt="wib2", threshold=25) as g:
+        g.start()
+        a = g.process_host(np.ascontiguousarray(units[:, :stride]), n_units=nu)
+        b = g.process_host(np.ascontiguousarray(units[:, stride:]))
+        assert_same_tps(np.concatenate([a, b]), np.concatenate(want), "wib2 ragged")
+    want2, _ = B.oracle_process_links(cfg, units)
+    got = []
+    with S.TPGenerator(n_links, 4, fmt="wib2", threshold=25, n_slots=3) as g:
+        g.start()
+        for u in range(2 * stride):
+            for l in range(n_links):
+                while not g.submit(l, units[l, u]):
+                    got.append(g.poll())
+            got.append(g.poll())
+        g.flush()
+        g.sync()
+        for _ in range(8):
+            got.append(g.poll())
+    assert_same_tps(np.concatenate(got), want2, "wib2 streaming")
+
+
+def test_wib2_running_sum_is_unsupported():
+    with pytest.raises(S.SwtpgError) as e:
+        S.TPGenerator(1, 4, fmt="wib2", algorithm="AbsRS")
+    assert e.value.status == 6  # SWTPG_ERR_UNSUPPORTED (reference: TPGAlgorithmInexistent)
 
 
 def test_ragged_and_empty_batches():
