@@ -1,0 +1,838 @@
+// Implementation of the host-side frame processors (see swtpg_host.hpp). Plain C++17; the only dependency is the C ABI of
+// libswtpg_b200.so. There is no CPU hit finder here: without a device, TpgEngine::start throws.
+#include "swtpg_host.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <thread>
+
+namespace swtpg {
+namespace host {
+
+namespace {
+// Lane l of AVX2 register r holds frame channel 16r + kPerm[l] (unittest/WIBEthFrameExpansion_test.cxx:111,124)
+constexpr int kPerm[16] = { 0, 1, 2, 3, 4, 5, 6, 7, 15, 8, 9, 10, 11, 12, 13, 14 };
+inline uint32_t
+position_to_frame_channel(uint32_t pos)
+{
+  return (pos & ~15u) | uint32_t(kPerm[pos & 15u]);
+}
+void
+check(swtpg_handle* h, swtpg_status s, const char* what)
+{
+  if (s != SWTPG_OK)
+    throw std::runtime_error(std::string(what) + ": " + swtpg_status_string(s) + " — " + (swtpg_last_error(h) ? swtpg_last_error(h) : ""));
+}
+} // namespace
+
+ChannelMap
+make_map(const std::string& name)
+{
+  // detchannelmaps is not part of the reference repository. "linear" numbers the channels of consecutive streams
+  // consecutively inside a (crate, slot); "reversed" additionally flips each group of 64 (exercises a non-monotonic map).
+  if (name == "linear")
+    return [](uint32_t crate, uint32_t slot, uint32_t stream, uint32_t chan) { return ((crate * 8 + slot) * 64 + stream) * 64 + chan; };
+  if (name == "reversed")
+    return [](uint32_t crate, uint32_t slot, uint32_t stream, uint32_t chan) { return ((crate * 8 + slot) * 64 + stream) * 64 + (63 - (chan & 63)) + (chan & ~63u); };
+  throw std::runtime_error("unknown channel map: " + name);
+}
+
+// ---- TpgEngine ------------------------------------------------------------------------------------------------------
+TpgEngine::TpgEngine(int device, swtpg_format format, uint32_t n_links, uint32_t superchunk_units, uint32_t n_slots, uint32_t tp_capacity)
+{
+  m_cfg.struct_size = sizeof m_cfg;
+  m_cfg.device = device;
+  m_cfg.format = format;
+  m_cfg.n_links = n_links;
+  m_cfg.max_units = superchunk_units;
+  m_cfg.n_slots = n_slots;
+  m_cfg.tp_capacity = tp_capacity;
+  m_procs.assign(n_links, nullptr);
+  m_buf.resize(1 << 16);
+}
+
+TpgEngine::~TpgEngine()
+{
+  if (m_h)
+    swtpg_destroy(m_h);
+}
+
+uint32_t
+TpgEngine::attach(FrameProcessorBase* p)
+{
+  std::lock_guard<std::mutex> lk(m_mu);
+  for (uint32_t i = 0; i < m_procs.size(); ++i)
+    if (m_procs[i] == p)
+      return i;
+  for (uint32_t i = 0; i < m_procs.size(); ++i)
+    if (!m_procs[i]) {
+      m_procs[i] = p;
+      return i;
+    }
+  throw std::runtime_error("TpgEngine: more frame processors than links");
+}
+
+void
+TpgEngine::configure(const swtpg_config& a)
+{
+  std::lock_guard<std::mutex> lk(m_mu);
+  if (m_configured) {
+    if (a.algorithm != m_cfg.algorithm || a.threshold != m_cfg.threshold || a.frugal_acc_limit != m_cfg.frugal_acc_limit ||
+        a.rs_memory_factor != m_cfg.rs_memory_factor || a.rs_scale_factor != m_cfg.rs_scale_factor)
+      throw std::runtime_error("TpgEngine: the links of one device must share one TPG configuration");
+    return;
+  }
+  m_cfg.algorithm = a.algorithm;
+  m_cfg.threshold = a.threshold;
+  m_cfg.frugal_acc_limit = a.frugal_acc_limit;
+  m_cfg.rs_memory_factor = a.rs_memory_factor;
+  m_cfg.rs_scale_factor = a.rs_scale_factor;
+  swtpg_handle* h = nullptr;
+  const swtpg_status s = swtpg_create(&m_cfg, &h);
+  if (s != SWTPG_OK)
+    throw std::runtime_error(std::string("swtpg_create: ") + swtpg_status_string(s) + " — " + swtpg_last_error(nullptr));
+  m_h = h;
+  m_configured = true;
+}
+
+void
+TpgEngine::start()
+{
+  std::lock_guard<std::mutex> lk(m_mu);
+  if (!m_h)
+    throw std::runtime_error("TpgEngine::start before conf");
+  if (m_started++ == 0)
+    check(m_h, swtpg_start(m_h), "swtpg_start");
+}
+
+void
+TpgEngine::stop()
+{
+  {
+    std::lock_guard<std::mutex> lk(m_mu);
+    if (m_started == 0 || --m_started != 0)
+      return;
+  }
+  check(m_h, swtpg_flush(m_h), "swtpg_flush");
+  drain(true);
+  check(m_h, swtpg_stop(m_h), "swtpg_stop");
+}
+
+void
+TpgEngine::set_link_memory_factor(uint32_t link, const uint16_t* by_channel, uint32_t n_channels)
+{
+  std::lock_guard<std::mutex> lk(m_mu);
+  if (m_rs_factor.empty())
+    m_rs_factor.assign(size_t(m_cfg.n_links) * n_channels, m_cfg.rs_memory_factor);
+  std::copy(by_channel, by_channel + n_channels, m_rs_factor.begin() + long(size_t(link) * n_channels));
+  check(m_h, swtpg_set_rs_memory_factor(m_h, m_rs_factor.data()), "swtpg_set_rs_memory_factor");
+}
+
+bool
+TpgEngine::submit(uint32_t link, const void* unit, size_t bytes)
+{
+  const swtpg_status s = swtpg_submit(m_h, link, unit, bytes);
+  if (s == SWTPG_ERR_BUSY)
+    return false;
+  check(m_h, s, "swtpg_submit");
+  return true;
+}
+
+void
+TpgEngine::drain(bool wait)
+{
+  std::unique_lock<std::mutex> lk(m_drain_mu, std::defer_lock);
+  if (wait)
+    lk.lock();
+  else if (!lk.try_lock())
+    return; // another link's thread is draining
+  auto deliver = [&]() -> size_t {
+    size_t n = 0;
+    const swtpg_status s = swtpg_poll(m_h, m_buf.data(), m_buf.size(), &n);
+    if (s != SWTPG_OK && s != SWTPG_ERR_OVERFLOW)
+      check(m_h, s, "swtpg_poll");
+    // route by link: records of one link are handed over in one call
+    std::sort(m_buf.begin(), m_buf.begin() + long(n), [](const swtpg_tp& a, const swtpg_tp& b) { return a.link < b.link; });
+    for (size_t i = 0; i < n;) {
+      size_t j = i;
+      while (j < n && m_buf[j].link == m_buf[i].link)
+        ++j;
+      FrameProcessorBase* p = m_buf[i].link < m_procs.size() ? m_procs[m_buf[i].link] : nullptr;
+      if (p)
+        p->process_swtpg_hits(m_buf.data() + i, j - i);
+      i = j;
+    }
+    return n;
+  };
+  if (!wait) {
+    for (int pass = 0; pass < 4 && deliver(); ++pass) {
+    }
+    return;
+  }
+  // stop(): every dispatched batch must be delivered. A poll may only have *started* a batch's TP copy, so alternate
+  // sync and poll until two polls in a row bring nothing.
+  for (int idle = 0; idle < 2;) {
+    check(m_h, swtpg_sync(m_h), "swtpg_sync");
+    idle = deliver() ? 0 : idle + 1;
+  }
+}
+
+// ---- WIBEthFrameProcessor ---------------------------------------------------------------------------------------------
+WIBEthFrameProcessor::WIBEthFrameProcessor(std::unique_ptr<FrameErrorRegistry>& error_registry, std::shared_ptr<TpgEngine> engine)
+  : inherited(error_registry)
+  , m_engine(std::move(engine))
+  , m_wibeth_frame_handler(std::make_unique<WIBEthFrameHandler>())
+{
+}
+
+WIBEthFrameProcessor::~WIBEthFrameProcessor()
+{
+  m_wibeth_frame_handler->reset();
+}
+
+void
+WIBEthFrameProcessor::conf(const RawDataProcessorConf& config)
+{
+  m_tpg_algorithm = config.tpg_algorithm;
+  swtpg_config a{};
+  if (m_tpg_algorithm == "SimpleThreshold") {
+    m_tp_algo = TriggerPrimitive::Algorithm::kSimpleThreshold;
+    a.algorithm = SWTPG_ALGO_SIMPLE_THRESHOLD;
+  } else if (m_tpg_algorithm == "AbsRS") {
+    m_tp_algo = TriggerPrimitive::Algorithm::kAbsRunningSum;
+    a.algorithm = SWTPG_ALGO_ABS_RS;
+    m_enable_simple_threshold_on_collection = config.enable_simple_threshold_on_collection;
+  } else if (m_tpg_algorithm == "StandardRS") {
+    m_tp_algo = TriggerPrimitive::Algorithm::kRunningSum;
+    a.algorithm = SWTPG_ALGO_STANDARD_RS;
+    m_enable_simple_threshold_on_collection = config.enable_simple_threshold_on_collection;
+  } else {
+    throw TPGAlgorithmInexistent(m_tpg_algorithm);
+  }
+  // Running-sum factors travel as integers x10 (src/wibeth/WIBEthFrameProcessor.cpp:199-206)
+  m_tpg_rs_memory_factor = uint16_t(10 * config.tpg_rs_memory_factor);
+  m_tpg_rs_scale_factor = config.tpg_rs_scale_factor != 0 ? uint16_t(10 / config.tpg_rs_scale_factor) : 0;
+  m_tpg_frugal_streaming_accumulator_limit = config.tpg_frugal_streaming_accumulator_limit;
+  m_tp_max_width = config.tp_timeout;
+  m_channel_mask_set.insert(config.tpg_channel_mask.begin(), config.tpg_channel_mask.end());
+  m_tpg_threshold = config.tpg_threshold;
+  m_crate_no = config.crate_id;
+  m_slot_no = config.slot_id;
+  m_stream_id = config.link_id;
+  m_correct_lookup = config.correct_channel_lookup;
+  m_block = config.block_on_backpressure;
+
+  inherited::reset_tasks();
+  inherited::add_preprocess_task([this](frameptr fp) { sequence_check(fp); });
+  inherited::add_preprocess_task([this](frameptr fp) { timestamp_check(fp); });
+  if (config.enable_tpg) {
+    m_tpg_enabled = true;
+    m_channel_map = make_map(config.channel_map_name);
+    a.threshold = m_tpg_threshold;
+    a.frugal_acc_limit = m_tpg_frugal_streaming_accumulator_limit;
+    a.rs_memory_factor = m_tpg_rs_memory_factor;
+    a.rs_scale_factor = m_tpg_rs_scale_factor;
+    m_engine->configure(a);
+    m_wibeth_frame_handler->link = m_engine->attach(this);
+    inherited::add_postprocess_task([this](constframeptr fp) { find_hits(fp, m_wibeth_frame_handler.get()); });
+  }
+  inherited::conf(config);
+}
+
+void
+WIBEthFrameProcessor::start()
+{
+  if (m_tpg_enabled) {
+    m_tps_suppressed_too_long = 0;
+    m_tps_send_failed = 0;
+    m_frames_dropped = 0;
+    m_wibeth_frame_handler->reset(); // = initialize(): fresh per-link resources; the device state is zeroed by swtpg_start
+    m_engine->start();
+  }
+  m_previous_ts = m_current_ts = 0;
+  m_first_ts_missmatch = true;
+  m_ts_error_ctr = 0;
+  m_first_seq_id_mismatch = true;
+  m_seq_id_error_ctr = 0;
+  m_t0 = std::chrono::high_resolution_clock::now();
+  m_new_tps = 0;
+  m_tpg_hits_count = 0;
+  inherited::start();
+}
+
+void
+WIBEthFrameProcessor::stop()
+{
+  inherited::stop();
+  if (m_tpg_enabled) {
+    m_engine->stop(); // flushes the partially filled superchunk and delivers the remaining TPs through process_swtpg_hits
+    m_wibeth_frame_handler->reset();
+  }
+}
+
+void
+WIBEthFrameProcessor::get_info(RawDataProcessorInfo& info)
+{
+  info = RawDataProcessorInfo{};
+  info.num_seq_id_errors = m_seq_id_error_ctr.load();
+  info.min_seq_id_jump = m_seq_id_min_jump.exchange(0);
+  info.max_seq_id_jump = m_seq_id_max_jump.exchange(0);
+  info.num_ts_errors = m_ts_error_ctr.load();
+  const auto now = std::chrono::high_resolution_clock::now();
+  if (m_tpg_enabled) {
+    const uint64_t new_hits = m_tpg_hits_count.exchange(0);
+    const double seconds = std::chrono::duration_cast<std::chrono::microseconds>(now - m_t0).count() / 1000000.;
+    info.rate_tp_hits = seconds > 0 ? new_hits / seconds / 1000. : 0;
+    info.num_tps_sent = m_new_tps.exchange(0);
+    info.num_tps_suppressed_too_long = m_tps_suppressed_too_long.exchange(0);
+    info.num_tps_send_failed = m_tps_send_failed.exchange(0);
+    info.num_frames_dropped_busy = m_frames_dropped.exchange(0);
+    // the ten channels with the most TPs since the last call, then reset (:263-284)
+    std::lock_guard<std::mutex> lk(m_rate_mu);
+    std::vector<std::pair<uint32_t, int>> v(m_tp_channel_rate_map.begin(), m_tp_channel_rate_map.end());
+    std::stable_sort(v.begin(), v.end(), [](const auto& x, const auto& y) { return x.second > y.second; });
+    info.n_top = uint32_t(std::min<size_t>(10, v.size()));
+    for (uint32_t i = 0; i < info.n_top; ++i) {
+      info.top_channels[i] = v[i].first;
+      info.top_channel_tps[i] = uint32_t(v[i].second);
+    }
+    for (auto& el : m_tp_channel_rate_map)
+      el.second = 0;
+  }
+  m_t0 = now;
+}
+
+void
+WIBEthFrameProcessor::sequence_check(frameptr fp)
+{
+  if (inherited::m_emulator_mode) { // emulated data: stamp the geo id and a perfectly incrementing sequence id
+    DAQEthHeader* h = fp->header();
+    h->crate_id = m_crate_no;
+    h->slot_id = m_slot_no;
+    h->stream_id = m_stream_id;
+    h->seq_id = m_previous_seq_id & 0xfff; // one frame per payload: (previous + i) with i = 0, as in the reference (:311)
+  }
+  m_current_seq_id = uint16_t(fp->header()->seq_id);
+  const uint16_t expected_seq_id = uint16_t((m_previous_seq_id + fp->get_num_frames()) & 0xfff);
+  int16_t delta_seq_id = int16_t(m_current_seq_id - expected_seq_id);
+  if (delta_seq_id > 0x800)
+    delta_seq_id -= 0x1000;
+  else if (delta_seq_id < -0x7ff)
+    delta_seq_id += 0x1000;
+  if (delta_seq_id != 0) {
+    ++m_seq_id_error_ctr;
+    m_seq_id_max_jump = std::max(delta_seq_id, m_seq_id_max_jump.load());
+    m_seq_id_min_jump = std::min(delta_seq_id, m_seq_id_min_jump.load());
+    m_error_registry->add_error("SEQUENCE_ID_JUMP", FrameErrorRegistry::ErrorInterval{ expected_seq_id, m_current_seq_id });
+    m_first_seq_id_mismatch = false;
+  }
+  m_previous_seq_id = m_current_seq_id;
+}
+
+void
+WIBEthFrameProcessor::timestamp_check(frameptr fp)
+{
+  const uint64_t frame_tick_difference = DUNEWIBEthTypeAdapter::expected_tick_difference * fp->get_num_frames();
+  if (inherited::m_emulator_mode) {
+    DAQEthHeader* h = fp->header();
+    h->crate_id = m_crate_no;
+    h->slot_id = m_slot_no;
+    h->stream_id = m_stream_id;
+    h->timestamp = m_previous_ts + frame_tick_difference;
+  }
+  m_current_ts = fp->get_first_timestamp();
+  if (m_current_ts - m_previous_ts != frame_tick_difference) {
+    ++m_ts_error_ctr;
+    m_error_registry->add_error("MISSING_FRAMES", FrameErrorRegistry::ErrorInterval{ m_previous_ts + frame_tick_difference, m_current_ts });
+    m_first_ts_missmatch = false;
+  }
+  m_previous_ts = m_current_ts;
+  m_last_processed_daq_ts = m_current_ts;
+}
+
+void
+WIBEthFrameProcessor::find_hits(constframeptr fp, WIBEthFrameHandler* frame_handler)
+{
+  if (!fp)
+    return;
+  const DAQEthHeader* hdr = fp->header();
+  if (frame_handler->first_hit) {
+    // Register-position -> offline channel map, built from the first frame's geo id (RegisterToChannelNumber.cpp:35-122):
+    // position p of the expanded registers holds frame channel 16(p/16) + perm[p%16].
+    for (uint32_t p = 0; p < 64; ++p)
+      frame_handler->register_channel_map[p] = m_channel_map(hdr->crate_id, hdr->slot_id, hdr->stream_id, position_to_frame_channel(p));
+    m_det_id = uint32_t(hdr->det_id);
+    if (hdr->crate_id != m_crate_no || hdr->slot_id != m_slot_no || hdr->stream_id != m_stream_id)
+      m_misconf.push_back({ uint32_t(hdr->crate_id), uint32_t(hdr->slot_id), uint32_t(hdr->stream_id), m_crate_no, m_slot_no, m_stream_id });
+    {
+      std::lock_guard<std::mutex> lk(m_rate_mu);
+      for (uint32_t p = 0; p < 64; ++p) {
+        m_register_channels[p] = frame_handler->register_channel_map[p];
+        m_tp_channel_rate_map[m_register_channels[p]] = 0;
+      }
+    }
+    if (m_enable_simple_threshold_on_collection) { // collection channels run with R = 0, i.e. a plain threshold (:441-450)
+      uint16_t factor[64];
+      for (uint32_t c = 0; c < 64; ++c) {
+        const uint32_t offline = m_channel_map(hdr->crate_id, hdr->slot_id, hdr->stream_id, c);
+        factor[c] = get_plane_from_offline_channel(offline) == 0 ? uint16_t(0) : m_tpg_rs_memory_factor;
+      }
+      m_engine->set_link_memory_factor(frame_handler->link, factor, 64);
+    }
+    frame_handler->first_hit = false;
+  }
+  // The frame is only borrowed for the duration of this call: swtpg_submit copies it into the pinned staging slot.
+  while (!m_engine->submit(frame_handler->link, fp->data, sizeof fp->data)) {
+    if (!m_block) {
+      ++m_frames_dropped;
+      break;
+    }
+    m_engine->drain(false);
+    std::this_thread::yield();
+  }
+  m_engine->drain(false);
+}
+
+void
+WIBEthFrameProcessor::process_swtpg_hits(const swtpg_tp* tps, size_t n)
+{
+  uint64_t nhits = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const swtpg_tp& r = tps[i];
+    // H2: production indexes the POSITION-ordered map with the FRAME channel the AVX2 code emits (:527).
+    uint32_t offline_channel = m_register_channels[r.channel & 63u];
+    if (m_correct_lookup)
+      offline_channel = m_channel_map(m_crate_no, m_slot_no, m_stream_id, r.channel);
+    if (m_channel_mask_set.find(offline_channel) != m_channel_mask_set.end())
+      continue;
+    TriggerPrimitiveTypeAdapter tp;
+    tp.tp.time_start = r.time_start;
+    tp.tp.time_peak = r.time_peak;
+    tp.tp.time_over_threshold = r.time_over_threshold;
+    tp.tp.channel = offline_channel;
+    tp.tp.adc_integral = r.adc_integral;
+    tp.tp.adc_peak = r.adc_peak;
+    tp.tp.detid = uint16_t(m_det_id);
+    tp.tp.type = TriggerPrimitive::Type::kTPC;
+    tp.tp.algorithm = m_tp_algo;
+    tp.tp.version = 1;
+    if (tp.tp.time_over_threshold > m_tp_max_width) {
+      m_tps_suppressed_too_long++; // reference: ers::warning(TPTooLong)
+    } else if (!m_tp_sink || !m_tp_sink(std::move(tp))) {
+      m_tps_send_failed++;         // reference: ers::warning(FailedToSendTP)
+    } else {
+      m_new_tps++;
+      ++nhits;
+    }
+    std::lock_guard<std::mutex> lk(m_rate_mu);
+    m_tp_channel_rate_map[offline_channel]++;
+  }
+  m_tpg_hits_count += nhits;
+}
+
+// ---- WIB2FrameProcessor ---------------------------------------------------------------------------------------------
+WIB2FrameProcessor::WIB2FrameProcessor(std::unique_ptr<FrameErrorRegistry>& error_registry, std::shared_ptr<TpgEngine> engine)
+  : inherited(error_registry)
+  , m_engine(std::move(engine))
+  , m_handler(std::make_unique<WIB2FrameHandler>())
+{
+}
+
+WIB2FrameProcessor::~WIB2FrameProcessor() = default;
+
+void
+WIB2FrameProcessor::conf(const RawDataProcessorConf& config)
+{
+  swtpg_config a{};
+  if (config.tpg_algorithm == "SimpleThreshold")
+    a.algorithm = SWTPG_ALGO_SIMPLE_THRESHOLD;
+  else if (config.tpg_algorithm == "FIR") // the FIR + IQR finder the reference ships in wib2/tpg/ProcessAVX2FIR.hpp
+    a.algorithm = SWTPG_ALGO_FIR_IQR;
+  else // "AbsRS" is selectable in the reference (src/wib2/WIB2FrameProcessor.cpp:388-392); it is not built for WIB2 here
+    throw TPGAlgorithmInexistent(config.tpg_algorithm);
+  m_tp_max_width = config.tp_timeout;
+  m_channel_mask_set.insert(config.tpg_channel_mask.begin(), config.tpg_channel_mask.end());
+  m_crate_no = config.crate_id;
+  m_slot_no = config.slot_id;
+  m_link = config.link_id;
+  m_block = config.block_on_backpressure;
+  inherited::reset_tasks();
+  inherited::add_preprocess_task([this](frameptr fp) { timestamp_check(fp); });
+  if (config.enable_tpg) {
+    m_tpg_enabled = true;
+    m_channel_map = make_map(config.channel_map_name);
+    a.threshold = config.tpg_threshold;
+    a.frugal_acc_limit = 10;
+    m_engine->configure(a);
+    m_handler->link = m_engine->attach(this);
+    inherited::add_postprocess_task([this](constframeptr fp) { find_hits(fp, m_handler.get()); });
+  }
+  inherited::conf(config);
+}
+
+void
+WIB2FrameProcessor::start()
+{
+  if (m_tpg_enabled) {
+    m_tps_suppressed_too_long = 0;
+    m_tps_send_failed = 0;
+    m_frames_dropped = 0;
+    m_handler->reset();
+    m_engine->start();
+  }
+  m_previous_ts = m_current_ts = 0;
+  m_first_ts_missmatch = true;
+  m_ts_error_ctr = 0;
+  m_t0 = std::chrono::high_resolution_clock::now();
+  m_new_tps = 0;
+  m_tpg_hits_count = 0;
+}
+
+void
+WIB2FrameProcessor::stop()
+{
+  if (m_tpg_enabled) {
+    m_engine->stop();
+    m_handler->reset();
+  }
+}
+
+void
+WIB2FrameProcessor::get_info(RawDataProcessorInfo& info)
+{
+  info = RawDataProcessorInfo{};
+  info.num_ts_errors = m_ts_error_ctr.load();
+  const auto now = std::chrono::high_resolution_clock::now();
+  if (m_tpg_enabled) {
+    const uint64_t new_hits = m_tpg_hits_count.exchange(0);
+    const double seconds = std::chrono::duration_cast<std::chrono::microseconds>(now - m_t0).count() / 1000000.;
+    info.rate_tp_hits = seconds > 0 ? new_hits / seconds / 1000. : 0;
+    info.num_tps_sent = m_new_tps.exchange(0);
+    info.num_tps_suppressed_too_long = m_tps_suppressed_too_long.exchange(0);
+    info.num_tps_send_failed = m_tps_send_failed.exchange(0);
+    info.num_frames_dropped_busy = m_frames_dropped.exchange(0);
+    std::lock_guard<std::mutex> lk(m_rate_mu);
+    std::vector<std::pair<uint32_t, int>> v(m_tp_channel_rate_map.begin(), m_tp_channel_rate_map.end());
+    std::stable_sort(v.begin(), v.end(), [](const auto& x, const auto& y) { return x.second > y.second; });
+    info.n_top = uint32_t(std::min<size_t>(10, v.size()));
+    for (uint32_t i = 0; i < info.n_top; ++i) {
+      info.top_channels[i] = v[i].first;
+      info.top_channel_tps[i] = uint32_t(v[i].second);
+    }
+    for (auto& el : m_tp_channel_rate_map)
+      el.second = 0;
+  }
+  m_t0 = now;
+}
+
+void
+WIB2FrameProcessor::timestamp_check(frameptr fp)
+{
+  const uint64_t tick = DUNEWIBSuperChunkTypeAdapter::expected_tick_difference;
+  const uint64_t superchunk_tick_difference = tick * fp->get_num_frames();
+  if (inherited::m_emulator_mode) {
+    uint64_t ts_next = m_previous_ts + superchunk_tick_difference;
+    for (size_t i = 0; i < fp->get_num_frames(); ++i) {
+      WIB2Header* h = fp->header(i);
+      h->crate = m_crate_no;
+      h->slot = m_slot_no;
+      h->link = m_link;
+      fp->set_timestamp(i, ts_next);
+      ts_next += tick;
+    }
+  }
+  m_current_ts = fp->get_first_timestamp();
+  if (m_current_ts - m_previous_ts != superchunk_tick_difference) {
+    ++m_ts_error_ctr;
+    m_error_registry->add_error("MISSING_FRAMES", FrameErrorRegistry::ErrorInterval{ m_previous_ts + superchunk_tick_difference, m_current_ts });
+    m_first_ts_missmatch = false;
+  }
+  m_previous_ts = m_current_ts;
+  m_last_processed_daq_ts = m_current_ts;
+}
+
+void
+WIB2FrameProcessor::find_hits(constframeptr fp, WIB2FrameHandler* frame_handler)
+{
+  if (!fp)
+    return;
+  if (frame_handler->first_hit) {
+    const WIB2Header* h = fp->header();
+    m_det_id = h->detector_id;
+    std::lock_guard<std::mutex> lk(m_rate_mu);
+    // WIB2's AVX2 code emits the register POSITION and the map is position-ordered (src/wib2/WIB2FrameProcessor.cpp:367-368),
+    // so the reported channel is the true offline channel of the frame channel: a frame-channel-ordered map is equivalent.
+    for (uint32_t c = 0; c < 256; ++c) {
+      m_register_channels[c] = m_channel_map(h->crate, h->slot, h->link, c);
+      m_tp_channel_rate_map[m_register_channels[c]] = 0;
+    }
+    frame_handler->first_hit = false;
+  }
+  while (!m_engine->submit(frame_handler->link, fp->data, sizeof fp->data)) {
+    if (!m_block) {
+      ++m_frames_dropped;
+      break;
+    }
+    m_engine->drain(false);
+    std::this_thread::yield();
+  }
+  m_engine->drain(false);
+}
+
+void
+WIB2FrameProcessor::process_swtpg_hits(const swtpg_tp* tps, size_t n)
+{
+  uint64_t nhits = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const swtpg_tp& r = tps[i];
+    const uint32_t offline_channel = m_register_channels[r.channel & 255u];
+    if (m_channel_mask_set.find(offline_channel) != m_channel_mask_set.end())
+      continue;
+    TriggerPrimitiveTypeAdapter tp;
+    tp.tp.time_start = r.time_start;
+    tp.tp.time_peak = r.time_peak;
+    tp.tp.time_over_threshold = r.time_over_threshold;
+    tp.tp.channel = offline_channel;
+    tp.tp.adc_integral = r.adc_integral;
+    tp.tp.adc_peak = r.adc_peak;
+    tp.tp.detid = uint16_t(m_det_id);
+    tp.tp.type = TriggerPrimitive::Type::kTPC;
+    tp.tp.algorithm = TriggerPrimitive::Algorithm::kUnknown; // never assigned in the reference (wib2/WIB2FrameProcessor.hpp:137)
+    tp.tp.version = 1;
+    if (tp.tp.time_over_threshold > m_tp_max_width)
+      m_tps_suppressed_too_long++;
+    else if (!m_tp_sink || !m_tp_sink(std::move(tp)))
+      m_tps_send_failed++;
+    m_new_tps++; // counted regardless of the outcome, as the reference does (:469-470)
+    ++nhits;
+    std::lock_guard<std::mutex> lk(m_rate_mu);
+    m_tp_channel_rate_map[offline_channel]++;
+  }
+  m_tpg_hits_count += nhits;
+}
+
+} // namespace host
+} // namespace swtpg
+
+// =====================================================================================================================
+// C test harness (tests/test_host_shim.py drives the classes above through ctypes): one engine + n frame processors with
+// in-memory "tp_out" queues. Not part of the drop-in surface.
+// =====================================================================================================================
+using namespace swtpg::host;
+
+struct swtpg_host_conf
+{
+  int32_t device, format; // swtpg_format
+  uint32_t n_links, superchunk_units;
+  char tpg_algorithm[32];
+  float tpg_rs_memory_factor, tpg_rs_scale_factor;
+  uint16_t tpg_threshold;
+  int16_t tpg_frugal_streaming_accumulator_limit;
+  uint64_t tp_timeout;
+  uint32_t channel_mask[16];
+  uint32_t n_mask;
+  uint16_t crate_id, slot_id, first_link_id;
+  uint8_t enable_tpg, emulator_mode, correct_channel_lookup, reversed_map, enable_simple_threshold_on_collection, block_on_backpressure, pad[2];
+  uint32_t sink_capacity; // per link; try_send fails beyond it (0 = unbounded)
+};
+
+struct swtpg_host_tp
+{
+  uint64_t time_start, time_peak, time_over_threshold;
+  uint32_t channel, adc_integral;
+  uint16_t adc_peak, detid;
+  uint32_t type, algorithm;
+  uint16_t version, flag;
+};
+
+struct swtpg_host
+{
+  std::shared_ptr<TpgEngine> engine;
+  std::vector<std::unique_ptr<FrameErrorRegistry>> regs;
+  std::vector<std::unique_ptr<WIBEthFrameProcessor>> eth;
+  std::vector<std::unique_ptr<WIB2FrameProcessor>> wib2;
+  std::vector<std::vector<TriggerPrimitiveTypeAdapter>> queues;
+  std::vector<std::unique_ptr<std::mutex>> qmu;
+  uint32_t sink_capacity = 0;
+  std::string error;
+};
+
+static thread_local std::string g_host_error;
+
+extern "C" {
+
+const char*
+swtpg_host_last_error(void)
+{
+  return g_host_error.c_str();
+}
+
+swtpg_host*
+swtpg_host_create(const swtpg_host_conf* c)
+{
+  try {
+    auto h = std::make_unique<swtpg_host>();
+    h->engine = std::make_shared<TpgEngine>(c->device, swtpg_format(c->format), c->n_links, c->superchunk_units);
+    h->sink_capacity = c->sink_capacity;
+    h->queues.resize(c->n_links);
+    h->regs.resize(c->n_links); // the processors keep REFERENCES to these unique_ptrs (as the reference's model does): no reallocation later
+    for (uint32_t l = 0; l < c->n_links; ++l) {
+      h->qmu.push_back(std::make_unique<std::mutex>());
+      h->regs[l] = std::make_unique<FrameErrorRegistry>();
+      RawDataProcessorConf rc;
+      rc.tpg_algorithm = c->tpg_algorithm;
+      rc.tpg_threshold = c->tpg_threshold;
+      rc.tpg_rs_memory_factor = c->tpg_rs_memory_factor;
+      rc.tpg_rs_scale_factor = c->tpg_rs_scale_factor;
+      rc.tpg_frugal_streaming_accumulator_limit = c->tpg_frugal_streaming_accumulator_limit;
+      rc.tp_timeout = c->tp_timeout;
+      rc.tpg_channel_mask.assign(c->channel_mask, c->channel_mask + std::min<uint32_t>(c->n_mask, 16));
+      rc.crate_id = c->crate_id;
+      rc.slot_id = c->slot_id;
+      rc.link_id = uint16_t(c->first_link_id + l);
+      rc.enable_tpg = c->enable_tpg != 0;
+      rc.emulator_mode = c->emulator_mode != 0;
+      rc.correct_channel_lookup = c->correct_channel_lookup != 0;
+      rc.channel_map_name = c->reversed_map ? "reversed" : "linear";
+      rc.enable_simple_threshold_on_collection = c->enable_simple_threshold_on_collection != 0;
+      rc.block_on_backpressure = c->block_on_backpressure != 0;
+      swtpg_host* hp = h.get();
+      auto sink = [hp, l](TriggerPrimitiveTypeAdapter&& tp) {
+        std::lock_guard<std::mutex> lk(*hp->qmu[l]);
+        if (hp->sink_capacity && hp->queues[l].size() >= hp->sink_capacity)
+          return false;
+        hp->queues[l].push_back(std::move(tp));
+        return true;
+      };
+      if (c->format == SWTPG_FORMAT_WIBETH) {
+        h->eth.push_back(std::make_unique<WIBEthFrameProcessor>(h->regs[l], h->engine));
+        h->eth[l]->init(sink);
+        h->eth[l]->conf(rc);
+      } else {
+        h->wib2.push_back(std::make_unique<WIB2FrameProcessor>(h->regs[l], h->engine));
+        h->wib2[l]->init(sink);
+        h->wib2[l]->conf(rc);
+      }
+    }
+    return h.release();
+  } catch (const TPGAlgorithmInexistent& e) {
+    g_host_error = std::string("TPGAlgorithmInexistent: ") + e.what();
+  } catch (const std::exception& e) {
+    g_host_error = e.what();
+  }
+  return nullptr;
+}
+
+void
+swtpg_host_destroy(swtpg_host* h)
+{
+  delete h;
+}
+
+int
+swtpg_host_start(swtpg_host* h)
+{
+  try {
+    for (auto& p : h->eth)
+      p->start();
+    for (auto& p : h->wib2)
+      p->start();
+    return 0;
+  } catch (const std::exception& e) {
+    g_host_error = e.what();
+    return -1;
+  }
+}
+
+int
+swtpg_host_stop(swtpg_host* h)
+{
+  try {
+    for (auto& p : h->eth)
+      p->stop();
+    for (auto& p : h->wib2)
+      p->stop();
+    return 0;
+  } catch (const std::exception& e) {
+    g_host_error = e.what();
+    return -1;
+  }
+}
+
+// One payload of one link through the consumer path: pre-process tasks (may rewrite the header in emulator mode — the
+// buffer is the caller's, as the latency buffer element is in the reference), then the post-process task.
+int
+swtpg_host_push(swtpg_host* h, uint32_t link, void* payload)
+{
+  try {
+    if (!h->eth.empty()) {
+      auto* fp = static_cast<DUNEWIBEthTypeAdapter*>(payload);
+      h->eth[link]->preprocess_item(fp);
+      h->eth[link]->postprocess_item(fp);
+    } else {
+      auto* fp = static_cast<DUNEWIBSuperChunkTypeAdapter*>(payload);
+      h->wib2[link]->preprocess_item(fp);
+      h->wib2[link]->postprocess_item(fp);
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_host_error = e.what();
+    return -1;
+  }
+}
+
+size_t
+swtpg_host_take_tps(swtpg_host* h, uint32_t link, swtpg_host_tp* out, size_t cap)
+{
+  std::lock_guard<std::mutex> lk(*h->qmu[link]);
+  auto& q = h->queues[link];
+  const size_t n = std::min(cap, q.size());
+  for (size_t i = 0; i < n; ++i) {
+    const TriggerPrimitive& t = q[i].tp;
+    out[i] = { t.time_start, t.time_peak, t.time_over_threshold, t.channel, t.adc_integral, t.adc_peak, t.detid, uint32_t(t.type),
+               uint32_t(t.algorithm), t.version, t.flag };
+  }
+  q.erase(q.begin(), q.begin() + long(n));
+  return n;
+}
+
+void
+swtpg_host_get_info(swtpg_host* h, uint32_t link, RawDataProcessorInfo* info)
+{
+  if (!h->eth.empty())
+    h->eth[link]->get_info(*info);
+  else
+    h->wib2[link]->get_info(*info);
+}
+
+uint64_t
+swtpg_host_error_count(swtpg_host* h, uint32_t link, const char* name)
+{
+  std::lock_guard<std::mutex> lk(h->regs[link]->mu);
+  auto it = h->regs[link]->counts.find(name);
+  return it == h->regs[link]->counts.end() ? 0 : it->second;
+}
+
+uint32_t
+swtpg_host_misconfigurations(swtpg_host* h, uint32_t link)
+{
+  return h->eth.empty() ? 0u : uint32_t(h->eth[link]->misconfigurations().size());
+}
+
+uint64_t
+swtpg_host_last_daq_time(swtpg_host* h, uint32_t link)
+{
+  return h->eth.empty() ? h->wib2[link]->get_last_daq_time() : h->eth[link]->get_last_daq_time();
+}
+
+// position -> offline channel map of a link (after its first frame)
+void
+swtpg_host_register_channel_map(swtpg_host* h, uint32_t link, uint32_t* out64)
+{
+  if (h->eth.empty())
+    return;
+  for (int p = 0; p < 64; ++p)
+    out64[p] = h->eth[link]->handler()->register_channel_map[size_t(p)];
+}
+
+} // extern "C"

@@ -1,0 +1,149 @@
+"""ctypes face of libswtpg_host.so — the C++ frame-processor shim (fdreadoutlibs_b200/host/). Test harness only: a C++
+application links the classes of swtpg_host.hpp directly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(_HERE, "libswtpg_host.so")
+
+
+class HostConf(C.Structure):
+    _fields_ = [("device", C.c_int32), ("format", C.c_int32), ("n_links", C.c_uint32), ("superchunk_units", C.c_uint32),
+                ("tpg_algorithm", C.c_char * 32), ("tpg_rs_memory_factor", C.c_float), ("tpg_rs_scale_factor", C.c_float),
+                ("tpg_threshold", C.c_uint16), ("tpg_frugal_streaming_accumulator_limit", C.c_int16), ("tp_timeout", C.c_uint64),
+                ("channel_mask", C.c_uint32 * 16), ("n_mask", C.c_uint32), ("crate_id", C.c_uint16), ("slot_id", C.c_uint16),
+                ("first_link_id", C.c_uint16), ("enable_tpg", C.c_uint8), ("emulator_mode", C.c_uint8),
+                ("correct_channel_lookup", C.c_uint8), ("reversed_map", C.c_uint8), ("enable_simple_threshold_on_collection", C.c_uint8),
+                ("block_on_backpressure", C.c_uint8), ("pad", C.c_uint8 * 2), ("sink_capacity", C.c_uint32)]
+
+
+HOST_TP_DTYPE = np.dtype([("time_start", "<u8"), ("time_peak", "<u8"), ("time_over_threshold", "<u8"), ("channel", "<u4"),
+                          ("adc_integral", "<u4"), ("adc_peak", "<u2"), ("detid", "<u2"), ("type", "<u4"), ("algorithm", "<u4"),
+                          ("version", "<u2"), ("flag", "<u2")], align=True)
+
+
+class HostInfo(C.Structure):
+    _fields_ = [("num_seq_id_errors", C.c_uint64), ("min_seq_id_jump", C.c_int32), ("max_seq_id_jump", C.c_int32),
+                ("num_ts_errors", C.c_uint64), ("rate_tp_hits", C.c_double), ("num_tps_sent", C.c_uint64),
+                ("num_tps_suppressed_too_long", C.c_uint64), ("num_tps_send_failed", C.c_uint64), ("num_frames_dropped_busy", C.c_uint64),
+                ("top_channels", C.c_uint32 * 10), ("top_channel_tps", C.c_uint32 * 10), ("n_top", C.c_uint32)]
+
+
+EXPORTS = ["swtpg_host_last_error", "swtpg_host_create", "swtpg_host_destroy", "swtpg_host_start", "swtpg_host_stop", "swtpg_host_push",
+           "swtpg_host_take_tps", "swtpg_host_get_info", "swtpg_host_error_count", "swtpg_host_misconfigurations",
+           "swtpg_host_last_daq_time", "swtpg_host_register_channel_map"]
+
+_lib = None
+
+
+def host_lib():
+    global _lib
+    if _lib is None:
+        lib = C.CDLL(HOST_LIB_PATH)
+        lib.swtpg_host_last_error.restype = C.c_char_p
+        lib.swtpg_host_create.restype = C.c_void_p
+        lib.swtpg_host_create.argtypes = [C.POINTER(HostConf)]
+        lib.swtpg_host_destroy.argtypes = [C.c_void_p]
+        lib.swtpg_host_start.argtypes = [C.c_void_p]
+        lib.swtpg_host_stop.argtypes = [C.c_void_p]
+        lib.swtpg_host_push.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.swtpg_host_take_tps.restype = C.c_size_t
+        lib.swtpg_host_take_tps.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]
+        lib.swtpg_host_get_info.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(HostInfo)]
+        lib.swtpg_host_error_count.restype = C.c_uint64
+        lib.swtpg_host_error_count.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p]
+        lib.swtpg_host_misconfigurations.restype = C.c_uint32
+        lib.swtpg_host_misconfigurations.argtypes = [C.c_void_p, C.c_uint32]
+        lib.swtpg_host_last_daq_time.restype = C.c_uint64
+        lib.swtpg_host_last_daq_time.argtypes = [C.c_void_p, C.c_uint32]
+        lib.swtpg_host_register_channel_map.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+class HostError(RuntimeError):
+    pass
+
+
+class FrameProcessors:
+    """n_links frame processors (WIBEthFrameProcessor / WIB2FrameProcessor) sharing one TpgEngine on one device."""
+
+    def __init__(self, n_links: int, superchunk_units: int, fmt: str = "wibeth", algorithm: str = "SimpleThreshold", threshold: int = 60,
+                 rs_memory_factor: float = 0.8, rs_scale_factor: float = 2.0, acc_limit: int = 10, tp_timeout: int = 10 ** 9, channel_mask=(),
+                 crate_id: int = 1, slot_id: int = 0, first_link_id: int = 0, enable_tpg: bool = True, emulator_mode: bool = False,
+                 correct_channel_lookup: bool = False, reversed_map: bool = False, collection_simple_threshold: bool = False,
+                 sink_capacity: int = 0, block_on_backpressure: bool = True, device: int = 0):
+        c = HostConf()
+        c.device, c.format, c.n_links, c.superchunk_units = device, 1 if fmt == "wib2" else 0, n_links, superchunk_units
+        c.tpg_algorithm = algorithm.encode()
+        c.tpg_threshold, c.tpg_rs_memory_factor, c.tpg_rs_scale_factor = threshold, rs_memory_factor, rs_scale_factor
+        c.tpg_frugal_streaming_accumulator_limit, c.tp_timeout = acc_limit, tp_timeout
+        for i, m in enumerate(channel_mask):
+            c.channel_mask[i] = m
+        c.n_mask = len(channel_mask)
+        c.crate_id, c.slot_id, c.first_link_id = crate_id, slot_id, first_link_id
+        c.enable_tpg, c.emulator_mode, c.correct_channel_lookup, c.reversed_map = enable_tpg, emulator_mode, correct_channel_lookup, reversed_map
+        c.enable_simple_threshold_on_collection = collection_simple_threshold
+        c.sink_capacity = sink_capacity
+        c.block_on_backpressure = block_on_backpressure
+        self.lib = host_lib()
+        self.n_links = n_links
+        self.h = self.lib.swtpg_host_create(C.byref(c))
+        if not self.h:
+            raise HostError(self.lib.swtpg_host_last_error().decode())
+
+    def _check(self, rc):
+        if rc != 0:
+            raise HostError(self.lib.swtpg_host_last_error().decode())
+
+    def start(self):
+        self._check(self.lib.swtpg_host_start(self.h))
+
+    def stop(self):
+        self._check(self.lib.swtpg_host_stop(self.h))
+
+    def push(self, link: int, payload: np.ndarray):
+        """payload: writable uint8 array of one frame / superchunk (pre-process tasks may rewrite its header)."""
+        assert payload.dtype == np.uint8 and payload.flags["C_CONTIGUOUS"] and payload.flags["WRITEABLE"]
+        self._check(self.lib.swtpg_host_push(self.h, link, payload.ctypes.data))
+
+    def take_tps(self, link: int, cap: int = 1 << 18) -> np.ndarray:
+        out = np.zeros(cap, dtype=HOST_TP_DTYPE)
+        n = self.lib.swtpg_host_take_tps(self.h, link, out.ctypes.data, cap)
+        return out[:n].copy()
+
+    def get_info(self, link: int) -> dict:
+        i = HostInfo()
+        self.lib.swtpg_host_get_info(self.h, link, C.byref(i))
+        d = {n: getattr(i, n) for n, _ in HostInfo._fields_ if not n.startswith("top")}
+        d["top"] = [(i.top_channels[k], i.top_channel_tps[k]) for k in range(i.n_top)]
+        return d
+
+    def error_count(self, link: int, name: str) -> int:
+        return int(self.lib.swtpg_host_error_count(self.h, link, name.encode()))
+
+    def misconfigurations(self, link: int) -> int:
+        return int(self.lib.swtpg_host_misconfigurations(self.h, link))
+
+    def last_daq_time(self, link: int) -> int:
+        return int(self.lib.swtpg_host_last_daq_time(self.h, link))
+
+    def register_channel_map(self, link: int) -> np.ndarray:
+        out = np.zeros(64, dtype=np.uint32)
+        self.lib.swtpg_host_register_channel_map(self.h, link, out.ctypes.data)
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.swtpg_host_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
