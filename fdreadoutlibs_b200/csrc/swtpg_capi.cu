@@ -62,7 +62,7 @@ struct swtpg_handle
   swtpg_config cfg{};
   uint32_t unit_bytes = 0, channels = 0, ticks = 0, groups_per_link = 0, n_groups = 0;
   uint32_t tp_capacity = 0;
-  bool fast_simple = false;
+  bool fast_simple = false, fast_fir = false;
   bool started = false;
 
   cudaStream_t stream = nullptr; // batch path + all kernels (state is carried batch to batch: kernels are ordered)
@@ -256,7 +256,8 @@ launch(const swtpg_handle* h, const KernelParams& kp, cudaStream_t s)
       case SWTPG_ALGO_SIMPLE_THRESHOLD:
         return h->fast_simple ? launch_wib2<PackedSimpleWib2, DUMP>(kp, s)
                               : launch_wib2<ScalarAlgo<SWTPG_ALGO_SIMPLE_THRESHOLD, true>, DUMP>(kp, s);
-      case SWTPG_ALGO_FIR_IQR: return launch_wib2<ScalarAlgo<SWTPG_ALGO_FIR_IQR, true>, DUMP>(kp, s);
+      case SWTPG_ALGO_FIR_IQR:
+        return h->fast_fir ? launch_wib2<PackedFirIqr, DUMP>(kp, s) : launch_wib2<ScalarAlgo<SWTPG_ALGO_FIR_IQR, true>, DUMP>(kp, s);
       default: return cudaErrorNotSupported;
     }
   }
@@ -267,7 +268,8 @@ launch(const swtpg_handle* h, const KernelParams& kp, cudaStream_t s)
                               : launch_wibeth<ScalarAlgo<SWTPG_ALGO_SIMPLE_THRESHOLD, false>, DUMP>(kp, s);
       case SWTPG_ALGO_ABS_RS: return launch_wibeth<ScalarAlgo<SWTPG_ALGO_ABS_RS, false>, DUMP>(kp, s);
       case SWTPG_ALGO_STANDARD_RS: return launch_wibeth<ScalarAlgo<SWTPG_ALGO_STANDARD_RS, false>, DUMP>(kp, s);
-      case SWTPG_ALGO_FIR_IQR: return launch_wibeth<ScalarAlgo<SWTPG_ALGO_FIR_IQR, false>, DUMP>(kp, s);
+      case SWTPG_ALGO_FIR_IQR:
+        return h->fast_fir ? launch_wibeth<PackedFirIqr, DUMP>(kp, s) : launch_wibeth<ScalarAlgo<SWTPG_ALGO_FIR_IQR, false>, DUMP>(kp, s);
     }
   }
   return cudaErrorNotSupported;
@@ -296,6 +298,8 @@ make_params(const swtpg_handle* h, const void* d_frames, const uint32_t* d_nunit
   for (int i = 0; i < 8; ++i)
     kp.taps[i] = h->cfg.fir_taps[i];
   kp.wib2_adc_offset = h->cfg.wib2_adc_offset;
+  static const bool force_exact = [] { const char* e = getenv("SWTPG_FIR_FORCE_EXACT"); return e && atoi(e) != 0; }();
+  kp.debug_flags = force_exact ? 1u : 0u;
   return kp;
 }
 
@@ -624,7 +628,19 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
   h->tp_capacity = uint32_t(cap);
   // Packed fast path validity (see PackedSimpleWibEth)
   h->fast_simple = cfg->algorithm == SWTPG_ALGO_SIMPLE_THRESHOLD && cfg->threshold <= 32767 &&
-                   (wib2 || (cfg->frugal_acc_limit >= 1 && cfg->frugal_acc_limit <= 1000));
+                   (wib2 || (cfg->frugal_acc_limit >= 1 && cfg->frugal_acc_limit <= 1000)) && getenv("SWTPG_FORCE_SCALAR") == nullptr;
+
+  // Packed FIR fast path validity (see PackedFirIqr): binomial taps, and (sigmaMax + 3) * multiplier * threshold < 2^16
+  {
+    static const int16_t kBinomial[8] = { 1, 6, 15, 20, 15, 6, 1, 0 };
+    bool taps_ok = true;
+    for (int i = 0; i < 8; ++i)
+      taps_ok &= h->cfg.fir_taps[i] == kBinomial[i];
+    const uint32_t e = h->cfg.tap_exponent, mult = 1u << e;
+    const uint64_t sigma_max = (1u << 15) / (mult * 5u);
+    h->fast_fir = cfg->algorithm == SWTPG_ALGO_FIR_IQR && taps_ok && e >= 1 && e <= 10 &&
+                  (sigma_max + 3) * mult * uint64_t(cfg->threshold) < 65536 && getenv("SWTPG_FORCE_SCALAR") == nullptr;
+  }
 
   swtpg_handle* hp = h.get();
   SW_CUDA(hp, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));

@@ -125,6 +125,24 @@ ne2_abs_one(uint32_t a, uint32_t b)
   asm("{.reg .b32 t; abs.f16x2 t, %1; set.ne.f16x2.f16x2 %0, t, %2;}" : "=r"(r) : "r"(a), "r"(b));
   return r;
 }
+// Per half: 1.0 (0x3C00) where a == b as fp16, else 0.0 (HSET2.BF.EQ).
+__device__ __forceinline__ uint32_t
+eq2_one(uint32_t a, uint32_t b)
+{
+  uint32_t r;
+  asm("set.eq.f16x2.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+// Per-half "a > b" as 0xFFFF / 0x0000 for 0 <= a <= 32767 and 0 <= b <= 32640, computed by the bf16 comparator on the bit
+// patterns (HSET2.BF16_V2.GTU): non-negative bf16 values order like their patterns up to +inf = 0x7F80 = 32640; patterns
+// above that are NaNs, for which the "or unordered" flavour answers true — and a > 32640 >= b is indeed true.
+__device__ __forceinline__ uint32_t
+gt2_mask_bf16(uint32_t a, uint32_t b)
+{
+  uint32_t r;
+  asm("set.gtu.u32.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 __device__ __forceinline__ uint32_t
 pack2(int lo, int hi)
 {
@@ -311,16 +329,20 @@ struct HitStage
   // Warp-uniform (every lane reads the same word); call after __syncwarp().
   __device__ __forceinline__ bool nearly_full() const { return *reinterpret_cast<volatile uint32_t*>(cnt) > kFlushAbove; }
 
-  // Converts and writes out everything staged (see flush_hits_wibeth). Whole warp calls, converged.
-  __device__ __forceinline__ void flush_wibeth(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const;
-  __device__ __forceinline__ void flush_wib2(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const;
+  // Converts and writes out everything staged (see flush_hits). Whole warp calls, converged.
+  template<bool WIB2_UNITS, bool WIB2_FIELDS>
+  __device__ __forceinline__ void flush(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const;
 };
 
-// WIBEth TP fields: src/wibeth/WIBEthFrameProcessor.cpp:520-545. Out of line (cold: once per ~32 hits) and all-by-value, so
-// the caller keeps its state in registers.
+// Hit record -> swtpg_tp. Out of line (cold: once per ~32 hits) and all-by-value, so the caller keeps its state in registers.
+//   WIB2_UNITS : where the unit's timestamp lives — WIBEthFrame DAQEthHeader word 1 (docs/README.md:81) or
+//                WIB2Frame::get_timestamp of the superchunk's first frame (bytes 4..11, src/wib2/WIB2FrameProcessor.cpp:350-351)
+//   WIB2_FIELDS: which process_swtpg_hits derives the fields — src/wibeth/WIBEthFrameProcessor.cpp:520-545 (peak from the
+//                tracked peak) or src/wib2/WIB2FrameProcessor.cpp:429-455 (time_peak = middle of the hit, adc_peak = integral/20)
+template<bool WIB2_UNITS, bool WIB2_FIELDS>
 __device__ __noinline__ void
-flush_hits_wibeth(uint4* buf, uint32_t* cnt, swtpg_tp* out, unsigned int* out_count, uint32_t out_cap, const uint8_t* link_base, uint32_t link,
-                  uint32_t lane)
+flush_hits(uint4* buf, uint32_t* cnt, swtpg_tp* out, unsigned int* out_count, uint32_t out_cap, const uint8_t* link_base, uint32_t link,
+           uint32_t lane)
 {
   __syncwarp();
   const uint32_t n = *reinterpret_cast<volatile uint32_t*>(cnt);
@@ -333,14 +355,28 @@ flush_hits_wibeth(uint4* buf, uint32_t* cnt, swtpg_tp* out, unsigned int* out_co
   for (uint32_t i = lane; i < n; i += 32) {
     const uint4 r = buf[i];
     const uint32_t chan = r.x & 0xFFu, t_end = r.x >> 8, charge = r.z & 0xFFFFu, tover = r.z >> 16, peak = r.w & 0xFFFFu, ptime = r.w >> 16;
-    const uint64_t ts = *reinterpret_cast<const unsigned long long*>(link_base + size_t(r.y) * SWTPG_WIBETH_FRAME_BYTES + 8);
+    uint64_t ts;
+    if constexpr (WIB2_UNITS) {
+      const uint32_t* hdr = reinterpret_cast<const uint32_t*>(link_base + size_t(r.y) * SWTPG_WIB2_SUPERCHUNK_BYTES + 4);
+      ts = uint64_t(hdr[0]) | (uint64_t(hdr[1]) << 32);
+    } else {
+      ts = *reinterpret_cast<const unsigned long long*>(link_base + size_t(r.y) * SWTPG_WIBETH_FRAME_BYTES + 8);
+    }
     const uint64_t t0 = ts + uint64_t(32ll * (int64_t(t_end) - int64_t(tover)));
     const unsigned idx = base + i;
     if (idx < out_cap) {
       uint4* d = reinterpret_cast<uint4*>(out + idx);
-      const uint64_t tp = t0 + 32ull * ptime;
+      uint64_t tp;
+      uint32_t pk;
+      if constexpr (WIB2_FIELDS) {
+        tp = (t0 + (ts + uint64_t(32ll * int64_t(t_end)))) / 2;
+        pk = (charge / 20u) & 0xFFFFu;
+      } else {
+        tp = t0 + 32ull * ptime;
+        pk = peak;
+      }
       d[0] = make_uint4(uint32_t(t0), uint32_t(t0 >> 32), uint32_t(tp), uint32_t(tp >> 32));
-      d[1] = make_uint4(32u * tover, charge, peak | (chan << 16), link);
+      d[1] = make_uint4(32u * tover, charge, pk | (chan << 16), link);
     }
   }
   __syncwarp();
@@ -349,51 +385,11 @@ flush_hits_wibeth(uint4* buf, uint32_t* cnt, swtpg_tp* out, unsigned int* out_co
   __syncwarp();
 }
 
-// WIB2 TP fields: src/wib2/WIB2FrameProcessor.cpp:429-455 (time_peak = middle of the hit, adc_peak = integral / 20).
-// The unit's timestamp is WIB2Frame::get_timestamp of the superchunk's first frame (bytes 4..11, :350-351).
-__device__ __noinline__ void
-flush_hits_wib2(uint4* buf, uint32_t* cnt, swtpg_tp* out, unsigned int* out_count, uint32_t out_cap, const uint8_t* link_base, uint32_t link,
-                uint32_t lane)
-{
-  __syncwarp();
-  const uint32_t n = *reinterpret_cast<volatile uint32_t*>(cnt);
-  if (n == 0)
-    return;
-  unsigned base = 0;
-  if (lane == 0)
-    base = atomicAdd(out_count, n);
-  base = __shfl_sync(0xFFFFFFFFu, base, 0);
-  for (uint32_t i = lane; i < n; i += 32) {
-    const uint4 r = buf[i];
-    const uint32_t chan = r.x & 0xFFu, t_end = r.x >> 8, charge = r.z & 0xFFFFu, tover = r.z >> 16;
-    const uint32_t* hdr = reinterpret_cast<const uint32_t*>(link_base + size_t(r.y) * SWTPG_WIB2_SUPERCHUNK_BYTES + 4);
-    const uint64_t ts = uint64_t(hdr[0]) | (uint64_t(hdr[1]) << 32);
-    const uint64_t t0 = ts + uint64_t(32ll * (int64_t(t_end) - int64_t(tover)));
-    const uint64_t t1 = ts + uint64_t(32ll * int64_t(t_end));
-    const unsigned idx = base + i;
-    if (idx < out_cap) {
-      uint4* d = reinterpret_cast<uint4*>(out + idx);
-      const uint64_t tp = (t0 + t1) / 2;
-      d[0] = make_uint4(uint32_t(t0), uint32_t(t0 >> 32), uint32_t(tp), uint32_t(tp >> 32));
-      d[1] = make_uint4(32u * tover, charge, ((charge / 20u) & 0xFFFFu) | (chan << 16), link);
-    }
-  }
-  __syncwarp();
-  if (lane == 0)
-    *reinterpret_cast<volatile uint32_t*>(cnt) = 0u;
-  __syncwarp();
-}
-
+template<bool WIB2_UNITS, bool WIB2_FIELDS>
 __device__ __forceinline__ void
-HitStage::flush_wibeth(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const
+HitStage::flush(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const
 {
-  flush_hits_wibeth(buf, cnt, k.buf, k.count, k.cap, link_base, link, lane);
-}
-
-__device__ __forceinline__ void
-HitStage::flush_wib2(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const
-{
-  flush_hits_wib2(buf, cnt, k.buf, k.count, k.cap, link_base, link, lane);
+  flush_hits<WIB2_UNITS, WIB2_FIELDS>(buf, cnt, k.buf, k.count, k.cap, link_base, link, lane);
 }
 
 } // namespace swtpg

@@ -19,6 +19,9 @@
 #ifndef SWTPG_GROUP_UNROLL
 #define SWTPG_GROUP_UNROLL 4
 #endif
+#ifndef SWTPG_FIR_GROUP_UNROLL
+#define SWTPG_FIR_GROUP_UNROLL 1
+#endif
 #ifndef SWTPG_FLOAT_ACC
 #define SWTPG_FLOAT_ACC 1
 #endif
@@ -67,6 +70,7 @@ struct KernelParams
   int32_t tap_exponent;
   int32_t taps[8];
   uint32_t wib2_adc_offset;
+  uint32_t debug_flags;    // bit 0: PackedFirIqr always takes its exact-threshold tier (test aid, SWTPG_FIR_FORCE_EXACT=1)
 };
 
 struct TickCtx
@@ -108,6 +112,43 @@ frugal_scalar(int& median, int s, int& accum, int L, bool mask)
     accum = 0;
 }
 
+// Threshold of the FIR + IQR finder for the two channels of a lane: the 16-bit lanes of `sigma * multiplier * threshold`
+// evaluated the way GCC evaluates `__m256i * int` — as 4 x int64 lanes (wib2/tpg/ProcessAVX2FIR.hpp:208): the
+// sigmas of 4 adjacent register POSITIONS form one u64 that is multiplied mod 2^64, so carries run from one position into
+// the next. Position q of a register holds channel perm[q] of its 16 (perm = {0..7,15,8..14}). Whole warp calls;
+// sig_packed = this lane's two sigmas (s16x2), lane = index inside the 64-channel group.
+__device__ __noinline__ uint32_t
+iqr_threshold_exact(uint32_t sig_packed, uint32_t lane, int multiplier, uint32_t threshold)
+{
+  uint32_t sig8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    sig8[j] = __shfl_sync(0xFFFFFFFFu, sig_packed, int((lane & ~7u) + j));
+  const uint64_t K = uint64_t(int64_t(int16_t(multiplier))) * uint64_t(threshold); // (sigma*mult)*thr mod 2^64
+  int th[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int ch16 = int(2 * (lane & 7u)) + h;                           // channel within the 16-channel register
+    const int pos = ch16 < 8 ? ch16 : (ch16 == 15 ? 8 : ch16 + 1);       // inverse of perm {0..7,15,8..14}
+    const int g = pos >> 2, jj = pos & 3;
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pp = 4 * g + i;
+      const int cc = pp < 8 ? pp : (pp == 8 ? 15 : pp - 1);              // perm
+      uint32_t w = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        w = (cc >> 1) == q ? sig8[q] : w;
+      const uint64_t s16 = (cc & 1) ? (w >> 16) : (w & 0xFFFFu);
+      v |= s16 << (16 * i);
+    }
+    v *= K;
+    th[h] = int(int16_t(uint16_t(v >> (16 * jj))));
+  }
+  return pack2(th[0], th[1]);
+}
+
 struct ChanRegs
 { // one channel, unpacked
   int median, accum, prev, charge, tover, peak_adc, peak_time;
@@ -119,6 +160,7 @@ struct ChanRegs
 template<int ALGO, bool WIB2>
 struct ScalarAlgo
 {
+  static constexpr int kGroupUnroll = 1;
   ChanRegs c[2];
   uint32_t kphase; // FIR ring phase
 
@@ -139,7 +181,7 @@ struct ScalarAlgo
     }
     kphase = (flags >> 8) & 7u;
   }
-  __device__ __forceinline__ void store(uint32_t* st, uint32_t lane) const
+  __device__ __forceinline__ void store(uint32_t* st, uint32_t lane, uint32_t) const
   {
     auto put = [&](int v, int lo, int hi) { st[v * 32 + lane] = pack2(lo, hi); };
     put(SV_MEDIAN, c[0].median, c[1].median); put(SV_ACCUM, c[0].accum, c[1].accum); put(SV_PREV, c[0].prev, c[1].prev);
@@ -153,6 +195,8 @@ struct ScalarAlgo
   }
   __device__ __forceinline__ uint32_t phase_after(uint32_t ticks) const { return (kphase + ticks) & 7u; }
   __device__ __forceinline__ void configure(const KernelParams&) {}
+  template<bool WIB2_UNITS>
+  static __device__ __forceinline__ void flush(const HitStage&, const TpSink&, const uint8_t*, uint32_t, uint32_t) {} // emits directly
 
   // setState: pedestal = first sample, quartiles +-20 (wibeth/tpg/ProcessingInfo.hpp:116-144)
   __device__ __forceinline__ void seed(uint32_t S)
@@ -166,7 +210,7 @@ struct ScalarAlgo
     }
   }
 
-  template<int G, bool DUMP, int ROW_WORDS = 28>
+  template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
   __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
                                         uint32_t* wav_out)
   {
@@ -225,32 +269,10 @@ struct ScalarAlgo
         wav[h] = f;
       }
       // Threshold = 16-bit lane of a 64-bit-lane product over 4 adjacent AVX2 register POSITIONS.
-      // Position q of register r holds channel 16r + perm[q]; gather the 16 sigmas of this lane's register.
-      const uint32_t sig_packed = pack2(sigma[0], sigma[1]);
-      uint32_t sig8[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        sig8[j] = __shfl_sync(0xFFFFFFFFu, sig_packed, int((lane & ~7u) + j));
-      const uint64_t K = uint64_t(int64_t(int16_t(multiplier))) * uint64_t(p.threshold); // (sigma*mult)*thr mod 2^64
+      const uint32_t th2 = iqr_threshold_exact(pack2(sigma[0], sigma[1]), lane, multiplier, p.threshold);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int ch16 = int(2 * (lane & 7u)) + h;                           // channel within the 16-channel register
-        const int pos = ch16 < 8 ? ch16 : (ch16 == 15 ? 8 : ch16 + 1);       // inverse of perm {0..7,15,8..14}
-        const int g = pos >> 2, jj = pos & 3;
-        uint64_t v = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int pp = 4 * g + i;
-          const int cc = pp < 8 ? pp : (pp == 8 ? 15 : pp - 1);              // perm
-          uint32_t w = 0;
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            w = (cc >> 1) == q ? sig8[q] : w;
-          const uint64_t s16 = (cc & 1) ? (w >> 16) : (w & 0xFFFFu);
-          v |= s16 << (16 * i);
-        }
-        v *= K;
-        const int th = int(int16_t(uint16_t(v >> (16 * jj))));
+        const int th = h ? hi16s(th2) : lo16s(th2);
         ChanRegs& r = c[h];
         const bool over = filt[h] > th;
         const bool left = r.prev && !over;
@@ -334,6 +356,7 @@ struct ScalarAlgo
 // =====================================================================================================================
 struct PackedSimpleWibEth
 {
+  static constexpr int kGroupUnroll = SWTPG_GROUP_UNROLL;
   uint32_t Mq, A, prev, C, Tn, PK1, PTn;
   uint32_t cUp, cDn, thr1;
 
@@ -383,7 +406,7 @@ struct PackedSimpleWibEth
     PTn = neg2(st[SV_PEAK_TIME * 32 + lane]);
   }
   __device__ __forceinline__ uint32_t median() const { return add2(~Mq, 0x00020002u); } // 1 - Mq
-  __device__ __forceinline__ void store(uint32_t* st, uint32_t lane) const
+  __device__ __forceinline__ void store(uint32_t* st, uint32_t lane, uint32_t) const
   {
     st[SV_MEDIAN * 32 + lane] = median();
     st[SV_ACCUM * 32 + lane] = acc_from_reg(A);
@@ -395,6 +418,11 @@ struct PackedSimpleWibEth
   }
   __device__ __forceinline__ uint32_t phase_after(uint32_t) const { return 0; }
   __device__ __forceinline__ void seed(uint32_t S) { Mq = add2(~S, 0x00020002u); }
+  template<bool WIB2_UNITS>
+  static __device__ __forceinline__ void flush(const HitStage& h, const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane)
+  {
+    h.template flush<WIB2_UNITS, false>(k, link_base, link, lane);
+  }
 
   // frugal streaming median (wibeth/tpg/UtilsAVX2.hpp:38-73) + pedestal subtraction (ProcessAVX2.hpp:85): S -> s' + 1
   __device__ __forceinline__ uint32_t pedestal_step(uint32_t S)
@@ -456,7 +484,7 @@ struct PackedSimpleWibEth
   //     peak_time = 0 again (ProcessAVX2.hpp:134-136). Outside a hit peak_adc <= threshold (it restarts from 0 when a
   //     hit ends and every sample since was not over), so "new peak > threshold" <=> "some sample of the group is over".
   //  3. Otherwise per-tick bookkeeping for the whole warp.
-  template<int G, bool DUMP, int ROW_WORDS = 28>
+  template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
   __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
                                         uint32_t* wav_out)
   {
@@ -482,7 +510,7 @@ struct PackedSimpleWibEth
       hit_update(sp[g], ctx, t0 + g);
     __syncwarp();
     if (ctx.stage->nearly_full())
-      ctx.stage->flush_wibeth(ctx.p->sink, ctx.link_base, ctx.link, ctx.chan0 >> 1);
+      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
   }
 };
 
@@ -494,6 +522,12 @@ struct PackedSimpleWibEth
 struct PackedSimpleWib2 : PackedSimpleWibEth
 {
   uint32_t shift, shmask;
+
+  template<bool WIB2_UNITS>
+  static __device__ __forceinline__ void flush(const HitStage& h, const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane)
+  {
+    h.template flush<WIB2_UNITS, true>(k, link_base, link, lane);
+  }
 
   __device__ __forceinline__ void configure(const KernelParams& p)
   {
@@ -523,7 +557,7 @@ struct PackedSimpleWib2 : PackedSimpleWibEth
       Tn &= ~left;
     }
   }
-  template<int G, bool DUMP, int ROW_WORDS>
+  template<int G, bool DUMP, int ROW_WORDS, bool WIB2_UNITS>
   __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
                                         uint32_t* wav_out)
   {
@@ -547,7 +581,256 @@ struct PackedSimpleWib2 : PackedSimpleWibEth
       hit_update(sp[g], ctx, t0 + g);
     __syncwarp();
     if (ctx.stage->nearly_full())
-      ctx.stage->flush_wib2(ctx.p->sink, ctx.link_base, ctx.link, ctx.chan0 >> 1 & 31u);
+      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
+  }
+};
+
+// =====================================================================================================================
+// Packed fast path: FIR matched filter + IQR threshold (wib2/tpg/ProcessAVX2FIR.hpp:21-314), on either frame layout.
+// Three frugal trackers per channel (quartiles on the lanes below / above the OLD median, then the median, all with
+// L = 10, :108-125), sigma = min(q75 - q25, sigmaMax), s' = min(s - median, adcMax), the 7-tap filter over the ring
+// (which excludes the two newest samples, :160-201), threshold sigma * multiplier * threshold, charge += filt >> exponent.
+//
+// Validity (checked by the host): taps == {1,6,15,20,15,6,1,0}, 1 <= tap_exponent <= 10, sigmaMax * multiplier * threshold
+// < 2^16. What makes it fast:
+//   * the taps firwin_int(7, 0.1, 64) produces are the binomial row (1+z)^6, so the filter is six cascaded two-tap adders:
+//     6 packed adds per tick instead of 7 multiply-adds on a rotating ring, and every add wraps mod 2^16 exactly like the
+//     reference's mullo/add chain (ring homomorphism). The carried state stays the reference's ring: it is converted to
+//     cascade registers when a link is loaded and back when it is stored, which also removes the ring phase from the loop;
+//   * accumulators are fp16x2 subnormals (see PackedSimpleWibEth); q25 is kept as 1 - q25 and q75 as q75 + 2, so that the
+//     sign tests are single VIADDMNMX.RELU ops against S and ~S and sigma + 3 is their clamped sum;
+//   * while every sigma of the warp is >= 0 the 64-bit-lane product equals the per-channel product (no carries between
+//     positions) and is one packed IMAD; a warp that sees a negative sigma in a 4-tick group recomputes that
+//     group's thresholds with iqr_threshold_exact.
+// =====================================================================================================================
+struct PackedFirIqr
+{
+  static constexpr int kGroupUnroll = SWTPG_FIR_GROUP_UNROLL;
+  uint32_t Mq, A, Q25q, A25, Q75p, A75; // 1 - median, (acc - 1); 1 - q25, acc25; q75 + 2, acc75   (accumulators: fp16 subnormals)
+  uint32_t d1, d2, d3, d4, d5, d6, o1, o2; // cascade: d_j = previous input of stage j, o1/o2 = previous two outputs
+  uint32_t prev, C, Tn;
+  uint32_t xmax1, sig3max, K, Kneg3, shift, shmask, thr_cfg, mult;
+
+  static constexpr uint32_t kTiny = 0x00010001u;    // 2^-24 per half
+  static constexpr uint32_t kNegTiny = 0x80018001u;
+  static constexpr uint32_t kUp = 0x000B000Bu;      // (L+1) * 2^-24, L = 10
+  static constexpr uint32_t kDnEq = 0x800B800Bu;    // -(L+1)
+  static constexpr uint32_t kNegL = 0x800A800Au;    // -L
+  static constexpr uint32_t kOne = 0x3C003C00u, kNegOne = 0xBC00BC00u;
+
+  template<bool WIB2_UNITS>
+  static __device__ __forceinline__ void flush(const HitStage& h, const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane)
+  {
+    h.template flush<WIB2_UNITS, true>(k, link_base, link, lane); // FIR hit blocks carry {chan, t, charge, tover} only
+  }
+  __device__ __forceinline__ void configure(const KernelParams& p)
+  {
+    mult = 1u << p.tap_exponent;
+    const uint32_t adc_max = 32767u / mult;                   // wib2/tpg/ProcessingInfo.hpp:93
+    const uint32_t sigma_max = (1u << 15) / (mult * 5u);      // ProcessAVX2FIR.hpp:36
+    xmax1 = (adc_max + 1u) * 0x00010001u;
+    sig3max = (sigma_max + 3u) * 0x00010001u;
+    thr_cfg = p.threshold;
+    K = mult * p.threshold;
+    Kneg3 = 0u - 3u * K * 0x00010001u;                        // -(3K, 3K) as ONE 32-bit integer (see threshold())
+    shift = uint32_t(p.tap_exponent);
+    const uint32_t m = 0xFFFFu >> shift;
+    shmask = m | (m << 16);
+  }
+  static __device__ __forceinline__ uint32_t to_sm(uint32_t v)
+  { // two's complement s16x2 -> sign-magnitude (= bit pattern of value * 2^-24 as fp16), |v| <= 1023
+    const uint32_t neg = (v & 0x80008000u) >> 15, m = neg * 0xFFFFu;
+    return (add2(v ^ m, neg) & 0x7FFF7FFFu) | (m & 0x80008000u);
+  }
+  static __device__ __forceinline__ uint32_t from_sm(uint32_t v)
+  {
+    const uint32_t neg = (v & 0x80008000u) >> 15, m = neg * 0xFFFFu;
+    return add2((v & 0x7FFF7FFFu) ^ m, neg);
+  }
+  __device__ __forceinline__ void cascade(uint32_t x)
+  {
+    const uint32_t y1 = add2(x, d1), y2 = add2(y1, d2), y3 = add2(y2, d3), y4 = add2(y3, d4), y5 = add2(y4, d5), y6 = add2(y5, d6);
+    d1 = x; d2 = y1; d3 = y2; d4 = y3; d5 = y4; d6 = y5;
+    o2 = o1;
+    o1 = y6;
+  }
+  __device__ __forceinline__ void load(const uint32_t* st, uint32_t lane, uint32_t flags)
+  {
+    Mq = add2(~st[SV_MEDIAN * 32 + lane], 0x00020002u);
+    A = to_sm(add2(st[SV_ACCUM * 32 + lane], 0xFFFFFFFFu));
+    Q25q = add2(~st[SV_Q25 * 32 + lane], 0x00020002u);
+    A25 = to_sm(st[SV_A25 * 32 + lane]);
+    Q75p = add2(st[SV_Q75 * 32 + lane], 0x00020002u);
+    A75 = to_sm(st[SV_A75 * 32 + lane]);
+    prev = st[SV_PREV * 32 + lane];
+    C = st[SV_CHARGE * 32 + lane];
+    Tn = neg2(st[SV_TOVER * 32 + lane]);
+    // ring -> cascade: replay the ring's 8 samples, oldest first, through an empty cascade (the state only depends on them)
+    const uint32_t k = (flags >> 8) & 7u; // next slot to be written = oldest sample
+    kphase0 = k;
+    d1 = d2 = d3 = d4 = d5 = d6 = o1 = o2 = 0u;
+    for (uint32_t i = 0; i < 8; ++i)
+      cascade(st[(SV_RING0 + ((k + i) & 7u)) * 32 + lane]);
+  }
+  __device__ __forceinline__ uint32_t median() const { return add2(~Mq, 0x00020002u); }
+  __device__ __forceinline__ void store(uint32_t* st, uint32_t lane, uint32_t k_end) const
+  {
+    st[SV_MEDIAN * 32 + lane] = median();
+    st[SV_ACCUM * 32 + lane] = add2(from_sm(A), 0x00010001u);
+    st[SV_Q25 * 32 + lane] = add2(~Q25q, 0x00020002u);
+    st[SV_A25 * 32 + lane] = from_sm(A25);
+    st[SV_Q75 * 32 + lane] = add2(Q75p, 0xFFFEFFFEu);
+    st[SV_A75 * 32 + lane] = from_sm(A75);
+    st[SV_PREV * 32 + lane] = prev;
+    st[SV_CHARGE * 32 + lane] = C;
+    st[SV_TOVER * 32 + lane] = neg2(Tn);
+    // cascade -> ring, by running the cascade backwards: with Y[j] = y_j one tick ago (y_0 = the sample itself),
+    // y_{j-1}(two ticks ago) = Y[j] - Y[j-1]; every step back in time loses the top stage, and y_0 is the ring entry.
+    uint32_t Y[7] = { d1, d2, d3, d4, d5, d6, o1 };
+    int top = 6;             // Y[0..top] valid
+    uint32_t known_top = o2; // y_6 two ticks ago
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i) {
+      st[(SV_RING0 + ((k_end + 7u - i) & 7u)) * 32 + lane] = Y[0]; // sample i+1 ticks ago
+      uint32_t Z[7] = {};
+#pragma unroll
+      for (int jj = 1; jj <= 6; ++jj)
+        if (jj <= top)
+          Z[jj - 1] = add2(Y[jj], neg2(Y[jj - 1]));
+      if (i == 0) { // the column two ticks ago still has its top entry (o2)
+        Z[6] = known_top;
+      } else {
+        top -= 1;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 7; ++jj)
+        Y[jj] = Z[jj];
+    }
+  }
+  uint32_t kphase0;
+  __device__ __forceinline__ uint32_t phase_after(uint32_t ticks) const { return (kphase0 + ticks) & 7u; }
+  // setState: pedestal = first sample, quartiles +-20 (wib2/tpg/ProcessingInfo.hpp:101-141)
+  __device__ __forceinline__ void seed(uint32_t S)
+  {
+    Mq = add2(~S, 0x00020002u);                // 1 - ped
+    Q25q = add2(~S, 0x00160016u);              // 1 - (ped - 20)
+    Q75p = add2(S, 0x00160016u);               // (ped + 20) + 2
+  }
+
+  // One frugal quartile step on the lanes `en` (1.0 / 0.0 per half). sgn = sign(raw - q) * 2^-24.
+  //   NEG_REP: q is held as 1 - q (step up = add the 0xFFFF mask, step down = add the bit pattern 1), else as q + 2.
+  template<bool NEG_REP>
+  static __device__ __forceinline__ void quartile_step(uint32_t& Q, uint32_t& Aq, uint32_t sgn, uint32_t en)
+  {
+    const uint32_t T = hfma2_bits(en, sgn, Aq);                       // acc (+= sign on enabled lanes)
+    const uint32_t keep = ne2_abs_one(T, kUp);                        // 1.0 unless |acc| == L+1
+    uint32_t a, b;
+    if constexpr (NEG_REP) {
+      a = eq2_mask(T, kUp);                                           // up:   -1
+      b = hfma2_sat_bits(T, kNegOne, kNegL);                          // down: +1
+    } else {
+      a = hfma2_sat_bits(T, kOne, kNegL);                             // up:   +1
+      b = eq2_mask(T, kDnEq);                                         // down: -1
+    }
+    Aq = hfma2_bits(keep, T, 0u);                                     // reset where stepped
+    Q = add2(add2(Q, a), b);
+  }
+
+  // One tick: returns the filter output of this tick; sig3 = min(sigma, sigmaMax) + 3.
+  __device__ __forceinline__ uint32_t tick(uint32_t S, uint32_t& sig3)
+  {
+    const uint32_t sg1 = addclamp2(S, Mq, 0x00020002u);               // sign(raw - median) + 1, OLD median   (:108-117)
+    const uint32_t ltf = eq2_one(sg1, 0u), gtf = eq2_one(sg1, 0x00020002u);
+    // q25 on the lanes below the median (:119)
+    quartile_step<true>(Q25q, A25, hadd2_bits(addclamp2(S, Q25q, 0x00020002u), kNegTiny), ltf);
+    // q75 on the lanes above (:121): 1 - sign(raw - q75) from ~S = -S - 1
+    quartile_step<false>(Q75p, A75, hfma2_bits(addclamp2(~S, Q75p, 0x00020002u), kNegOne, kTiny), gtf);
+    // median (:125), as PackedSimpleWibEth::pedestal_step with L = 10
+    const uint32_t T = hadd2_bits(A, sg1);
+    const uint32_t upm = eq2_mask(T, kUp);
+    const uint32_t dn1 = hfma2_sat_bits(T, kNegOne, kNegL);
+    A = hfma2_bits(ne2_abs_one(T, kUp), T, kNegTiny);
+    Mq = add2(add2(Mq, upm), dn1);
+    const uint32_t x = add2(min2(add2(S, Mq), xmax1), 0xFFFFFFFFu);   // min(raw - median, adcMax)           (:128,142)
+    sig3 = addmin2(Q75p, Q25q, sig3max);                              // min(q75 - q25, sigmaMax) + 3        (:131-134)
+    const uint32_t filt = o2;                                         // window = samples t-8 .. t-2          (:160-201)
+    cascade(x);
+    return filt;
+  }
+  // sigma * multiplier * threshold for sigma >= 0: (sig3 - 3) * K per half, as one 32-bit multiply-add — no carry crosses
+  // the halves because each half of sig3 * K is >= 3K and < 2^16 + 3K... the host checks (sigmaMax + 3) * K < 2^16.
+  __device__ __forceinline__ uint32_t threshold(uint32_t sig3) const { return sig3 * K + Kneg3; }
+
+  template<bool EXACT>
+  __device__ __forceinline__ void hit_update(uint32_t filt, uint32_t thr, const TickCtx& ctx, int t)
+  {
+    uint32_t over;
+    if constexpr (EXACT) // any threshold value: plain signed compares
+      over = (lo16s(filt) > lo16s(thr) ? 0xFFFFu : 0u) | (hi16s(filt) > hi16s(thr) ? 0xFFFF0000u : 0u);
+    else
+      over = gt2_mask_bf16(max2(filt, 0u), thr);          // 0 <= thr <= 32640                        (:208)
+    const uint32_t left = prev & ~over;                   //                                           (:210)
+    uint32_t add;
+    if constexpr (EXACT)
+      add = pack2((lo16s(filt & over)) >> shift, (hi16s(filt & over)) >> shift);
+    else
+      add = ((filt & over) >> shift) & shmask;            // over => filt > thr >= 0: arithmetic == logical shift (:221-223)
+    if constexpr (EXACT)
+      C = pack2(sat16(lo16s(C) + lo16s(add)), sat16(hi16s(C) + hi16s(add)));
+    else
+      C = minu2(add2(C, add), 0x7FFF7FFFu);               // adds_epi16 of two non-negative halves
+    Tn = addmax2(Tn, over, 0x80018001u);                  // tover = adds(tover, 1)                    (:236-237)
+    prev = over;
+    if (left != 0u) {                                     //                                           (:251-281)
+      const uint32_t T = neg2(Tn);
+      if ((left & 0xFFFFu) && (C & 0xFFFFu))              // accepted iff hit_charge != 0 (src/wib2/WIB2FrameProcessor.cpp:429)
+        ctx.stage->push(ctx.chan0, ctx.unit, uint32_t(t), C & 0xFFFFu, T & 0xFFFFu, 0u, 0u);
+      if ((left >> 16) && (C >> 16))
+        ctx.stage->push(ctx.chan0 + 1u, ctx.unit, uint32_t(t), C >> 16, T >> 16, 0u, 0u);
+      C &= ~left;
+      Tn &= ~left;
+    }
+  }
+
+  template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
+  __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
+                                        uint32_t* wav_out)
+  {
+    static_assert(G == 4, "trees below are written for 4 ticks");
+    uint32_t filt[G], sig3[G], thr[G];
+    uint32_t neg = 0u; // min over the group of (sigma, 0): non-zero <=> some sigma < 0
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      filt[g] = tick(extract_pair(rows + g * ROW_WORDS, pp), sig3[g]);
+      thr[g] = threshold(sig3[g]);
+      neg = addmin2(sig3[g], 0xFFFDFFFDu, neg);
+      if constexpr (DUMP) {
+        ped_out[g] = median();
+        wav_out[g] = filt[g];
+      }
+    }
+    // conservative quiet test: max filter output of the group vs min threshold of the group
+    const uint32_t mx = __vimax3_s16x2(__vimax3_s16x2(filt[0], filt[1], filt[2]), filt[3], 0u);
+    const uint32_t mn = __vimin3_s16x2(__vimin3_s16x2(thr[0], thr[1], thr[2]), thr[3], thr[3]);
+    if (ctx.p->debug_flags & 1u)
+      neg = 0xFFFFFFFFu;
+    const uint32_t busy = gt2_mask_bf16(mx, mn) | prev | neg;
+    if (__builtin_expect(!__any_sync(0xFFFFFFFFu, busy != 0u), 1))
+      return; // nothing but the trackers and the filter moves outside hits
+    if (__any_sync(0xFFFFFFFFu, neg != 0u)) { // rare: carries between the positions of a 64-bit lane (H7)
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const uint32_t th = iqr_threshold_exact(add2(sig3[g], 0xFFFDFFFDu), (ctx.chan0 >> 1) & 31u, int(mult), thr_cfg);
+        hit_update<true>(filt[g], th, ctx, t0 + g);
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        hit_update<false>(filt[g], thr[g], ctx, t0 + g);
+    }
+    __syncwarp();
+    if (ctx.stage->nearly_full())
+      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
   }
 };
 
@@ -671,7 +954,7 @@ wibeth_kernel(const KernelParams p)
         }
         constexpr int G = 4;
         static_assert(CHUNK_TICKS % G == 0, "group must divide the chunk");
-        constexpr int kGroupUnroll = SWTPG_GROUP_UNROLL;
+        constexpr int kGroupUnroll = Algo::kGroupUnroll;
 #pragma unroll kGroupUnroll
         for (int tt = 0; tt < CHUNK_TICKS; tt += G) {
           uint32_t ped[G], wav[G];
@@ -699,10 +982,11 @@ wibeth_kernel(const KernelParams p)
       }
     }
 
-    hits.flush_wibeth(p.sink, link_base, link, lane); // records carry unit indices of THIS link
-    algo.store(st, lane);
+    Algo::template flush<false>(hits, p.sink, link_base, link, lane); // records carry unit indices of THIS link
+    const uint32_t k_end = algo.phase_after(n_units * 64u);
+    algo.store(st, lane, k_end);
     if (lane == 0)
-      p.group_flags[link] = kFlagInitialized | (algo.phase_after(n_units * 64u) << 8);
+      p.group_flags[link] = kFlagInitialized | (k_end << 8);
   }
 }
 
@@ -822,7 +1106,7 @@ wib2_kernel(const KernelParams p)
 #pragma unroll
       for (int tt = 0; tt < 12; tt += G) {
         uint32_t ped[G], wav[G];
-        algo.template group<G, DUMP, kWib2FrameWords>(rows + tt * kWib2FrameWords, pp, ctx, tt, ped, wav);
+        algo.template group<G, DUMP, kWib2FrameWords, true>(rows + tt * kWib2FrameWords, pp, ctx, tt, ped, wav);
         if constexpr (DUMP) {
 #pragma unroll
           for (int g = 0; g < G; ++g) {
@@ -852,11 +1136,11 @@ wib2_kernel(const KernelParams p)
       }
     }
 
-    if constexpr (std::is_same<Algo, PackedSimpleWib2>::value)
-      hits.flush_wib2(p.sink, link_base, link, lane);
-    algo.store(st, lane);
+    Algo::template flush<true>(hits, p.sink, link_base, link, lane);
+    const uint32_t k_end = algo.phase_after(n_units * 12u);
+    algo.store(st, lane, k_end);
     if (lane == 0)
-      p.group_flags[group] = kFlagInitialized | (algo.phase_after(n_units * 12u) << 8);
+      p.group_flags[group] = kFlagInitialized | (k_end << 8);
   }
 }
 
