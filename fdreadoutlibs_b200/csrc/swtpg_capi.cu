@@ -62,7 +62,7 @@ struct swtpg_handle
   swtpg_config cfg{};
   uint32_t unit_bytes = 0, channels = 0, ticks = 0, groups_per_link = 0, n_groups = 0;
   uint32_t tp_capacity = 0;
-  bool fast_simple = false, fast_fir = false;
+  bool fast_simple = false, fast_fir = false, fast_rs = false;
   bool started = false;
 
   cudaStream_t stream = nullptr; // batch path + all kernels (state is carried batch to batch: kernels are ordered)
@@ -266,8 +266,11 @@ launch(const swtpg_handle* h, const KernelParams& kp, cudaStream_t s)
       case SWTPG_ALGO_SIMPLE_THRESHOLD:
         return h->fast_simple ? launch_wibeth<PackedSimpleWibEth, DUMP>(kp, s)
                               : launch_wibeth<ScalarAlgo<SWTPG_ALGO_SIMPLE_THRESHOLD, false>, DUMP>(kp, s);
-      case SWTPG_ALGO_ABS_RS: return launch_wibeth<ScalarAlgo<SWTPG_ALGO_ABS_RS, false>, DUMP>(kp, s);
-      case SWTPG_ALGO_STANDARD_RS: return launch_wibeth<ScalarAlgo<SWTPG_ALGO_STANDARD_RS, false>, DUMP>(kp, s);
+      case SWTPG_ALGO_ABS_RS:
+        return h->fast_rs ? launch_wibeth<PackedRsWibEth<false>, DUMP>(kp, s) : launch_wibeth<ScalarAlgo<SWTPG_ALGO_ABS_RS, false>, DUMP>(kp, s);
+      case SWTPG_ALGO_STANDARD_RS:
+        return h->fast_rs ? launch_wibeth<PackedRsWibEth<true>, DUMP>(kp, s)
+                          : launch_wibeth<ScalarAlgo<SWTPG_ALGO_STANDARD_RS, false>, DUMP>(kp, s);
       case SWTPG_ALGO_FIR_IQR:
         return h->fast_fir ? launch_wibeth<PackedFirIqr, DUMP>(kp, s) : launch_wibeth<ScalarAlgo<SWTPG_ALGO_FIR_IQR, false>, DUMP>(kp, s);
     }
@@ -630,6 +633,8 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
   h->fast_simple = cfg->algorithm == SWTPG_ALGO_SIMPLE_THRESHOLD && cfg->threshold <= 32767 &&
                    (wib2 || (cfg->frugal_acc_limit >= 1 && cfg->frugal_acc_limit <= 1000)) && getenv("SWTPG_FORCE_SCALAR") == nullptr;
 
+  h->fast_rs = !wib2 && (cfg->algorithm == SWTPG_ALGO_ABS_RS || cfg->algorithm == SWTPG_ALGO_STANDARD_RS) && cfg->threshold <= 32767 &&
+               cfg->frugal_acc_limit >= 1 && cfg->frugal_acc_limit <= 1000 && getenv("SWTPG_FORCE_SCALAR") == nullptr;
   // Packed FIR fast path validity (see PackedFirIqr): binomial taps, and (sigmaMax + 3) * multiplier * threshold < 2^16
   {
     static const int16_t kBinomial[8] = { 1, 6, 15, 20, 15, 6, 1, 0 };

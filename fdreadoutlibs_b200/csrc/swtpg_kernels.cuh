@@ -586,6 +586,154 @@ struct PackedSimpleWib2 : PackedSimpleWibEth
 };
 
 // =====================================================================================================================
+// Packed fast path: WIBEth running-sum finders — AbsRS (wibeth/tpg/ProcessAbsRSAVX2.hpp:21-345) and StandardRS
+// (wibeth/tpg/ProcessStandardRSAVX2.hpp:23-). Per tick and channel:
+//   s' = raw - median                                     (frugal pedestal as in SimpleThreshold)
+//   sum = RS * R + |s'| * scale      (AbsRS, :137-150)    or   RS * R + s'   (StandardRS, :140-144)   — mullo / add, mod 2^16
+//   RS  = mulhrs(sum, 32768/10)                           (UtilsAVX2.hpp:77-81: round(sum / 10))
+//   RS -= median_RS  after a second frugal update on RS   (:152-159)
+//   threshold on RS; charge accumulates s' with signed saturation (:204); peak tracking on s' as in SimpleThreshold.
+// The two 16-bit multiplies are done per half with 32-bit IMADs (only the low 16 bits of a product are used, so the packed
+// register itself is the low-half operand and no sign extension is needed); mulhrs is one IMAD.WIDE per half on the value
+// shifted into the top half, with the rounding constant as the 64-bit addend. |RS| <= 3277 by construction, so the RS
+// median lives in [-3277, 3277] and the packed sign tests cannot overflow.
+// Validity: 1 <= L <= 1000, 0 <= threshold <= 32767; any per-channel memory factor and any scale factor.
+// =====================================================================================================================
+template<bool STANDARD>
+struct PackedRsWibEth : PackedSimpleWibEth
+{
+  static constexpr int kGroupUnroll = 1;
+  uint32_t RS1, MRq, AR;     // RS + 1 (carried value, after median subtraction); 1 - median_RS; (acc_RS - 1) as fp16 subnormal
+  int f_lo, f_hi, nf_lo, nf_hi, scale;
+
+  __device__ __forceinline__ void configure(const KernelParams& p)
+  {
+    PackedSimpleWibEth::configure(p);
+    // RS - median_RS is in [-6554, 6554]: a larger threshold is never exceeded (and stays inside the comparator's range)
+    uint32_t th = p.threshold > 6555u ? 6555u : p.threshold;
+    th += 1u;
+    thr1 = th | (th << 16);
+    scale = p.rs_scale;
+  }
+  __device__ __forceinline__ void load(const uint32_t* st, uint32_t lane, uint32_t flags)
+  {
+    PackedSimpleWibEth::load(st, lane, flags);
+    RS1 = add2(st[SV_RS * 32 + lane], 0x00010001u);
+    MRq = add2(~st[SV_MED_RS * 32 + lane], 0x00020002u);
+    AR = acc_to_reg(st[SV_ACC_RS * 32 + lane]);
+    const uint32_t f = st[SV_RS_FACTOR * 32 + lane];
+    f_lo = lo16s(f);
+    f_hi = hi16s(f);
+    nf_lo = -f_lo; // RS * R = (RS + 1) * R - R: the "- R" rides on an IMAD addend
+    nf_hi = -f_hi;
+  }
+  __device__ __forceinline__ void store(uint32_t* st, uint32_t lane, uint32_t k) const
+  {
+    PackedSimpleWibEth::store(st, lane, k);
+    st[SV_RS * 32 + lane] = add2(RS1, 0xFFFFFFFFu);
+    st[SV_MED_RS * 32 + lane] = add2(~MRq, 0x00020002u);
+    st[SV_ACC_RS * 32 + lane] = acc_from_reg(AR);
+  }
+  // frugal update of (Mq_, A_) = (1 - median, accumulator) with sample S; returns S - median + 1 with the updated median
+  __device__ __forceinline__ uint32_t frugal(uint32_t S, uint32_t& Mq_, uint32_t& A_) const
+  {
+    const uint32_t sg1 = addclamp2(S, Mq_, 0x00020002u);
+#if SWTPG_FLOAT_ACC
+    const uint32_t T = hadd2_bits(A_, sg1);
+    const uint32_t upm = eq2_mask(T, cUp);
+    const uint32_t dn1 = hfma2_sat_bits(T, 0xBC00BC00u, cDn);
+    A_ = hfma2_bits(ne2_abs_one(T, cUp), T, 0x80018001u);
+    Mq_ = add2(add2(Mq_, upm), dn1);
+#else
+    const uint32_t T = add2(A_, sg1);
+    const uint32_t up = addmax2(T, cUp, 0u), dn = addmin2(T, cDn, 0u), upm = up * 0xFFFFu;
+    A_ = add2(T, 0xFFFFFFFFu) & ~(upm | dn);
+    Mq_ = add2(Mq_, upm | (dn & 0x00010001u));
+#endif
+    return add2(S, Mq_);
+  }
+  // mulhrs(v, 3276) of the 16-bit value sitting in the TOP half of `top` (low half ignored), sign-extended result
+  static __device__ __forceinline__ int mulhrs_top(uint32_t top)
+  {
+    // (v * 65536) * 6552 + 2^31 = (v * 3276 + 2^14) * 2^17: bits 32.. hold floor((v * 3276 + 2^14) / 2^15) = mulhrs
+    const long long w = (long long)(int)(top & 0xFFFF0000u) * 6552ll + 0x80000000ll;
+    return int(w >> 32);
+  }
+  // One tick: sp1 = s' + 1 (pedestal-subtracted sample, biased), returns RS - median_RS + 1
+  __device__ __forceinline__ uint32_t rs_step(uint32_t sp1)
+  {
+    const uint32_t x = add2(sp1, 0xFFFFFFFFu);
+    uint32_t lo, hi;
+    if constexpr (STANDARD) {
+      lo = uint32_t(int(RS1) * f_lo + int(x) + nf_lo);                       // low 16 bits: RS * R + s'
+      hi = uint32_t(int(RS1 >> 16) * f_hi + int(x >> 16) + nf_hi);
+    } else {
+      const uint32_t ax = max2(x, neg2(x));                                  // |s'| (s' > -32768)
+      lo = uint32_t(int(RS1) * f_lo + (int(ax) * scale + nf_lo));            // low 16 bits: RS * R + |s'| * scale
+      hi = uint32_t(int(RS1 >> 16) * f_hi + (int(ax >> 16) * scale + nf_hi));
+    }
+    const int r_lo = mulhrs_top(lo << 16), r_hi = mulhrs_top(hi << 16);
+    const uint32_t rs = __byte_perm(uint32_t(r_lo), uint32_t(r_hi), 0x5410);  // pack the two low halves
+    RS1 = frugal(rs, MRq, AR);                                               // second pedestal, on the running sum
+    return RS1;
+  }
+
+  __device__ __forceinline__ void hit_update(uint32_t sp1, uint32_t lv1, const TickCtx& ctx, int t)
+  {
+    const uint32_t over = gt2_mask_nonneg(lv1, thr1);
+    const uint32_t left = prev & ~over;
+    const uint32_t xm = add2(sp1, 0xFFFFFFFFu) & over;
+    C = pack2(sat16(lo16s(C) + lo16s(xm)), sat16(hi16s(C) + hi16s(xm)));    // adds_epi16 (:204): s' may be negative here
+    const uint32_t gtp = gt2_mask_nonneg(sp1, PK1);                          // un-gated peak tracking on s'
+    PK1 = max2(PK1, sp1);
+    PTn = (Tn & gtp) | (PTn & ~gtp);
+    Tn = addmax2(Tn, over, 0x80018001u);
+    prev = over;
+    if (left != 0u) {
+      const uint32_t T = neg2(Tn), PK = add2(PK1, 0xFFFFFFFFu), PT = neg2(PTn);
+      if ((left & 0xFFFFu) && (C & 0xFFFFu))
+        ctx.stage->push(ctx.chan0, ctx.unit, uint32_t(t), C & 0xFFFFu, T & 0xFFFFu, PK & 0xFFFFu, PT & 0xFFFFu);
+      if ((left >> 16) && (C >> 16))
+        ctx.stage->push(ctx.chan0 + 1u, ctx.unit, uint32_t(t), C >> 16, T >> 16, PK >> 16, PT >> 16);
+      C &= ~left;
+      Tn &= ~left;
+      PK1 = (PK1 & ~left) | (left & 0x00010001u);
+      PTn &= ~left;
+    }
+  }
+
+  template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
+  __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
+                                        uint32_t* wav_out)
+  {
+    static_assert(G == 4, "max trees below are written for 4 ticks");
+    uint32_t sp[G], lv[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      sp[g] = frugal(extract_pair(rows + g * ROW_WORDS, pp), Mq, A);
+      lv[g] = rs_step(sp[g]);
+      if constexpr (DUMP) {
+        ped_out[g] = median();
+        wav_out[g] = add2(lv[g], 0xFFFFFFFFu);
+      }
+    }
+    const uint32_t mxl = __vimax3_s16x2(__vimax3_s16x2(lv[0], lv[1], lv[2]), lv[3], lv[3]);
+    const uint32_t busy = gt2_mask_nonneg(mxl, thr1) | prev;
+    if (__builtin_expect(!__any_sync(0xFFFFFFFFu, busy != 0u), 1)) {
+      // outside hits only the un-gated peak tracker moves (peak_time = tover = 0 is rewritten with 0)
+      PK1 = __vimax3_s16x2(__vimax3_s16x2(sp[0], sp[1], sp[2]), sp[3], PK1);
+      return;
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      hit_update(sp[g], lv[g], ctx, t0 + g);
+    __syncwarp();
+    if (ctx.stage->nearly_full())
+      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
+  }
+};
+
+// =====================================================================================================================
 // Packed fast path: FIR matched filter + IQR threshold (wib2/tpg/ProcessAVX2FIR.hpp:21-314), on either frame layout.
 // Three frugal trackers per channel (quartiles on the lanes below / above the OLD median, then the median, all with
 // L = 10, :108-125), sigma = min(q75 - q25, sigmaMax), s' = min(s - median, adcMax), the 7-tap filter over the ring
