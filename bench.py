@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--pulse-rate", type=float, default=0.02, help="pulses per channel per 64 ticks")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the FIR / running-sum / WIB2 / stress side measurements")
     return ap.parse_args()
 
 
@@ -297,6 +298,47 @@ def main():
                       "kernel_ms": min(ms1[1:]), "real_time_multiple": s1 / APA_SAMPLES_PER_S}
         del d1
 
+    # --- the other kernels of the path, same box, same run (rank 0): FIR + IQR, running sums, WIB2, high-occupancy stress ---
+    others = None
+    if rank == 0 and not args.no_variants:
+        others = {}
+
+        def timed(fmt, algorithm, thr, d_ptr, links, units, unit_bytes, samples_per_unit, state_bytes, tp_cap=1 << 22):
+            with S.TPGenerator(links, units, fmt=fmt, algorithm=algorithm, threshold=thr, device=local_rank, tp_capacity=tp_cap) as g:
+                g.start()
+                for _ in range(3):
+                    g.process_device(d_ptr, units)
+                g.fetch_count()
+                ms = []
+                for _ in range(5):
+                    g.process_device(d_ptr, units)
+                    ntp = g.fetch_count()
+                    ms.append(g.last_kernel_ms())
+                k = sum(ms) / len(ms)
+                by = links * units * unit_bytes + ntp * TP_BYTES + 2 * state_bytes * links * (256 if fmt == "wib2" else 64)
+                return {"value": links * units * samples_per_unit / (k * 1e-3), "unit": UNIT, "kernel_ms": k, "tps_per_step": ntp,
+                        "roofline": {"bound": "hbm", "achieved": by / (k * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": by / (k * 1e-3) / 1e9 / hbm_peak}}
+
+        # BASELINE config[1]/[2] data already resident (SimpleThreshold workload): FIR + IQR matched filter, AbsRS, StandardRS
+        others["wibeth_fir_iqr_thr5"] = timed("wibeth", "FIR", 5, d_frames.data_ptr(), n_links, frames, FRAME_BYTES, SAMPLES_PER_FRAME, 38)
+        others["wibeth_abs_rs"] = timed("wibeth", "AbsRS", args.threshold, d_frames.data_ptr(), n_links, frames, FRAME_BYTES, SAMPLES_PER_FRAME, 22)
+        others["wibeth_standard_rs"] = timed("wibeth", "StandardRS", args.threshold, d_frames.data_ptr(), n_links, frames, FRAME_BYTES,
+                                             SAMPLES_PER_FRAME, 22)
+        # BASELINE config[3]: high-occupancy stress — threshold 8 ADC (1.6 sigma), dense pulses
+        S.gen_wibeth_device(S.gen_params(4, 0.5), d_frames.data_ptr(), n_links, frames, link0=link0)
+        torch.cuda.synchronize()
+        others["wibeth_simple_stress_thr8"] = timed("wibeth", "SimpleThreshold", 8, d_frames.data_ptr(), n_links, frames, FRAME_BYTES,
+                                                    SAMPLES_PER_FRAME, 14, tp_cap=1 << 25)
+        # BASELINE config[4]: legacy WIB2 superchunks (256 channels x 12 ticks), SimpleThreshold and FIR + IQR
+        w_links, w_units = n_links // 4, 340
+        d_w = torch.empty(w_links * w_units * 5664, dtype=torch.uint8, device="cuda")
+        S.gen_wib2_device(gp, d_w.data_ptr(), w_links, w_units)
+        torch.cuda.synchronize()
+        others["wib2_simple"] = timed("wib2", "SimpleThreshold", args.threshold, d_w.data_ptr(), w_links, w_units, 5664, 256 * 12, 10)
+        others["wib2_fir_iqr_thr5"] = timed("wib2", "FIR", 5, d_w.data_ptr(), w_links, w_units, 5664, 256 * 12, 38)
+        del d_w
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _, cpu = cpu_reference_run(args.threshold, steps=5, warmup=1, pulse_rate=args.pulse_rate)
@@ -316,6 +358,7 @@ def main():
             "cpu_baseline": cpu,
             "e2e": e2e,
             "single_apa": single,
+            "other_kernels": others,
             "gpu_launches": args.steps,
             "clocks": clocks.summary(),
         }

@@ -594,9 +594,8 @@ struct PackedSimpleWib2 : PackedSimpleWibEth
 //   RS -= median_RS  after a second frugal update on RS   (:152-159)
 //   threshold on RS; charge accumulates s' with signed saturation (:204); peak tracking on s' as in SimpleThreshold.
 // The two 16-bit multiplies are done per half with 32-bit IMADs (only the low 16 bits of a product are used, so the packed
-// register itself is the low-half operand and no sign extension is needed); mulhrs is one IMAD.WIDE per half on the value
-// shifted into the top half, with the rounding constant as the 64-bit addend. |RS| <= 3277 by construction, so the RS
-// median lives in [-3277, 3277] and the packed sign tests cannot overflow.
+// register itself is the low-half operand and no sign extension is needed); mulhrs is sign-extend + IMAD + shift per half.
+// |RS| <= 3277 by construction, so the RS median lives in [-3277, 3277] and the packed sign tests cannot overflow.
 // Validity: 1 <= L <= 1000, 0 <= threshold <= 32767; any per-channel memory factor and any scale factor.
 // =====================================================================================================================
 template<bool STANDARD>
@@ -652,12 +651,11 @@ struct PackedRsWibEth : PackedSimpleWibEth
 #endif
     return add2(S, Mq_);
   }
-  // mulhrs(v, 3276) of the 16-bit value sitting in the TOP half of `top` (low half ignored), sign-extended result
-  static __device__ __forceinline__ int mulhrs_top(uint32_t top)
+  // _mm256_mulhrs_epi16(v, 3276) for the 16-bit value in the LOW half of `w` (upper half ignored): ((v * 3276 >> 14) + 1) >> 1
+  // = (v * 3276 + 2^14) >> 15, which fits 32-bit arithmetic (|v * 3276| < 2^27).
+  static __device__ __forceinline__ int mulhrs_low(uint32_t w)
   {
-    // (v * 65536) * 6552 + 2^31 = (v * 3276 + 2^14) * 2^17: bits 32.. hold floor((v * 3276 + 2^14) / 2^15) = mulhrs
-    const long long w = (long long)(int)(top & 0xFFFF0000u) * 6552ll + 0x80000000ll;
-    return int(w >> 32);
+    return (int(int16_t(uint16_t(w))) * 3276 + 16384) >> 15;
   }
   // One tick: sp1 = s' + 1 (pedestal-subtracted sample, biased), returns RS - median_RS + 1
   __device__ __forceinline__ uint32_t rs_step(uint32_t sp1)
@@ -672,7 +670,7 @@ struct PackedRsWibEth : PackedSimpleWibEth
       lo = uint32_t(int(RS1) * f_lo + (int(ax) * scale + nf_lo));            // low 16 bits: RS * R + |s'| * scale
       hi = uint32_t(int(RS1 >> 16) * f_hi + (int(ax >> 16) * scale + nf_hi));
     }
-    const int r_lo = mulhrs_top(lo << 16), r_hi = mulhrs_top(hi << 16);
+    const int r_lo = mulhrs_low(lo), r_hi = mulhrs_low(hi);
     const uint32_t rs = __byte_perm(uint32_t(r_lo), uint32_t(r_hi), 0x5410);  // pack the two low halves
     RS1 = frugal(rs, MRq, AR);                                               // second pedestal, on the running sum
     return RS1;
@@ -683,7 +681,14 @@ struct PackedRsWibEth : PackedSimpleWibEth
     const uint32_t over = gt2_mask_nonneg(lv1, thr1);
     const uint32_t left = prev & ~over;
     const uint32_t xm = add2(sp1, 0xFFFFFFFFu) & over;
-    C = pack2(sat16(lo16s(C) + lo16s(xm)), sat16(hi16s(C) + hi16s(xm)));    // adds_epi16 (:204): s' may be negative here
+    // adds_epi16 (:204); s' may be negative here. Packed wrapping add, then repair the (rare) halves that overflowed:
+    // overflow <=> both operands have the same sign and the sum's sign differs.
+    const uint32_t Cw = add2(C, xm);
+    const uint32_t ovf = ~(C ^ xm) & (C ^ Cw) & 0x80008000u;
+    if (__builtin_expect(ovf != 0u, 0))
+      C = pack2(sat16(lo16s(C) + lo16s(xm)), sat16(hi16s(C) + hi16s(xm)));
+    else
+      C = Cw;
     const uint32_t gtp = gt2_mask_nonneg(sp1, PK1);                          // un-gated peak tracking on s'
     PK1 = max2(PK1, sp1);
     PTn = (Tn & gtp) | (PTn & ~gtp);

@@ -115,6 +115,49 @@ def test_wib2_against_oracle_with_state_and_dumps(algorithm, thr):
                 assert (sg[f] == so[f]).all(), f"link {l} state field {f}"
 
 
+@pytest.mark.parametrize("fmt,algorithm,thr,kw", [
+    ("wibeth", "SimpleThreshold", 100, {}), ("wibeth", "AbsRS", 100, dict(rs_memory_factor=8, rs_scale_factor=5)),
+    ("wibeth", "AbsRS", 50, dict(rs_memory_factor=9, rs_scale_factor=10)), ("wibeth", "StandardRS", 100, dict(rs_memory_factor=7, rs_scale_factor=2)),
+    ("wibeth", "FIR", 5, {}), ("wib2", "SimpleThreshold", 100, {}), ("wib2", "FIR", 5, {})])
+def test_extreme_amplitudes_wrap_and_saturate_like_the_reference(fmt, algorithm, thr, kw):
+    """Pulses up to the full 14-bit range on low pedestals, dense, bipolar: charge wraps (SimpleThreshold, H3) or saturates
+    (RS / WIB2 / FIR), |s'| * scale and RS * R overflow 16 bits, the FIR sum wraps, the input clamp at adcMax and the
+    sigma clamp at sigmaMax engage, hits span many frames. The packed fast paths must wrap / saturate bit for bit like the
+    reference arithmetic (oracle); per-channel RS memory factors include 0 and odd values."""
+    n_links, n_units, step = 2, 24 if fmt == "wibeth" else 120, 8 if fmt == "wibeth" else 40
+    p = S.gen_params(71, 0.9, amp_min=3000, amp_max=15000, hw_min=6, hw_max=16, ped_base=300, ped_step=3, noise_q8=40 * 256)
+    units = (S.gen_wib2_host if fmt == "wib2" else S.gen_wibeth_host)(p, n_links, n_units)
+    cfg = B.make_config(fmt=fmt, algorithm=S.ALGORITHMS[algorithm], threshold=thr, **kw)
+    nch = 256 if fmt == "wib2" else 64
+    factors = (np.arange(n_links * nch, dtype=np.uint16) * 7 % 13).reshape(n_links, nch)  # 0..12, incl. 0
+    oracles = [B.Oracle(cfg, link_id=l) for l in range(n_links)]
+    want, peds, wavs = [], [], []
+    for l in range(n_links):
+        if "RS" in algorithm:
+            oracles[l].set_memory_factor(factors[l])
+        t, pd, w = oracles[l].process(units[l], dump=True, cap=1 << 20)
+        want.append(t), peds.append(pd), wavs.append(w)
+    got, gp, gw = [], [], []
+    with S.TPGenerator(n_links, step, fmt=fmt, algorithm=algorithm, threshold=thr, tp_capacity=1 << 21, **kw) as g:
+        if "RS" in algorithm:
+            g.set_rs_memory_factor(factors)
+        g.start()
+        for u in range(0, n_units, step):
+            t, pd, w = g.process_host(np.ascontiguousarray(units[:, u:u + step]), debug=True, cap=1 << 21)
+            got.append(t), gp.append(pd), gw.append(w)
+        assert (np.concatenate(gp, axis=1) == np.stack(peds)).all(), "pedestal dump"
+        assert (np.concatenate(gw, axis=1) == np.stack(wavs)).all(), "waveform dump"
+        assert_same_tps(np.concatenate(got), np.concatenate(want), f"{fmt} {algorithm}")
+        for l in range(n_links):
+            sg, so = g.dump_state(l), oracles[l].state()
+            for f in ("pedestal", "accum", "prev_was_over", "hit_charge", "hit_tover"):
+                assert (sg[f] == so[f]).all(), f"link {l} state field {f}"
+    allt = np.concatenate(want)
+    assert allt.size > 200
+    if algorithm == "SimpleThreshold" and fmt == "wibeth":
+        assert (allt["adc_integral"] > 40000).any(), "no wrapped charge in the sample: the case does not test H3"
+
+
 def test_wib2_many_links_ragged_and_streaming():
     """More links than one wave of CTAs would be on a small grid, ragged unit counts, then the streaming entry points."""
     n_links, stride = 9, 8
