@@ -611,6 +611,121 @@ WIB2FrameProcessor::process_swtpg_hits(const swtpg_tp* tps, size_t n)
   m_tpg_hits_count += nhits;
 }
 
+// ---- TPCTPRequestHandler ----------------------------------------------------------------------------------------------
+void
+TPCTPRequestHandler::conf(const ReadoutModelConf& c)
+{
+  m_source_id = c.source_id;
+  m_tp_set_sender_sleep_us = int(1000000 / std::max<uint32_t>(1, c.tpset_transmission_rate_hz));
+  m_ts_set_sender_offset_ticks = c.tpset_min_latency_ticks;
+  m_tardy_tp_quiet_time_at_start_sec = c.tardy_tp_quiet_time_at_start_sec;
+}
+
+void
+TPCTPRequestHandler::start(uint32_t run_number)
+{
+  m_new_tps = 0;
+  m_new_tpsets = 0;
+  m_new_tps_in_tpsets_send_failed = 0;
+  m_new_tpsets_send_failed = 0;
+  m_new_tps_suppressed_tardy = 0;
+  m_new_heartbeats = 0;
+  m_latency_buffer.clear();
+  m_run_number = run_number;
+  m_cutoff_timestamp.store(0);
+  m_first_cycle = true;
+  m_start_win_ts = 0;
+  m_next_tpset_seqno = 0;
+  m_run_start_timepoint = std::chrono::high_resolution_clock::now();
+}
+
+void
+TPCTPRequestHandler::stop()
+{
+  m_cutoff_timestamp.store(0);
+}
+
+void
+TPCTPRequestHandler::get_info(TPRequestHandlerInfo& info)
+{
+  info.num_tps_sent = m_new_tps.exchange(0);
+  info.num_tpsets_sent = m_new_tpsets.exchange(0);
+  info.num_tps_in_tpsets_send_failed = m_new_tps_in_tpsets_send_failed.exchange(0);
+  info.num_tpsets_send_failed = m_new_tpsets_send_failed.exchange(0);
+  info.num_tps_suppressed_tardy = m_new_tps_suppressed_tardy.exchange(0);
+  info.num_heartbeats = m_new_heartbeats.exchange(0);
+}
+
+void
+TPCTPRequestHandler::report_tardy_packet(const TriggerPrimitiveTypeAdapter&, int64_t)
+{
+  ++m_new_tps_suppressed_tardy;
+  const auto now = std::chrono::high_resolution_clock::now();
+  if (std::chrono::duration_cast<std::chrono::seconds>(now - m_run_start_timepoint).count() > m_tardy_tp_quiet_time_at_start_sec)
+    ++m_late_warnings; // reference: ers::warning(DataPacketArrivedTooLate), muted during the quiet time after start (:88-96)
+}
+
+bool
+TPCTPRequestHandler::receive(TriggerPrimitiveTypeAdapter&& tp)
+{
+  const uint64_t cutoff = get_cutoff_timestamp();
+  if (tp.get_first_timestamp() < cutoff) {
+    report_tardy_packet(tp, int64_t(cutoff - tp.get_first_timestamp()));
+    return false;
+  }
+  m_latency_buffer.insert(std::move(tp));
+  return true;
+}
+
+void
+TPCTPRequestHandler::pop_older_than(uint64_t ts)
+{
+  while (!m_latency_buffer.empty() && m_latency_buffer.begin()->get_first_timestamp() < ts)
+    m_latency_buffer.erase(m_latency_buffer.begin());
+}
+
+bool
+TPCTPRequestHandler::send_tp_sets_once()
+{
+  if (m_latency_buffer.empty())
+    return false;
+  const uint64_t newest_ts = m_latency_buffer.rbegin()->get_first_timestamp();
+  const uint64_t oldest_ts = m_latency_buffer.begin()->get_first_timestamp();
+  if (m_first_cycle) {
+    m_start_win_ts = oldest_ts;
+    m_first_cycle = false;
+  }
+  if (!(newest_ts - m_start_win_ts > m_ts_set_sender_offset_ticks))
+    return false;
+  const uint64_t end_win_ts = newest_ts - m_ts_set_sender_offset_ticks;
+  // get_fragment_pieces(start, end): every element with start <= time_start < end, in (time_start, channel) order
+  TPSet tpset;
+  TriggerPrimitiveTypeAdapter lo;
+  lo.tp.time_start = m_start_win_ts;
+  lo.tp.channel = 0;
+  for (auto it = m_latency_buffer.lower_bound(lo); it != m_latency_buffer.end() && it->get_first_timestamp() < end_win_ts; ++it)
+    tpset.objects.push_back(it->tp);
+  const size_t num_tps = tpset.objects.size();
+  tpset.run_number = m_run_number;
+  tpset.type = num_tps > 0 ? TPSet::Type::kPayload : TPSet::Type::kHeartbeat;
+  tpset.origin = m_source_id;
+  tpset.start_time = num_tps ? tpset.objects.front().time_start : m_start_win_ts;
+  tpset.end_time = num_tps ? tpset.objects.back().time_start : end_win_ts;
+  tpset.seqno = m_next_tpset_seqno++;
+  m_cutoff_timestamp.store(tpset.end_time);
+  if (!m_tpset_sink || !m_tpset_sink(std::move(tpset))) {
+    m_new_tps_in_tpsets_send_failed += num_tps; // reference: ers::warning(FailedToSendTPSet)
+    ++m_new_tpsets_send_failed;
+  } else {
+    m_new_tps += num_tps;
+    ++m_new_tpsets;
+  }
+  if (num_tps == 0)
+    m_new_heartbeats++;
+  m_start_win_ts = end_win_ts; // remember what we sent for the next loop
+  return true;
+}
+
 } // namespace host
 } // namespace swtpg
 
@@ -833,6 +948,106 @@ swtpg_host_register_channel_map(swtpg_host* h, uint32_t link, uint32_t* out64)
     return;
   for (int p = 0; p < 64; ++p)
     out64[p] = h->eth[link]->handler()->register_channel_map[size_t(p)];
+}
+
+// ---- TPCTPRequestHandler harness ---------------------------------------------------------------------------------------------
+struct swtpg_host_tpsets
+{
+  TPCTPRequestHandler handler;
+  std::vector<TPSet> sent;
+  uint32_t sink_capacity = 0;
+};
+struct swtpg_host_tpset_hdr
+{
+  uint64_t seqno, start_time, end_time;
+  uint32_t run_number, origin, type, n_objects;
+};
+
+swtpg_host_tpsets*
+swtpg_host_tpsets_create(uint32_t source_id, uint32_t rate_hz, uint64_t min_latency_ticks, uint32_t run_number, uint32_t sink_capacity)
+{
+  auto* h = new swtpg_host_tpsets;
+  h->sink_capacity = sink_capacity;
+  h->handler.init([h](TPSet&& s) {
+    if (h->sink_capacity && h->sent.size() >= h->sink_capacity)
+      return false;
+    h->sent.push_back(std::move(s));
+    return true;
+  });
+  ReadoutModelConf c;
+  c.source_id = source_id;
+  c.tpset_transmission_rate_hz = rate_hz;
+  c.tpset_min_latency_ticks = min_latency_ticks;
+  h->handler.conf(c);
+  h->handler.start(run_number);
+  return h;
+}
+
+void
+swtpg_host_tpsets_destroy(swtpg_host_tpsets* h)
+{
+  delete h;
+}
+
+// feeds n harness TP records (e.g. taken from a frame processor's tp_out); returns how many were accepted (not tardy)
+size_t
+swtpg_host_tpsets_receive(swtpg_host_tpsets* h, const swtpg_host_tp* tps, size_t n)
+{
+  size_t ok = 0;
+  for (size_t i = 0; i < n; ++i) {
+    TriggerPrimitiveTypeAdapter a;
+    a.tp.time_start = tps[i].time_start;
+    a.tp.time_peak = tps[i].time_peak;
+    a.tp.time_over_threshold = tps[i].time_over_threshold;
+    a.tp.channel = tps[i].channel;
+    a.tp.adc_integral = tps[i].adc_integral;
+    a.tp.adc_peak = tps[i].adc_peak;
+    a.tp.detid = tps[i].detid;
+    a.tp.type = TriggerPrimitive::Type(tps[i].type);
+    a.tp.algorithm = TriggerPrimitive::Algorithm(tps[i].algorithm);
+    ok += h->handler.receive(std::move(a)) ? 1 : 0;
+  }
+  return ok;
+}
+
+int
+swtpg_host_tpsets_cycle(swtpg_host_tpsets* h)
+{
+  return h->handler.send_tp_sets_once() ? 1 : 0;
+}
+
+uint64_t
+swtpg_host_tpsets_cutoff(swtpg_host_tpsets* h)
+{
+  return h->handler.get_cutoff_timestamp();
+}
+
+size_t
+swtpg_host_tpsets_count(swtpg_host_tpsets* h)
+{
+  return h->sent.size();
+}
+
+// header of sent TPSet i and (if objs != NULL) its first `cap` objects
+int
+swtpg_host_tpsets_get(swtpg_host_tpsets* h, size_t i, swtpg_host_tpset_hdr* hdr, swtpg_host_tp* objs, size_t cap)
+{
+  if (i >= h->sent.size())
+    return -1;
+  const TPSet& s = h->sent[i];
+  *hdr = { s.seqno, s.start_time, s.end_time, s.run_number, s.origin, uint32_t(s.type), uint32_t(s.objects.size()) };
+  for (size_t k = 0; objs && k < std::min(cap, s.objects.size()); ++k) {
+    const TriggerPrimitive& t = s.objects[k];
+    objs[k] = { t.time_start, t.time_peak, t.time_over_threshold, t.channel, t.adc_integral, t.adc_peak, t.detid, uint32_t(t.type),
+                uint32_t(t.algorithm), t.version, t.flag };
+  }
+  return 0;
+}
+
+void
+swtpg_host_tpsets_info(swtpg_host_tpsets* h, TPRequestHandlerInfo* info)
+{
+  h->handler.get_info(*info);
 }
 
 } // extern "C"

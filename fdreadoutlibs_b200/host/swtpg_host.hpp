@@ -360,5 +360,70 @@ private:
   std::chrono::time_point<std::chrono::high_resolution_clock> m_t0;
 };
 
+// ---- downstream of the path: TPs -> time-ordered TPSets -------------------------------------------------------------------
+// trigger::TPSet as send_tp_sets fills it (src/TPCTPRequestHandler.cpp:145-165)
+struct TPSet
+{
+  enum class Type : uint32_t { kUnknown = 0, kPayload = 1, kHeartbeat = 2 };
+  uint64_t seqno = 0;
+  uint32_t run_number = 0;
+  uint32_t origin = 0; // source id
+  Type type = Type::kUnknown;
+  uint64_t start_time = 0, end_time = 0;
+  std::vector<TriggerPrimitive> objects;
+};
+// The fields of readoutlibs' ReadoutModelConf that TPCTPRequestHandler::conf reads (src/TPCTPRequestHandler.cpp:20-28)
+struct ReadoutModelConf
+{
+  uint32_t source_id = 0;
+  uint32_t tpset_transmission_rate_hz = 100;
+  uint64_t tpset_min_latency_ticks = 100000;
+  int tardy_tp_quiet_time_at_start_sec = 10;
+};
+struct TPRequestHandlerInfo // the readoutinfo fields get_info fills (:57-82)
+{
+  uint64_t num_tps_sent = 0, num_tpsets_sent = 0, num_tps_in_tpsets_send_failed = 0, num_tpsets_send_failed = 0, num_tps_suppressed_tardy = 0,
+           num_heartbeats = 0;
+};
+using TPSetSink = std::function<bool(TPSet&&)>;
+
+// include/fdreadoutlibs/TPCTPRequestHandler.hpp:57-108 + src/TPCTPRequestHandler.cpp: the consumer of the (merged) TP stream.
+// The skip-list latency buffer of readoutlibs is restated as an ordered multiset keyed like TriggerPrimitiveTypeAdapter
+// (time_start, channel); the periodic sender thread is one explicit call per cycle (send_tp_sets_once), so the windowing
+// logic can be driven deterministically. This is what bounds the GPU batching latency: a TP whose time_start is below the
+// published cut-off when it arrives is "tardy" and dropped (readoutlibs ReadoutModel consults get_cutoff_timestamp()).
+class TPCTPRequestHandler
+{
+public:
+  void init(TPSetSink tpset_out) { m_tpset_sink = std::move(tpset_out); }
+  void conf(const ReadoutModelConf& c);
+  void start(uint32_t run_number);
+  void stop();
+  void get_info(TPRequestHandlerInfo& info);
+  uint64_t get_cutoff_timestamp() const { return m_cutoff_timestamp.load(); }
+  bool supports_cutoff_timestamp() const { return true; }
+  void report_tardy_packet(const TriggerPrimitiveTypeAdapter& packet, int64_t tardy_ticks);
+  // what ReadoutModel's consumer does with an arriving TP: tardy check against the cut-off, else latency-buffer insert
+  bool receive(TriggerPrimitiveTypeAdapter&& tp);
+  // one iteration of the sender thread's loop body (:108-191); returns true if a TPSet (payload or heartbeat) was produced
+  bool send_tp_sets_once();
+  size_t occupancy() const { return m_latency_buffer.size(); }
+  // latency-buffer clean-up stand-in: forget TPs older than `ts` (the skip-list request handler pops them periodically)
+  void pop_older_than(uint64_t ts);
+
+private:
+  std::multiset<TriggerPrimitiveTypeAdapter> m_latency_buffer;
+  TPSetSink m_tpset_sink;
+  uint32_t m_source_id = 0, m_run_number = 0;
+  int m_tp_set_sender_sleep_us = 10000, m_tardy_tp_quiet_time_at_start_sec = 10;
+  uint64_t m_ts_set_sender_offset_ticks = 0, m_next_tpset_seqno = 0;
+  uint64_t m_start_win_ts = 0;
+  bool m_first_cycle = true;
+  std::atomic<uint64_t> m_new_tps{ 0 }, m_new_tpsets{ 0 }, m_new_tps_in_tpsets_send_failed{ 0 }, m_new_tpsets_send_failed{ 0 },
+    m_new_tps_suppressed_tardy{ 0 }, m_new_heartbeats{ 0 }, m_late_warnings{ 0 };
+  std::atomic<uint64_t> m_cutoff_timestamp{ 0 };
+  std::chrono::time_point<std::chrono::high_resolution_clock> m_run_start_timepoint;
+};
+
 } // namespace host
 } // namespace swtpg

@@ -33,7 +33,19 @@ class HostInfo(C.Structure):
                 ("top_channels", C.c_uint32 * 10), ("top_channel_tps", C.c_uint32 * 10), ("n_top", C.c_uint32)]
 
 
-EXPORTS = ["swtpg_host_last_error", "swtpg_host_create", "swtpg_host_destroy", "swtpg_host_start", "swtpg_host_stop", "swtpg_host_push",
+class TpSetHdr(C.Structure):
+    _fields_ = [("seqno", C.c_uint64), ("start_time", C.c_uint64), ("end_time", C.c_uint64), ("run_number", C.c_uint32),
+                ("origin", C.c_uint32), ("type", C.c_uint32), ("n_objects", C.c_uint32)]
+
+
+class TpHandlerInfo(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("num_tps_sent", "num_tpsets_sent", "num_tps_in_tpsets_send_failed", "num_tpsets_send_failed",
+                                          "num_tps_suppressed_tardy", "num_heartbeats")]
+
+
+EXPORTS = ["swtpg_host_tpsets_create", "swtpg_host_tpsets_destroy", "swtpg_host_tpsets_receive", "swtpg_host_tpsets_cycle",
+           "swtpg_host_tpsets_cutoff", "swtpg_host_tpsets_count", "swtpg_host_tpsets_get", "swtpg_host_tpsets_info",
+           "swtpg_host_last_error", "swtpg_host_create", "swtpg_host_destroy", "swtpg_host_start", "swtpg_host_stop", "swtpg_host_push",
            "swtpg_host_take_tps", "swtpg_host_get_info", "swtpg_host_error_count", "swtpg_host_misconfigurations",
            "swtpg_host_last_daq_time", "swtpg_host_register_channel_map"]
 
@@ -61,6 +73,18 @@ def host_lib():
         lib.swtpg_host_last_daq_time.restype = C.c_uint64
         lib.swtpg_host_last_daq_time.argtypes = [C.c_void_p, C.c_uint32]
         lib.swtpg_host_register_channel_map.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.swtpg_host_tpsets_create.restype = C.c_void_p
+        lib.swtpg_host_tpsets_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32]
+        lib.swtpg_host_tpsets_destroy.argtypes = [C.c_void_p]
+        lib.swtpg_host_tpsets_receive.restype = C.c_size_t
+        lib.swtpg_host_tpsets_receive.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        lib.swtpg_host_tpsets_cycle.argtypes = [C.c_void_p]
+        lib.swtpg_host_tpsets_cutoff.restype = C.c_uint64
+        lib.swtpg_host_tpsets_cutoff.argtypes = [C.c_void_p]
+        lib.swtpg_host_tpsets_count.restype = C.c_size_t
+        lib.swtpg_host_tpsets_count.argtypes = [C.c_void_p]
+        lib.swtpg_host_tpsets_get.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(TpSetHdr), C.c_void_p, C.c_size_t]
+        lib.swtpg_host_tpsets_info.argtypes = [C.c_void_p, C.POINTER(TpHandlerInfo)]
         _lib = lib
     return _lib
 
@@ -147,3 +171,41 @@ class FrameProcessors:
 
     def __exit__(self, *exc):
         self.close()
+
+
+class TPSetHandler:
+    """TPCTPRequestHandler (src/TPCTPRequestHandler.cpp): TPs in, time-ordered TPSets / heartbeats out."""
+
+    def __init__(self, source_id=7, rate_hz=100, min_latency_ticks=100000, run_number=1, sink_capacity=0):
+        self.lib = host_lib()
+        self.h = self.lib.swtpg_host_tpsets_create(source_id, rate_hz, min_latency_ticks, run_number, sink_capacity)
+
+    def receive(self, tps: np.ndarray) -> int:
+        tps = np.ascontiguousarray(tps, dtype=HOST_TP_DTYPE)
+        return int(self.lib.swtpg_host_tpsets_receive(self.h, tps.ctypes.data, tps.size))
+
+    def cycle(self) -> bool:
+        return bool(self.lib.swtpg_host_tpsets_cycle(self.h))
+
+    def cutoff(self) -> int:
+        return int(self.lib.swtpg_host_tpsets_cutoff(self.h))
+
+    def sets(self):
+        out = []
+        for i in range(self.lib.swtpg_host_tpsets_count(self.h)):
+            hdr = TpSetHdr()
+            self.lib.swtpg_host_tpsets_get(self.h, i, C.byref(hdr), None, 0)
+            objs = np.zeros(hdr.n_objects, dtype=HOST_TP_DTYPE)
+            self.lib.swtpg_host_tpsets_get(self.h, i, C.byref(hdr), objs.ctypes.data, objs.size)
+            out.append(({n: getattr(hdr, n) for n, _ in TpSetHdr._fields_}, objs))
+        return out
+
+    def info(self) -> dict:
+        i = TpHandlerInfo()
+        self.lib.swtpg_host_tpsets_info(self.h, C.byref(i))
+        return {n: getattr(i, n) for n, _ in TpHandlerInfo._fields_}
+
+    def close(self):
+        if self.h:
+            self.lib.swtpg_host_tpsets_destroy(self.h)
+            self.h = None

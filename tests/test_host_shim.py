@@ -40,6 +40,69 @@ def test_no_cpu_fallback():
         H.FrameProcessors(1, 4)
 
 
+def test_tpset_windows_heartbeats_and_tardy_cutoff():
+    """TPCTPRequestHandler::send_tp_sets (src/TPCTPRequestHandler.cpp:99-193) restated step by step in Python as the checker:
+    window [start, newest - min_latency), payload or heartbeat, start/end from the first/last TP, cut-off published, later TPs
+    below the cut-off are tardy. CPU only — this component sits after the GPU path and defines its latency budget."""
+    rng = np.random.default_rng(5)
+    lat = 5000
+    tp_t = np.sort(rng.integers(1_000_000, 1_200_000, 400).astype(np.uint64))
+    tp_t = tp_t[(tp_t < 1_060_000) | (tp_t > 1_100_000)]  # a 40k-tick hole -> heartbeats
+    tps = np.zeros(tp_t.size, dtype=H.HOST_TP_DTYPE)
+    tps["time_start"], tps["channel"], tps["adc_integral"] = tp_t, rng.integers(0, 2560, tp_t.size), rng.integers(1, 9999, tp_t.size)
+    h = H.TPSetHandler(source_id=9, min_latency_ticks=lat, run_number=42)
+    # model
+    buf, cutoff, first, start_win, seq, want, tardy = [], 0, True, 0, 0, [], 0
+    # TPs arrive in bursts (what a superchunk-batching producer does), each burst shuffled; one burst arrives late
+    n_b = tps.size - 60
+    bursts = np.array_split(np.arange(n_b), 25) + [np.array([i]) for i in range(n_b, tps.size)]  # the last 60 arrive one by one
+    order = list(range(len(bursts)))
+    order[10], order[14] = order[14], order[10]  # out-of-order delivery that is still above the cut-off (= time of the last TP sent)
+    order.remove(3)
+    order.insert(20, 3)                          # burst 3 shows up after ~17 later bursts: every TP in it is tardy
+    for b in order:
+        idx = rng.permutation(bursts[b])
+        accepted = h.receive(tps[idx])
+        ok = 0
+        for i in idx:
+            if int(tps["time_start"][i]) < cutoff:
+                tardy += 1
+            else:
+                buf.append((int(tps["time_start"][i]), int(tps["channel"][i]), int(tps["adc_integral"][i])))
+                ok += 1
+        assert accepted == ok
+        for _ in range(3):  # a few sender cycles per burst
+            produced = h.cycle()
+            buf.sort()
+            exp = False
+            if buf:
+                newest, oldest = buf[-1][0], buf[0][0]
+                if first:
+                    start_win, first = oldest, False
+                if newest - start_win > lat:
+                    end_win = newest - lat
+                    objs = [x for x in buf if start_win <= x[0] < end_win]
+                    want.append(dict(seqno=seq, type=1 if objs else 2, start_time=objs[0][0] if objs else start_win,
+                                     end_time=objs[-1][0] if objs else end_win, n=len(objs), objs=objs))
+                    cutoff = want[-1]["end_time"]
+                    seq += 1
+                    start_win = end_win
+                    exp = True
+            assert produced == exp
+            assert h.cutoff() == cutoff
+    got = h.sets()
+    assert len(got) == len(want) and len(want) > 10
+    for (hdr, objs), w in zip(got, want):
+        assert (hdr["seqno"], hdr["type"], hdr["start_time"], hdr["end_time"], hdr["n_objects"]) == (w["seqno"], w["type"], w["start_time"], w["end_time"], w["n"])
+        assert hdr["run_number"] == 42 and hdr["origin"] == 9
+        assert [(int(o["time_start"]), int(o["channel"]), int(o["adc_integral"])) for o in objs] == w["objs"]
+    info = h.info()
+    assert tardy > 0 and info["num_tps_suppressed_tardy"] == tardy
+    assert info["num_heartbeats"] == sum(1 for w in want if w["type"] == 2) and info["num_heartbeats"] > 0
+    assert info["num_tpsets_sent"] == len(want) and info["num_tps_sent"] == sum(w["n"] for w in want)
+    h.close()
+
+
 def expected_host_tps(tps, link_stream, *, mask=(), tp_timeout=10 ** 9, correct=False, crate=1, slot=0, wib2=False):
     """What process_swtpg_hits makes of device/oracle TP records of one link."""
     out = []
