@@ -133,7 +133,22 @@ def cpu_reference_run(threshold: int, steps: int, warmup: int, pulse_rate: float
     return value, info
 
 
+class OneLineStdout:
+    """Everything any library writes to fd 1 during the run (NCCL's version banner, the reference's setState printout, ...)
+    goes to stderr; the JSON line is the only thing that reaches the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
 def main():
+    out = OneLineStdout()
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -153,7 +168,7 @@ def main():
                 "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "real_time_apas": value / APA_SAMPLES_PER_S}
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
         return 0
 
     import numpy as np
@@ -362,7 +377,7 @@ def main():
             "gpu_launches": args.steps,
             "clocks": clocks.summary(),
         }
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -206,6 +206,10 @@ launch_wibeth(const KernelParams& kp, cudaStream_t s)
       case 13: return launch_wibeth_geo<Algo, DUMP, Geo<4, 2, 32>>(kp, s);
       case 14: return launch_wibeth_geo<Algo, DUMP, Geo<2, 2, 32>>(kp, s);
       case 15: return launch_wibeth_geo<Algo, DUMP, Geo<1, 3, 16>>(kp, s);
+      case 16: return launch_wibeth_geo<Algo, DUMP, Geo<1, 3, 32>>(kp, s);
+      case 17: return launch_wibeth_geo<Algo, DUMP, Geo<1, 4, 32>>(kp, s);
+      case 18: return launch_wibeth_geo<Algo, DUMP, Geo<1, 4, 16>>(kp, s);
+      case 19: return launch_wibeth_geo<Algo, DUMP, Geo<1, 8, 8>>(kp, s);
       default: break;
     }
   }

@@ -1032,10 +1032,11 @@ wibeth_kernel(const KernelParams p)
   auto units_of = [&](uint32_t link) -> uint32_t { return p.n_units ? p.n_units[link] : p.units_stride; };
   auto base_of = [&](uint32_t link) -> const uint8_t* { return p.frames + size_t(link) * p.units_stride * SWTPG_WIBETH_FRAME_BYTES; };
 
-  // Producer cursor (meaningful in lane 0 only): the next chunk to request is pr_src; pr_left chunks remain in link pr_link.
+  // Producer cursor: the next chunk to request is pr_src; pr_left chunks remain in link pr_link. Every lane keeps the same
+  // (warp-uniform) copy, so the bookkeeping runs on the uniform datapath; only lane 0 talks to the mbarrier / copy engine.
   uint32_t pr_link = first_link, pr_left = units_of(first_link) * kChunksPerUnit, pr_in_unit = 0, pr_slot = 0;
   const uint8_t* pr_src = base_of(first_link) + 32;
-  auto produce = [&]() { // lane 0: request one more chunk, if any link of this warp has one left
+  auto produce = [&]() { // request one more chunk, if any link of this warp has one left
     if (pr_left == 0) {  // link exhausted (or empty): next link of this warp that has data
       do {
         pr_link += warps_total;
@@ -1046,8 +1047,10 @@ wibeth_kernel(const KernelParams p)
       pr_src = base_of(pr_link) + 32;
       pr_in_unit = 0;
     }
-    mbar_arrive_expect_tx(&bars[pr_slot], kChunkBytes);
-    bulk_g2s(stages + pr_slot * kChunkBytes, pr_src, kChunkBytes, &bars[pr_slot]);
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars[pr_slot], kChunkBytes);
+      bulk_g2s(stages + pr_slot * kChunkBytes, pr_src, kChunkBytes, &bars[pr_slot]);
+    }
     pr_slot = pr_slot + 1 == NSTAGE ? 0 : pr_slot + 1;
     pr_src += kChunkBytes;
     if (++pr_in_unit == kChunksPerUnit) { // skip the 32 header bytes of the next frame
@@ -1063,10 +1066,10 @@ wibeth_kernel(const KernelParams p)
       mbar_init(&bars[s], 1);
     *hits.cnt = 0u;
     fence_mbar_init();
-    for (int s = 0; s < NSTAGE; ++s)
-      produce();
   }
   __syncwarp();
+  for (int s = 0; s < NSTAGE; ++s)
+    produce();
 
   Algo algo;
   algo.configure(p);
@@ -1126,8 +1129,7 @@ wibeth_kernel(const KernelParams p)
         // Every lane's loads from this stage have completed (their values were consumed above), so after the warp barrier
         // the stage can be handed back to the copy engine: a read-then-async-write hand-off needs no proxy fence.
         __syncwarp();
-        if (lane == 0)
-          produce();
+        produce();
         if (++stg == NSTAGE) {
           stg = 0;
           phase ^= 1u;

@@ -896,6 +896,44 @@ swtpg_host_push(swtpg_host* h, uint32_t link, void* payload)
   }
 }
 
+// The reference's threading model: one consumer/post-processing thread per link, all running concurrently. Each thread pushes
+// its link's n_units payloads (payloads: [n_links][n_units][unit_bytes], modified in place by the pre-process tasks).
+int
+swtpg_host_push_parallel(swtpg_host* h, void* payloads, uint32_t n_units)
+{
+  const size_t n_links = h->eth.empty() ? h->wib2.size() : h->eth.size();
+  const size_t unit_bytes = h->eth.empty() ? sizeof(DUNEWIBSuperChunkTypeAdapter) : sizeof(DUNEWIBEthTypeAdapter);
+  std::vector<std::thread> threads;
+  std::vector<std::string> errors(n_links);
+  for (size_t l = 0; l < n_links; ++l)
+    threads.emplace_back([=, &errors]() {
+      try {
+        for (uint32_t u = 0; u < n_units; ++u) {
+          char* p = static_cast<char*>(payloads) + (l * n_units + u) * unit_bytes;
+          if (!h->eth.empty()) {
+            auto* fp = reinterpret_cast<DUNEWIBEthTypeAdapter*>(p);
+            h->eth[l]->preprocess_item(fp);
+            h->eth[l]->postprocess_item(fp);
+          } else {
+            auto* fp = reinterpret_cast<DUNEWIBSuperChunkTypeAdapter*>(p);
+            h->wib2[l]->preprocess_item(fp);
+            h->wib2[l]->postprocess_item(fp);
+          }
+        }
+      } catch (const std::exception& e) {
+        errors[l] = e.what();
+      }
+    });
+  for (auto& t : threads)
+    t.join();
+  for (auto& e : errors)
+    if (!e.empty()) {
+      g_host_error = e;
+      return -1;
+    }
+  return 0;
+}
+
 size_t
 swtpg_host_take_tps(swtpg_host* h, uint32_t link, swtpg_host_tp* out, size_t cap)
 {

@@ -45,7 +45,7 @@ class TpHandlerInfo(C.Structure):
 
 EXPORTS = ["swtpg_host_tpsets_create", "swtpg_host_tpsets_destroy", "swtpg_host_tpsets_receive", "swtpg_host_tpsets_cycle",
            "swtpg_host_tpsets_cutoff", "swtpg_host_tpsets_count", "swtpg_host_tpsets_get", "swtpg_host_tpsets_info",
-           "swtpg_host_last_error", "swtpg_host_create", "swtpg_host_destroy", "swtpg_host_start", "swtpg_host_stop", "swtpg_host_push",
+           "swtpg_host_push_parallel", "swtpg_host_last_error", "swtpg_host_create", "swtpg_host_destroy", "swtpg_host_start", "swtpg_host_stop", "swtpg_host_push",
            "swtpg_host_take_tps", "swtpg_host_get_info", "swtpg_host_error_count", "swtpg_host_misconfigurations",
            "swtpg_host_last_daq_time", "swtpg_host_register_channel_map"]
 
@@ -63,6 +63,7 @@ def host_lib():
         lib.swtpg_host_start.argtypes = [C.c_void_p]
         lib.swtpg_host_stop.argtypes = [C.c_void_p]
         lib.swtpg_host_push.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.swtpg_host_push_parallel.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         lib.swtpg_host_take_tps.restype = C.c_size_t
         lib.swtpg_host_take_tps.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]
         lib.swtpg_host_get_info.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(HostInfo)]
@@ -134,6 +135,11 @@ class FrameProcessors:
         """payload: writable uint8 array of one frame / superchunk (pre-process tasks may rewrite its header)."""
         assert payload.dtype == np.uint8 and payload.flags["C_CONTIGUOUS"] and payload.flags["WRITEABLE"]
         self._check(self.lib.swtpg_host_push(self.h, link, payload.ctypes.data))
+
+    def push_parallel(self, payloads: np.ndarray):
+        """payloads: writable uint8 [n_links, n_units, unit_bytes]; one C++ thread per link pushes its units concurrently."""
+        assert payloads.dtype == np.uint8 and payloads.flags["C_CONTIGUOUS"] and payloads.flags["WRITEABLE"] and payloads.shape[0] == self.n_links
+        self._check(self.lib.swtpg_host_push_parallel(self.h, payloads.ctypes.data, payloads.shape[1]))
 
     def take_tps(self, link: int, cap: int = 1 << 18) -> np.ndarray:
         out = np.zeros(cap, dtype=HOST_TP_DTYPE)

