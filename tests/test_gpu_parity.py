@@ -363,3 +363,56 @@ def test_full_size_one_apa_properties():
         host = buf.view(n_links, n_units, 7200)[l].cpu().numpy()
         want = B.Oracle(cfg, link_id=l).process(host, cap=1 << 20)
         assert_same_tps(one[one["link"] == l], want, f"link {l} vs oracle")
+
+
+@pytest.mark.parametrize("thr", [60, 20])
+def test_config1_single_link_10k_frames(thr):
+    """BASELINE config[0]: one WIBEth link (64 ch x 64 ticks/frame), 10 000 synthetic frames (40.96 M samples), SimpleThreshold,
+    accumulator limit 10 — the run the reference's (absent) emulator app would do with AVX and NAIVE implementations.
+    GPU == AVX2 flavour on every field; == the reference's own compiled code where oracle/_ref travelled with the snapshot;
+    == NAIVE flavour after its position->channel mapping wherever the integral did not overflow 15 bits."""
+    n_frames = 10000
+    units = S.gen_wibeth_host(S.gen_params(1, 0.05), 1, n_frames)
+    with S.TPGenerator(1, 2500, threshold=thr, tp_capacity=1 << 20) as g:
+        g.start()
+        got = np.concatenate([g.process_host(np.ascontiguousarray(units[:, u:u + 2500])) for u in range(0, n_frames, 2500)])
+        ped = g.dump_state(0)["pedestal"]
+    o = B.Oracle(B.make_config(threshold=thr))
+    want = o.process(units[0], cap=1 << 20)
+    assert want.size > 3000
+    assert_same_tps(got, want, "AVX2 flavour")
+    assert (ped == o.state()["pedestal"]).all()
+    naive = B.Oracle(B.make_config(threshold=thr), B.FLAVOUR_NAIVE).process(units[0], cap=1 << 20)
+    keep = lambda a: a[a["adc_integral"] <= 32767]
+    assert_same_tps(keep(got), keep(naive), "NAIVE flavour (integrals <= 32767)")
+    if B.reference_available():
+        ref = B.ReferenceWibEth(B.REF_ETH_SIMPLE_AVX2, thr, 10).process(units[0], cap=1 << 20)
+        assert_same_tps(got, ref, "reference process_window_avx2 itself")
+
+
+@pytest.mark.skipif(not B.reference_available(), reason="oracle/_ref/libswtpg_ref.so did not travel with the snapshot")
+@pytest.mark.parametrize("algorithm,impl", [("AbsRS", B.REF_ETH_ABSRS_AVX2), ("StandardRS", B.REF_ETH_STDRS_AVX2)])
+def test_running_sums_against_the_reference_itself(algorithm, impl):
+    """GPU vs the reference's own process_window_rs_avx2 / process_window_standard_rs_avx2 (compiled from its headers), no
+    restatement in between."""
+    units = S.gen_wibeth_host(S.gen_params(72, 0.3), 1, 300)
+    ref = B.ReferenceWibEth(impl, 30, 10, 8, 5).process(units[0], cap=1 << 20)
+    with S.TPGenerator(1, 100, algorithm=algorithm, threshold=30, rs_memory_factor=8, rs_scale_factor=5) as g:
+        g.start()
+        got = np.concatenate([g.process_host(np.ascontiguousarray(units[:, u:u + 100])) for u in range(0, 300, 100)])
+    assert ref.size > 500
+    assert_same_tps(got, ref, algorithm)
+
+
+@pytest.mark.skipif(not B.reference_available(), reason="oracle/_ref/libswtpg_ref.so did not travel with the snapshot")
+@pytest.mark.parametrize("algorithm,impl,thr", [("SimpleThreshold", B.REF_WIB2_SIMPLE_AVX2, 60), ("FIR", B.REF_WIB2_FIR_AVX2, 5)])
+def test_wib2_against_the_reference_itself(algorithm, impl, thr):
+    """BASELINE config[4]: GPU vs the reference's own swtpg_wib2::process_window_avx2 (SimpleThreshold and FIR + IQR), both
+    register selectors."""
+    units = S.gen_wib2_host(S.gen_params(73, 0.3), 1, 600)
+    ref = B.ReferenceWib2(impl, thr).process(units[0], cap=1 << 20)
+    with S.TPGenerator(1, 200, fmt="wib2", algorithm=algorithm, threshold=thr) as g:
+        g.start()
+        got = np.concatenate([g.process_host(np.ascontiguousarray(units[:, u:u + 200])) for u in range(0, 600, 200)])
+    assert ref.size > 300
+    assert_same_tps(got, ref, f"wib2 {algorithm}")
