@@ -354,6 +354,28 @@ def main():
         others["wib2_fir_iqr_thr5"] = timed("wib2", "FIR", 5, d_w.data_ptr(), w_links, w_units, 5664, 256 * 12, 38)
         del d_w
 
+    # --- the drop-in path as a readout application drives it: one C++ thread per link calling the frame processor's
+    #     find_hits (swtpg_submit: copy into the pinned staging ring, superchunk dispatch, swtpg_poll -> TriggerPrimitives) ---
+    plugin = None
+    if rank == 0 and not args.no_variants:
+        from fdreadoutlibs_b200 import hostshim as H
+
+        p_links, p_units, p_sc = 2 * host_cores(), 2048, 64
+        h_units = S.gen_wibeth_host(gp, p_links, p_units, n_threads=host_cores())
+        with H.FrameProcessors(p_links, p_sc, threshold=args.threshold, device=local_rank, emulator_mode=True, block_on_backpressure=True) as fp:
+            fp.start()
+            fp.push_parallel(h_units[:, :256].copy())  # warm-up: staging ring allocation, first launches
+            t0 = time.perf_counter()
+            fp.push_parallel(h_units)
+            fp.stop()
+            dt = time.perf_counter() - t0
+            n_tp = sum(fp.take_tps(l, cap=1 << 20).size for l in range(p_links))
+        plugin = {"value": p_links * p_units * SAMPLES_PER_FRAME / dt, "unit": UNIT, "threads": p_links, "links": p_links,
+                  "frames_per_link": p_units, "superchunk_frames": p_sc, "tps": n_tp, "host_gbs": p_links * p_units * FRAME_BYTES / dt / 1e9,
+                  "note": "WIBEthFrameProcessor::find_hits per frame from one thread per link (C++ host shim), pageable frames in, "
+                          "TriggerPrimitives out; bounded by the per-frame memcpy into pinned staging on the host cores"}
+        del h_units
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _, cpu = cpu_reference_run(args.threshold, steps=5, warmup=1, pulse_rate=args.pulse_rate)
@@ -374,6 +396,7 @@ def main():
             "e2e": e2e,
             "single_apa": single,
             "other_kernels": others,
+            "plugin_streaming": plugin,
             "gpu_launches": args.steps,
             "clocks": clocks.summary(),
         }

@@ -762,7 +762,7 @@ struct PackedFirIqr
   uint32_t Mq, A, Q25q, A25, Q75p, A75; // 1 - median, (acc - 1); 1 - q25, acc25; q75 + 2, acc75   (accumulators: fp16 subnormals)
   uint32_t d1, d2, d3, d4, d5, d6, o1, o2; // cascade: d_j = previous input of stage j, o1/o2 = previous two outputs
   uint32_t prev, C, Tn;
-  uint32_t xmax1, sig3max, K, Kneg3, shift, shmask, thr_cfg, mult;
+  uint32_t xmax, sig3max, K, Kneg3, shift, shmask, thr_cfg, mult;
 
   static constexpr uint32_t kTiny = 0x00010001u;    // 2^-24 per half
   static constexpr uint32_t kNegTiny = 0x80018001u;
@@ -781,7 +781,7 @@ struct PackedFirIqr
     mult = 1u << p.tap_exponent;
     const uint32_t adc_max = 32767u / mult;                   // wib2/tpg/ProcessingInfo.hpp:93
     const uint32_t sigma_max = (1u << 15) / (mult * 5u);      // ProcessAVX2FIR.hpp:36
-    xmax1 = (adc_max + 1u) * 0x00010001u;
+    xmax = adc_max * 0x00010001u;
     sig3max = (sigma_max + 3u) * 0x00010001u;
     thr_cfg = p.threshold;
     K = mult * p.threshold;
@@ -904,7 +904,7 @@ struct PackedFirIqr
     const uint32_t dn1 = hfma2_sat_bits(T, kNegOne, kNegL);
     A = hfma2_bits(ne2_abs_one(T, kUp), T, kNegTiny);
     Mq = add2(add2(Mq, upm), dn1);
-    const uint32_t x = add2(min2(add2(S, Mq), xmax1), 0xFFFFFFFFu);   // min(raw - median, adcMax)           (:128,142)
+    const uint32_t x = addmin2(add2(S, Mq), 0xFFFFFFFFu, xmax);       // min(raw - median, adcMax)           (:128,142)
     sig3 = addmin2(Q75p, Q25q, sig3max);                              // min(q75 - q25, sigmaMax) + 3        (:131-134)
     const uint32_t filt = o2;                                         // window = samples t-8 .. t-2          (:160-201)
     cascade(x);
@@ -950,24 +950,22 @@ struct PackedFirIqr
                                         uint32_t* wav_out)
   {
     static_assert(G == 4, "trees below are written for 4 ticks");
-    uint32_t filt[G], sig3[G], thr[G];
-    uint32_t neg = 0u; // min over the group of (sigma, 0): non-zero <=> some sigma < 0
+    uint32_t filt[G], sig3[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       filt[g] = tick(extract_pair(rows + g * ROW_WORDS, pp), sig3[g]);
-      thr[g] = threshold(sig3[g]);
-      neg = addmin2(sig3[g], 0xFFFDFFFDu, neg);
       if constexpr (DUMP) {
         ped_out[g] = median();
         wav_out[g] = filt[g];
       }
     }
-    // conservative quiet test: max filter output of the group vs min threshold of the group
+    // conservative quiet test: max filter output of the group vs the threshold of the group's smallest sigma
     const uint32_t mx = __vimax3_s16x2(__vimax3_s16x2(filt[0], filt[1], filt[2]), filt[3], 0u);
-    const uint32_t mn = __vimin3_s16x2(__vimin3_s16x2(thr[0], thr[1], thr[2]), thr[3], thr[3]);
+    const uint32_t smin = __vimin3_s16x2(__vimin3_s16x2(sig3[0], sig3[1], sig3[2]), sig3[3], sig3[3]);
+    uint32_t neg = addmin2(smin, 0xFFFDFFFDu, 0u); // min(sigma, 0) of the group: non-zero <=> some sigma < 0
     if (ctx.p->debug_flags & 1u)
       neg = 0xFFFFFFFFu;
-    const uint32_t busy = gt2_mask_bf16(mx, mn) | prev | neg;
+    const uint32_t busy = gt2_mask_bf16(mx, threshold(smin)) | prev | neg;
     if (__builtin_expect(!__any_sync(0xFFFFFFFFu, busy != 0u), 1))
       return; // nothing but the trackers and the filter moves outside hits
     if (__any_sync(0xFFFFFFFFu, neg != 0u)) { // rare: carries between the positions of a 64-bit lane (H7)
@@ -979,7 +977,7 @@ struct PackedFirIqr
     } else {
 #pragma unroll
       for (int g = 0; g < G; ++g)
-        hit_update<false>(filt[g], thr[g], ctx, t0 + g);
+        hit_update<false>(filt[g], threshold(sig3[g]), ctx, t0 + g);
     }
     __syncwarp();
     if (ctx.stage->nearly_full())

@@ -390,7 +390,8 @@ WIBEthFrameProcessor::find_hits(constframeptr fp, WIBEthFrameHandler* frame_hand
     m_engine->drain(false);
     std::this_thread::yield();
   }
-  m_engine->drain(false);
+  if ((++m_frames_since_drain & 7u) == 0) // TPs only appear once per superchunk: polling on every frame would only contend
+    m_engine->drain(false);
 }
 
 void
@@ -576,7 +577,8 @@ WIB2FrameProcessor::find_hits(constframeptr fp, WIB2FrameHandler* frame_handler)
     m_engine->drain(false);
     std::this_thread::yield();
   }
-  m_engine->drain(false);
+  if ((++m_frames_since_drain & 7u) == 0) // TPs only appear once per superchunk: polling on every frame would only contend
+    m_engine->drain(false);
 }
 
 void

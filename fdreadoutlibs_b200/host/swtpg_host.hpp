@@ -301,6 +301,7 @@ private:
   std::map<uint32_t, int> m_tp_channel_rate_map;
   std::mutex m_rate_mu;
   std::vector<LinkMisconfiguration> m_misconf;
+  uint32_t m_frames_since_drain = 0;
 
   uint64_t m_previous_ts = 0, m_current_ts = 0;
   uint16_t m_previous_seq_id = 0, m_current_seq_id = 0;
@@ -351,6 +352,7 @@ private:
   std::set<uint32_t> m_channel_mask_set;
   uint32_t m_crate_no = 0, m_slot_no = 0, m_link = 0, m_det_id = 0;
   std::array<uint32_t, 256> m_register_channels{};
+  uint32_t m_frames_since_drain = 0;
   std::map<uint32_t, int> m_tp_channel_rate_map;
   std::mutex m_rate_mu;
   uint64_t m_previous_ts = 0, m_current_ts = 0;
