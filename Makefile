@@ -12,8 +12,9 @@ all: lib host oracle
 
 lib: $(LIB)
 
-$(LIB): $(CSRC)/swtpg_capi.cu $(CSRC)/framegen_capi.cu $(CSRC)/swtpg_kernels.cuh $(CSRC)/swtpg_device.cuh $(CSRC)/framegen.h include/swtpg.h include/swtpg_framegen.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/swtpg_capi.cu $(CSRC)/framegen_capi.cu 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
+$(LIB): $(CSRC)/swtpg_capi.cu $(CSRC)/framegen_capi.cu $(CSRC)/stage_copy.cpp $(CSRC)/swtpg_kernels.cuh $(CSRC)/swtpg_device.cuh $(CSRC)/framegen.h include/swtpg.h include/swtpg_framegen.h
+	g++ -O2 -std=c++17 -Wall -fPIC -c -o build_stage_copy.o $(CSRC)/stage_copy.cpp
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/swtpg_capi.cu $(CSRC)/framegen_capi.cu build_stage_copy.o 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
 	@grep -E "error|warning: v" build_ptxas.log || true
 
 # Host-side C++ mirror of the reference's frame processors (plain g++; links against the C ABI only)

@@ -861,6 +861,9 @@ swtpg_process_host_debug(swtpg_handle* h, const void* frames, const uint32_t* n_
 }
 
 // ---- streaming path ---------------------------------------------------------------------------------------------------
+// Copy of one payload into the pinned staging slot (csrc/stage_copy.cpp: non-temporal stores where the CPU has AVX2).
+extern "C" void swtpg_stage_copy(void* dst, const void* src, size_t bytes);
+
 swtpg_status
 swtpg_submit(swtpg_handle* h, uint32_t link, const void* unit, size_t bytes)
 {
@@ -885,7 +888,7 @@ swtpg_submit(swtpg_handle* h, uint32_t link, const void* unit, size_t bytes)
     h->submit_busy.fetch_add(1, std::memory_order_relaxed);
     return SWTPG_ERR_BUSY; // ring full: the caller drops or retries, like a failed try_send
   }
-  memcpy(s.h_frames + (size_t(link) * h->cfg.max_units + u) * h->unit_bytes, unit, bytes);
+  swtpg_stage_copy(s.h_frames + (size_t(link) * h->cfg.max_units + u) * h->unit_bytes, unit, bytes);
   h->submitted[link].store(seq + 1, std::memory_order_release);
   if (s.remaining.fetch_sub(1, std::memory_order_acq_rel) == 1) { // this unit completed the batch
     std::lock_guard<std::mutex> lk(h->dispatch_mu);

@@ -1,5 +1,5 @@
-"""Small run of every kernel family under compute-sanitizer (memcheck / racecheck / synccheck); results checked against the oracle.
-usage: compute-sanitizer --tool memcheck python tools/sanitize_probe.py"""
+"""Small run of every kernel family, checked against the oracle (quick sanity probe; also usable under compute-sanitizer where that is allowed).
+usage: python tools/small_parity_probe.py"""
 import sys
 sys.path.insert(0, '.')
 import numpy as np
