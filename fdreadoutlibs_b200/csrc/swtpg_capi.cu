@@ -262,6 +262,7 @@ launch(const swtpg_handle* h, const KernelParams& kp, cudaStream_t s)
                               : launch_wib2<ScalarAlgo<SWTPG_ALGO_SIMPLE_THRESHOLD, true>, DUMP>(kp, s);
       case SWTPG_ALGO_FIR_IQR:
         return h->fast_fir ? launch_wib2<PackedFirIqr, DUMP>(kp, s) : launch_wib2<ScalarAlgo<SWTPG_ALGO_FIR_IQR, true>, DUMP>(kp, s);
+      case SWTPG_ALGO_ABS_RS: return launch_wib2<ScalarAlgo<SWTPG_ALGO_ABS_RS, true>, DUMP>(kp, s);
       default: return cudaErrorNotSupported;
     }
   }
@@ -582,8 +583,10 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
     return fail(nullptr, SWTPG_ERR_UNSUPPORTED, "unknown frame format");
   if (cfg->algorithm < SWTPG_ALGO_SIMPLE_THRESHOLD || cfg->algorithm > SWTPG_ALGO_FIR_IQR)
     return fail(nullptr, SWTPG_ERR_UNSUPPORTED, "unknown tpg_algorithm (reference: TPGAlgorithmInexistent)");
-  if (cfg->format == SWTPG_FORMAT_WIB2 && (cfg->algorithm == SWTPG_ALGO_ABS_RS || cfg->algorithm == SWTPG_ALGO_STANDARD_RS))
-    return fail(nullptr, SWTPG_ERR_UNSUPPORTED, "running-sum algorithms are only built for the WIBEth format");
+  if (cfg->format == SWTPG_FORMAT_WIB2 && cfg->algorithm == SWTPG_ALGO_STANDARD_RS)
+    return fail(nullptr, SWTPG_ERR_UNSUPPORTED, "StandardRS does not exist for the WIB2 format (reference: SimpleThreshold and AbsRS only)");
+  if (cfg->format == SWTPG_FORMAT_WIB2 && cfg->algorithm == SWTPG_ALGO_ABS_RS && cfg->threshold == 0)
+    return fail(nullptr, SWTPG_ERR_INVALID_ARG, "WIB2 AbsRS needs threshold >= 1 (sigmaMax = 2^15 / (multiplier * threshold))");
   if (cfg->wib2_adc_offset % 4 != 0 || cfg->wib2_adc_offset > SWTPG_WIB2_FRAME_BYTES - 448)
     return fail(nullptr, SWTPG_ERR_INVALID_ARG, "wib2_adc_offset must be a multiple of 4 and leave room for the 448-byte ADC block");
   if (cfg->tap_exponent > 14)

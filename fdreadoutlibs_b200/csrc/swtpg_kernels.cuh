@@ -284,6 +284,50 @@ struct ScalarAlgo
         }
         r.prev = over ? 0xFFFF : 0;
       }
+    } else if constexpr (WIB2 && ALGO == SWTPG_ALGO_ABS_RS) {
+      // wib2/tpg/ProcessRSAVX2.hpp:24-330: quartile trackers as in the FIR finder, running sum with the literal factors
+      // R = 8 and scale = 5 (:29-33), every frugal limit 10, threshold sigma * info.threshold on 4 x int64 lanes (:198),
+      // charge accumulates adds(RS, medianRS) >> tap_exponent (:210-213).
+      const int multiplier = 1 << p.tap_exponent;
+      const int sigma_max = (1 << 15) / (multiplier * int(p.threshold)); // threshold >= 1 (checked by the host)
+      int sigma[2], lv[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        ChanRegs& r = c[h];
+        const int raw = h ? int(S >> 16) : int(S & 0xFFFFu);
+        const bool is_gt = raw > r.median, is_lt = raw < r.median;
+        frugal_scalar(r.q25, raw, r.a25, 10, is_lt);
+        frugal_scalar(r.q75, raw, r.a75, 10, is_gt);
+        frugal_scalar(r.median, raw, r.accum, 10, true);
+        const int x = wrap16(raw - r.median);
+        const int first = wrap16(r.rs * 8);
+        const int second = wrap16((x < 0 ? wrap16(-x) : x) * 5);
+        int rs = wrap16((((wrap16(first + second) * 3276) >> 14) + 1) >> 1); // _mm256_mulhrs_epi16(sum, 32768/10)
+        frugal_scalar(r.med_rs, rs, r.acc_rs, 10, true);
+        rs = wrap16(rs - r.med_rs);
+        r.rs = rs;
+        lv[h] = rs;
+        int sg = wrap16(r.q75 - r.q25);
+        sigma[h] = sg > sigma_max ? sigma_max : sg;
+        ped[h] = r.median;
+        wav[h] = rs;
+      }
+      const uint32_t th2 = iqr_threshold_exact(pack2(sigma[0], sigma[1]), lane, 1, p.threshold);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        ChanRegs& r = c[h];
+        const int th = h ? hi16s(th2) : lo16s(th2);
+        const bool over = lv[h] > th;
+        const bool left = r.prev && !over;
+        const int temp = sat16(lv[h] + r.med_rs);
+        r.charge = sat16(int(int16_t(r.charge)) + ((over ? temp : 0) >> p.tap_exponent)) & 0xFFFF;
+        r.tover = sat16(int(int16_t(r.tover)) + (over ? 1 : 0)) & 0xFFFF;
+        if (left) {
+          emit_wib2(p.sink, ctx.ts, t, uint32_t(r.charge), uint32_t(r.tover), ctx.chan0 + h, ctx.link);
+          r.charge = r.tover = 0;
+        }
+        r.prev = over ? 0xFFFF : 0;
+      }
     } else {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {

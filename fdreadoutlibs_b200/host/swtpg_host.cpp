@@ -447,9 +447,11 @@ WIB2FrameProcessor::conf(const RawDataProcessorConf& config)
   swtpg_config a{};
   if (config.tpg_algorithm == "SimpleThreshold")
     a.algorithm = SWTPG_ALGO_SIMPLE_THRESHOLD;
+  else if (config.tpg_algorithm == "AbsRS") // src/wib2/WIB2FrameProcessor.cpp:388-392
+    a.algorithm = SWTPG_ALGO_ABS_RS;
   else if (config.tpg_algorithm == "FIR") // the FIR + IQR finder the reference ships in wib2/tpg/ProcessAVX2FIR.hpp
     a.algorithm = SWTPG_ALGO_FIR_IQR;
-  else // "AbsRS" is selectable in the reference (src/wib2/WIB2FrameProcessor.cpp:388-392); it is not built for WIB2 here
+  else
     throw TPGAlgorithmInexistent(config.tpg_algorithm);
   m_tp_max_width = config.tp_timeout;
   m_channel_mask_set.insert(config.tpg_channel_mask.begin(), config.tpg_channel_mask.end());

@@ -432,6 +432,62 @@ tick_fir_register(oracle_link* lk, const int* chan_of_pos, const int16_t* raw, i
   }
 }
 
+/* WIB2 AbsRS: wib2/tpg/ProcessRSAVX2.hpp:24-330, 16 positions (one AVX2 register) at a time because the threshold
+ * `sigma * info.threshold` (:186) is again a product on 4 x int64 lanes. R = 8 and scale = 5 are literals (:29-33); all
+ * four frugal trackers use L = 10; sigmaMax = 2^15 / (multiplier * threshold) (:36); the charge accumulates
+ * adds(RS, medianRS) >> tap_exponent (:200-203). level_out[p] receives RS - medianRS. */
+static void
+tick_absrs_wib2_register(oracle_link* lk, const int* chan_of_pos, const int16_t* raw, int t, uint64_t ts, tp_sink* k, int16_t* level_out)
+{
+  const swtpg_config* cfg = &lk->cfg;
+  const int multiplier = 1 << cfg->tap_exponent;
+  const int16_t sigma_max = (int16_t)((1 << 15) / (multiplier * (int)cfg->threshold)); /* threshold >= 1 (else the reference divides by 0) */
+  int16_t sigma[16], rsv[16];
+  for (int p = 0; p < 16; ++p) {
+    oracle_chan* s = &lk->ch[chan_of_pos[p]];
+    const int16_t r = raw[p];
+    const int is_gt = r > s->median, is_lt = r < s->median;   /* :116-124 masks from the OLD median */
+    frugal_avx2(&s->q25, r, &s->a25, 10, is_lt);               /* :126 */
+    frugal_avx2(&s->q75, r, &s->a75, 10, is_gt);               /* :128 */
+    frugal_avx2(&s->median, r, &s->accum, 10, 1);              /* :132 */
+    const int16_t x = wrap16((int32_t)r - s->median);          /* :135 */
+    const int16_t first = wrap16((int32_t)s->rs * 8);          /* :151 mullo(RS, R_factor) */
+    const int16_t second = wrap16((int32_t)abs16(x) * 5);      /* :154 */
+    int16_t rs = mulhrs16(wrap16((int32_t)first + second), (int16_t)(32768 / 10)); /* :158, UtilsAVX2.hpp:77-81 */
+    frugal_avx2(&s->median_rs, rs, &s->accum_rs, 10, 1);       /* :169 */
+    rs = wrap16((int32_t)rs - s->median_rs);                   /* :173 */
+    s->rs = rs;
+    rsv[p] = rs;
+    level_out[p] = rs;
+    int16_t sg = wrap16((int32_t)s->q75 - s->q25);             /* :184 */
+    if (sg > sigma_max)
+      sg = sigma_max;                                          /* :188 */
+    sigma[p] = sg;
+  }
+  for (int g = 0; g < 4; ++g) { /* :198 `sigma * info.threshold` on 4 x int64 lanes */
+    uint64_t v = 0;
+    for (int j = 0; j < 4; ++j)
+      v |= (uint64_t)(uint16_t)sigma[4 * g + j] << (16 * j);
+    v = v * (uint64_t)cfg->threshold;
+    for (int j = 0; j < 4; ++j) {
+      const int p = 4 * g + j;
+      oracle_chan* s = &lk->ch[chan_of_pos[p]];
+      const int16_t thr = (int16_t)(uint16_t)(v >> (16 * j));
+      const int is_over = rsv[p] > thr;
+      const int left = s->prev_over && !is_over;                                           /* :200 */
+      const int16_t temp = sat16((int32_t)rsv[p] + s->median_rs);                          /* :210 adds_epi16(RS, medianRS) */
+      const int16_t add = (int16_t)((is_over ? temp : 0) >> cfg->tap_exponent);            /* :211-213 */
+      s->charge = (uint16_t)sat16((int32_t)(int16_t)s->charge + add);
+      s->tover = (uint16_t)sat16((int32_t)(int16_t)s->tover + (is_over ? 1 : 0));          /* :230-231 */
+      if (left) {
+        emit_wib2(k, ts, chan_of_pos[p], t, s->charge, s->tover);
+        s->charge = s->tover = 0;
+      }
+      s->prev_over = is_over ? 0xFFFFu : 0;
+    }
+  }
+}
+
 /* ---- driver ---------------------------------------------------------------------------------------------------- */
 long
 oracle_process(oracle_link* lk, const uint8_t* units, size_t n_units, uint32_t link_id, swtpg_tp* out, size_t cap,
@@ -467,7 +523,23 @@ oracle_process(oracle_link* lk, const uint8_t* units, size_t n_units, uint32_t l
       }
       int16_t* ped_row = pedestal_out ? pedestal_out + ((u * nticks + t) * (size_t)nch) : 0;
       int16_t* wav_row = waveform_out ? waveform_out + ((u * nticks + t) * (size_t)nch) : 0;
-      if (cfg->algorithm == SWTPG_ALGO_FIR_IQR) {
+      if (wib2 && cfg->algorithm == SWTPG_ALGO_ABS_RS) {
+        for (int r = 0; r < nch / 16; ++r) {
+          int chan_of_pos[16];
+          int16_t raw[16], lvl[16];
+          for (int p = 0; p < 16; ++p) {
+            chan_of_pos[p] = 16 * r + kPerm[p];
+            raw[p] = (int16_t)oracle_unpack14(row, (unsigned)chan_of_pos[p]);
+          }
+          tick_absrs_wib2_register(lk, chan_of_pos, raw, t, ts, &k, lvl);
+          for (int p = 0; p < 16; ++p) {
+            if (ped_row)
+              ped_row[chan_of_pos[p]] = lk->ch[chan_of_pos[p]].median;
+            if (wav_row)
+              wav_row[chan_of_pos[p]] = lvl[p];
+          }
+        }
+      } else if (cfg->algorithm == SWTPG_ALGO_FIR_IQR) {
         const unsigned kk = (lk->k0 + (unsigned)t) & 7u;
         for (int r = 0; r < nch / 16; ++r) {
           int chan_of_pos[16];

@@ -69,6 +69,10 @@ GOLDEN_CASES = {
                               ref_impl=3, flavour=0, rs_memory_factor=8, rs_scale_factor=5),
     "wib2_simple_thr100": dict(fmt="wib2", kind="gen", seed=5, rate=0.05, n_links=1, n_units=300, algorithm="SimpleThreshold",
                                threshold=100, ref_impl=0, flavour=0),
+    "wib2_absrs_thr60": dict(fmt="wib2", kind="gen", seed=5, rate=0.05, n_links=1, n_units=300, algorithm="AbsRS", threshold=60, ref_impl=3,
+                             flavour=0),
+    "wib2_absrs_thr5_dense": dict(fmt="wib2", kind="gen", seed=6, rate=0.6, n_links=1, n_units=150, algorithm="AbsRS", threshold=5, ref_impl=3,
+                                  flavour=0),
     "wib2_fir_thr5": dict(fmt="wib2", kind="gen", seed=5, rate=0.05, n_links=1, n_units=300, algorithm="FIR", threshold=5, ref_impl=1,
                           flavour=0),
     "wib2_fir_thr5_naive": dict(fmt="wib2", kind="gen", seed=5, rate=0.05, n_links=1, n_units=300, algorithm="FIR", threshold=5,

@@ -37,7 +37,7 @@ def test_golden_cases(name, golden):
     assert (ped == golden[name + "__pedestal"]).all()
 
 
-@pytest.mark.parametrize("name", ["noise_simple_thr60", "dense_simple_thr8", "noise_absrs_thr30", "wib2_simple_thr100", "wib2_fir_thr5"])
+@pytest.mark.parametrize("name", ["noise_simple_thr60", "dense_simple_thr8", "noise_absrs_thr30", "wib2_simple_thr100", "wib2_fir_thr5", "wib2_absrs_thr60"])
 @pytest.mark.parametrize("max_units", [1, 7, 32])
 def test_batching_does_not_change_results(name, max_units, golden):
     """Superchunk length is an implementation choice: state carried across batches must make it invisible."""
@@ -84,7 +84,8 @@ def test_against_oracle_with_state_and_dumps(algorithm, thr, L):
                 assert (sg[f] == so[f]).all(), f"link {l} state field {f}"
 
 
-@pytest.mark.parametrize("algorithm,thr", [("SimpleThreshold", 30), ("SimpleThreshold", 2), ("SimpleThreshold", 40000), ("FIR", 5), ("FIR", 2)])
+@pytest.mark.parametrize("algorithm,thr", [("SimpleThreshold", 30), ("SimpleThreshold", 2), ("SimpleThreshold", 40000), ("FIR", 5), ("FIR", 2),
+                                           ("AbsRS", 60), ("AbsRS", 3), ("AbsRS", 700)])
 def test_wib2_against_oracle_with_state_and_dumps(algorithm, thr):
     """BASELINE config 5: WIB2 superchunks (256 channels x 12 ticks) through the same fused kernels — SimpleThreshold with the
     >>6 charge (wib2/tpg/ProcessAVX2.hpp) and the FIR + IQR finder (wib2/tpg/ProcessAVX2FIR.hpp). Ragged batches, several
@@ -118,7 +119,7 @@ def test_wib2_against_oracle_with_state_and_dumps(algorithm, thr):
 @pytest.mark.parametrize("fmt,algorithm,thr,kw", [
     ("wibeth", "SimpleThreshold", 100, {}), ("wibeth", "AbsRS", 100, dict(rs_memory_factor=8, rs_scale_factor=5)),
     ("wibeth", "AbsRS", 50, dict(rs_memory_factor=9, rs_scale_factor=10)), ("wibeth", "StandardRS", 100, dict(rs_memory_factor=7, rs_scale_factor=2)),
-    ("wibeth", "FIR", 5, {}), ("wib2", "SimpleThreshold", 100, {}), ("wib2", "FIR", 5, {})])
+    ("wibeth", "FIR", 5, {}), ("wib2", "SimpleThreshold", 100, {}), ("wib2", "FIR", 5, {}), ("wib2", "AbsRS", 40, {})])
 def test_extreme_amplitudes_wrap_and_saturate_like_the_reference(fmt, algorithm, thr, kw):
     """Pulses up to the full 14-bit range on low pedestals, dense, bipolar: charge wraps (SimpleThreshold, H3) or saturates
     (RS / WIB2 / FIR), |s'| * scale and RS * R overflow 16 bits, the FIR sum wraps, the input clamp at adcMax and the
@@ -133,13 +134,13 @@ def test_extreme_amplitudes_wrap_and_saturate_like_the_reference(fmt, algorithm,
     oracles = [B.Oracle(cfg, link_id=l) for l in range(n_links)]
     want, peds, wavs = [], [], []
     for l in range(n_links):
-        if "RS" in algorithm:
+        if "RS" in algorithm and fmt == "wibeth":
             oracles[l].set_memory_factor(factors[l])
         t, pd, w = oracles[l].process(units[l], dump=True, cap=1 << 20)
         want.append(t), peds.append(pd), wavs.append(w)
     got, gp, gw = [], [], []
     with S.TPGenerator(n_links, step, fmt=fmt, algorithm=algorithm, threshold=thr, tp_capacity=1 << 21, **kw) as g:
-        if "RS" in algorithm:
+        if "RS" in algorithm and fmt == "wibeth":
             g.set_rs_memory_factor(factors)
         g.start()
         for u in range(0, n_units, step):
@@ -189,10 +190,13 @@ def test_wib2_many_links_ragged_and_streaming():
     assert_same_tps(np.concatenate(got), want2, "wib2 streaming")
 
 
-def test_wib2_running_sum_is_unsupported():
+def test_wib2_standard_rs_does_not_exist():
     with pytest.raises(S.SwtpgError) as e:
-        S.TPGenerator(1, 4, fmt="wib2", algorithm="AbsRS")
+        S.TPGenerator(1, 4, fmt="wib2", algorithm="StandardRS")
     assert e.value.status == 6  # SWTPG_ERR_UNSUPPORTED (reference: TPGAlgorithmInexistent)
+    with pytest.raises(S.SwtpgError) as e:
+        S.TPGenerator(1, 4, fmt="wib2", algorithm="AbsRS", threshold=0)
+    assert e.value.status == 1  # the reference would divide by zero (sigmaMax)
 
 
 def test_ragged_and_empty_batches():

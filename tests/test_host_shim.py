@@ -31,7 +31,7 @@ def test_unknown_algorithm_is_tpg_algorithm_inexistent():
     with pytest.raises(H.HostError, match="TPGAlgorithmInexistent"):
         H.FrameProcessors(1, 4, algorithm="NoSuchAlgo")
     with pytest.raises(H.HostError, match="TPGAlgorithmInexistent"):
-        H.FrameProcessors(1, 4, fmt="wib2", algorithm="AbsRS")
+        H.FrameProcessors(1, 4, fmt="wib2", algorithm="StandardRS")
 
 
 @pytest.mark.skipif(S.device_available(), reason="needs a box WITHOUT a GPU")
@@ -232,10 +232,10 @@ def test_collection_channels_fall_back_to_simple_threshold():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("algorithm,algo_id", [("SimpleThreshold", 0), ("FIR", 3)])
+@pytest.mark.parametrize("algorithm,algo_id", [("SimpleThreshold", 0), ("FIR", 3), ("AbsRS", 1)])
 def test_wib2_frame_processor_end_to_end(algorithm, algo_id):
     n_links, n_units = 2, 40
-    thr = 30 if algo_id == 0 else 5
+    thr = {0: 30, 3: 5, 1: 20}[algo_id]
     units = S.gen_wib2_host(S.gen_params(64, 0.5), n_links, n_units)
     want, _ = B.oracle_process_links(B.make_config(fmt="wib2", algorithm=algo_id, threshold=thr), units)
     with H.FrameProcessors(n_links, 8, fmt="wib2", algorithm=algorithm, threshold=thr) as fp:

@@ -50,7 +50,9 @@ def test_wibeth_rs_memory_factor_per_channel():
 
 @pytest.mark.parametrize("seed,rate", [(31, 0.05), (32, 0.6)])
 @pytest.mark.parametrize("algo,impl,flav,thr", [(0, B.REF_WIB2_SIMPLE_AVX2, 0, 100), (0, B.REF_WIB2_SIMPLE_AVX2, 0, 30),
-                                                (3, B.REF_WIB2_FIR_AVX2, 0, 5), (3, B.REF_WIB2_FIR_NAIVE, 1, 5), (3, B.REF_WIB2_FIR_AVX2, 0, 2)])
+                                                (3, B.REF_WIB2_FIR_AVX2, 0, 5), (3, B.REF_WIB2_FIR_NAIVE, 1, 5), (3, B.REF_WIB2_FIR_AVX2, 0, 2),
+                                                (1, B.REF_WIB2_ABSRS_AVX2, 0, 60), (1, B.REF_WIB2_ABSRS_AVX2, 0, 5), (1, B.REF_WIB2_ABSRS_AVX2, 0, 1),
+                                                (1, B.REF_WIB2_ABSRS_AVX2, 0, 500)])
 def test_wib2_matches_reference(seed, rate, algo, impl, flav, thr):
     sc = S.gen_wib2_host(S.gen_params(seed, rate), 1, 250)[0]
     o = B.Oracle(B.make_config(fmt="wib2", algorithm=algo, threshold=thr), flav)
@@ -59,7 +61,7 @@ def test_wib2_matches_reference(seed, rate, algo, impl, flav, thr):
     assert_same_tps(o.process(sc), tr, f"wib2 algo {algo} impl {impl} thr {thr}")
     st = o.state()
     assert (st["pedestal"] == sd[-1, 0]).all()
-    if algo == 3:
+    if algo in (1, 3):
         assert (st["quantile25"] == sd[-1, 1]).all() and (st["quantile75"] == sd[-1, 2]).all()
 
 
