@@ -126,7 +126,15 @@ def cpu_reference_run(threshold: int, steps: int, warmup: int, pulse_rate: float
             secs.append(time.perf_counter() - t0)
     total = sum(secs)
     value = samples * len(secs) / total
-    info = {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+    extra = {}
+    if kind == "reference":  # also one worker alone (per-core figure), AVX2 and the scalar "naive" processor
+        one = frames[:8]
+        t_avx = min(B.ref_wibeth_bench(one, 1, B.REF_ETH_SIMPLE_AVX2, threshold, 10, reps=1)[0] for _ in range(3))
+        t_naive = B.ref_wibeth_bench(one[:2], 1, B.REF_ETH_SIMPLE_NAIVE, threshold, 10, reps=1)[0]
+        per_core = 8 * n_frames * SAMPLES_PER_FRAME / t_avx
+        extra = {"avx2_one_core": per_core, "naive_one_core": 2 * n_frames * SAMPLES_PER_FRAME / t_naive,
+                 "links_real_time_per_core": per_core / 125.0e6}
+    info = {"value": value, "unit": UNIT, "cores": cores, "kind": kind, **extra,
             "sample": f"{n_links} links x {n_frames} frames ({samples / 1e6:.0f} Msamples, {n_links * n_frames * FRAME_BYTES / 1e6:.0f} MB) per pass, "
                       f"{len(secs)} timed passes, threshold {threshold}, one pinned worker per core",
             "ms_per_pass": 1e3 * total / len(secs)}
@@ -165,7 +173,8 @@ def main():
                 "warmup": args.warmup, "ms_per_step": info["ms_per_pass"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int16", "data": "synthetic",
                 "config": {"workload": workload, "note": "reference arm: bounded sample of the same workload on the host cores"},
-                "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample", "avx2_one_core", "naive_one_core",
+                                                       "links_real_time_per_core") if k in info},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "real_time_apas": value / APA_SAMPLES_PER_S}
         out.emit(json.dumps(line))
@@ -379,7 +388,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _, cpu = cpu_reference_run(args.threshold, steps=5, warmup=1, pulse_rate=args.pulse_rate)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "avx2_one_core", "naive_one_core", "links_real_time_per_core") if k in cpu}
 
     gen.close()
     if rank == 0:
