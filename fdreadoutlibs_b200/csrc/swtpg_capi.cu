@@ -72,6 +72,7 @@ struct swtpg_handle
 
   uint32_t* d_state = nullptr;
   uint32_t* d_flags = nullptr;
+  uint32_t* d_link_cursor = nullptr; // {claimed, finished}: dynamic link hand-out of the WIBEth kernel, self-resetting
   swtpg_tp* d_tps = nullptr;
   unsigned* d_count = nullptr;
   unsigned* h_count = nullptr;
@@ -143,6 +144,7 @@ launch_wibeth_geo(const KernelParams& kp, cudaStream_t s)
   auto k = wibeth_kernel<Algo, G::warps, G::stages, G::chunk, DUMP, G::min_ctas>;
   // Persistent grid: as many CTAs as the device holds at once (SMs x resident CTAs per SM); warps walk the links.
   static int resident[64]; // per instantiation and device: CTAs the whole GPU can hold, 0 = not queried yet
+  static int sm_count[64];
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess)
@@ -162,13 +164,20 @@ launch_wibeth_geo(const KernelParams& kp, cudaStream_t s)
       return e;
     if (const char* cap = getenv("SWTPG_CTAS_PER_SM")) // tuning aid
       per_sm = std::min(per_sm, std::max(1, atoi(cap)));
+    sm_count[dev] = std::max(1, sms);
     resident[dev] = std::max(1, per_sm * sms);
   }
-  // Balanced grid: with R = ceil(links / resident warps) rounds, use just enough warps that every warp walks R links (+-1).
-  // 5920 links on 148 SMs x 5 CTAs x 4 warps -> 2960 warps x 2 links, no partially filled last round.
-  const unsigned max_warps = unsigned(resident[dev]) * G::warps;
-  const unsigned rounds = (kp.n_links + max_warps - 1) / max_warps;
-  const unsigned warps = (kp.n_links + rounds - 1) / rounds;
+  // Persistent warps claim links dynamically (wibeth_kernel), so the grid only has to load every SM sub-partition alike:
+  // a multiple of 4 single-warp CTAs per SM (20 on B200: 5 warps per sub-partition; a 21st warp would make one
+  // sub-partition of every SM 20 % slower than its neighbours — profiles/README.md).
+  const unsigned per_sm = unsigned(resident[dev]) / unsigned(sm_count[dev]);
+  unsigned even = G::warps == 1 && per_sm >= 4 ? per_sm / 4 * 4 : per_sm;
+  if (G::warps == 1 && Algo::kWarpsPerSm > 0) // the policy's measured optimum, if the device holds that many
+    even = std::min<unsigned>(even, unsigned(Algo::kWarpsPerSm));
+  unsigned warps = std::min<unsigned>(kp.n_links, even * unsigned(sm_count[dev]) * G::warps);
+  static const int warps_override = [] { const char* e = getenv("SWTPG_WARPS"); return e ? atoi(e) : 0; }(); // tuning aid
+  if (warps_override > 0)
+    warps = std::min<unsigned>(unsigned(warps_override), kp.n_links);
   const unsigned grid = std::min<unsigned>((warps + G::warps - 1) / G::warps, unsigned(resident[dev]));
   k<<<grid, G::warps * 32, G::smem, s>>>(kp);
   return cudaGetLastError();
@@ -294,6 +303,7 @@ make_params(const swtpg_handle* h, const void* d_frames, const uint32_t* d_nunit
   kp.n_links = h->cfg.n_links;
   kp.state = h->d_state;
   kp.group_flags = h->d_flags;
+  kp.link_cursor = h->d_link_cursor;
   kp.sink.buf = d_tps;
   kp.sink.count = d_count;
   kp.sink.cap = h->tp_capacity;
@@ -330,6 +340,7 @@ reset_state(swtpg_handle* h)
   }
   SW_CUDA(h, cudaMemcpyAsync(h->d_state, st.data(), st.size() * 4, cudaMemcpyHostToDevice, h->stream));
   SW_CUDA(h, cudaMemsetAsync(h->d_flags, 0, size_t(h->n_groups) * 4, h->stream));
+  SW_CUDA(h, cudaMemsetAsync(h->d_link_cursor, 0, 2 * sizeof(uint32_t), h->stream));
   SW_CUDA(h, cudaStreamSynchronize(h->stream));
   return SWTPG_OK;
 }
@@ -660,6 +671,8 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
   SW_CUDA(hp, cudaEventCreate(&h->ev1));
   SW_CUDA(hp, cudaMalloc(&h->d_state, size_t(h->n_groups) * kStateWordsPerGroup * 4));
   SW_CUDA(hp, cudaMalloc(&h->d_flags, size_t(h->n_groups) * 4));
+  SW_CUDA(hp, cudaMalloc(&h->d_link_cursor, 2 * sizeof(uint32_t)));
+  SW_CUDA(hp, cudaMemset(h->d_link_cursor, 0, 2 * sizeof(uint32_t)));
   SW_CUDA(hp, cudaMalloc(&h->d_tps, size_t(h->tp_capacity) * sizeof(swtpg_tp)));
   SW_CUDA(hp, cudaMalloc(&h->d_count, sizeof(unsigned)));
   SW_CUDA(hp, cudaMallocHost(&h->h_count, sizeof(unsigned)));
@@ -683,6 +696,7 @@ swtpg_destroy(swtpg_handle* h)
     free_slot(*s);
   if (h->d_state) cudaFree(h->d_state);
   if (h->d_flags) cudaFree(h->d_flags);
+  if (h->d_link_cursor) cudaFree(h->d_link_cursor);
   if (h->d_tps) cudaFree(h->d_tps);
   if (h->d_count) cudaFree(h->d_count);
   if (h->h_count) cudaFreeHost(h->h_count);

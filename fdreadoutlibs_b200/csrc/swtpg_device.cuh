@@ -243,7 +243,11 @@ __device__ __forceinline__ uint32_t
 extract_pair(const uint32_t* row, const PairPos& pp)
 {
   const uint32_t x = __funnelshift_r(row[pp.w0], row[pp.w1], pp.sh); // 28 payload bits + 4 junk bits on top
-#if SWTPG_EXTRACT_IMAD
+#if SWTPG_EXTRACT_IMAD == 2
+  // z = f0 + f1*2^14 (28 bits); z + (z >> 14) * (2^16 - 2^14) = f0 + f1*2^16: LOP3 + SHF (ALU pipe) + IMAD (FMA pipe)
+  const uint32_t z = x & 0x0FFFFFFFu;
+  return (z >> 14) * 0xC000u + z;
+#elif SWTPG_EXTRACT_IMAD
   // Same result with one ALU-pipe op fewer (the ALU pipe is the kernel's bottleneck, profiles/r01_*): z = f0 + f1*2^14;
   // f1 = z >> 14 as a high multiply (IMAD.HI, FMA pipe), then z + f1*(2^16 - 2^14) = f0 + f1*2^16 (IMAD, FMA pipe).
   const uint32_t z = x & 0x0FFFFFFFu;
@@ -324,7 +328,9 @@ struct HitStage
   __device__ __forceinline__ void push(uint32_t chan, uint32_t unit, uint32_t t_end, uint32_t charge, uint32_t tover, uint32_t peak,
                                        uint32_t ptime) const
   {
+#if !defined(SWTPG_EXPERIMENT_NO_PUSH) // timing experiment only (no TPs come out): upper bound of what a smaller push site can gain
     push_hit(buf, cnt, chan | (t_end << 8), unit, (charge & 0xFFFFu) | (tover << 16), (peak & 0xFFFFu) | (ptime << 16));
+#endif
   }
   // Warp-uniform (every lane reads the same word); call after __syncwarp().
   __device__ __forceinline__ bool nearly_full() const { return *reinterpret_cast<volatile uint32_t*>(cnt) > kFlushAbove; }

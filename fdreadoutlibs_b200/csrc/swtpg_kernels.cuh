@@ -60,6 +60,7 @@ struct KernelParams
   uint32_t n_links;
   uint32_t* state;         // [n_groups][SV_COUNT][32]
   uint32_t* group_flags;   // [n_groups]: bit 0 initialized, bits 8..10 FIR ring phase (absTimeModNTAPS)
+  uint32_t* link_cursor;   // [2] {links claimed beyond each warp's first, warps finished}; zero between launches (WIBEth kernel)
   TpSink sink;
   int16_t* pedestal_out;   // debug dumps [link][unit][tick][channel] or nullptr
   int16_t* waveform_out;
@@ -161,6 +162,7 @@ template<int ALGO, bool WIB2>
 struct ScalarAlgo
 {
   static constexpr int kGroupUnroll = 1;
+  static constexpr int kWarpsPerSm = 0; // persistent single-warp CTAs per SM the WIBEth launch aims for; 0 = as many as fit
   ChanRegs c[2];
   uint32_t kphase; // FIR ring phase
 
@@ -401,6 +403,7 @@ struct ScalarAlgo
 struct PackedSimpleWibEth
 {
   static constexpr int kGroupUnroll = SWTPG_GROUP_UNROLL;
+  static constexpr int kWarpsPerSm = 20; // measured best on B200 (profiles/r01_warps_sweep.txt): 5 warps per sub-partition
   uint32_t Mq, A, prev, C, Tn, PK1, PTn;
   uint32_t cUp, cDn, thr1;
 
@@ -646,6 +649,7 @@ template<bool STANDARD>
 struct PackedRsWibEth : PackedSimpleWibEth
 {
   static constexpr int kGroupUnroll = 1;
+  static constexpr int kWarpsPerSm = STANDARD ? 20 : 16; // AbsRS: 4 warps per sub-partition beat 5 by 3 % (same sweep)
   uint32_t RS1, MRq, AR;     // RS + 1 (carried value, after median subtraction); 1 - median_RS; (acc_RS - 1) as fp16 subnormal
   int f_lo, f_hi, nf_lo, nf_hi, scale;
 
@@ -803,6 +807,7 @@ struct PackedRsWibEth : PackedSimpleWibEth
 struct PackedFirIqr
 {
   static constexpr int kGroupUnroll = SWTPG_FIR_GROUP_UNROLL;
+  static constexpr int kWarpsPerSm = 12; // 3 warps per sub-partition: 3 % faster than the 16 its 128 registers allow (same sweep)
   uint32_t Mq, A, Q25q, A25, Q75p, A75; // 1 - median, (acc - 1); 1 - q25, acc25; q75 + 2, acc75   (accumulators: fp16 subnormals)
   uint32_t d1, d2, d3, d4, d5, d6, o1, o2; // cascade: d_j = previous input of stage j, o1/o2 = previous two outputs
   uint32_t prev, C, Tn;
@@ -1031,13 +1036,15 @@ struct PackedFirIqr
 
 // =====================================================================================================================
 // WIBEth kernel: persistent warps, one link (64 channels) at a time per warp, per-warp TMA ring of CHUNK_TICKS-tick stages.
-// Warp w of the grid walks links w, w + W, w + 2W, ... (W = warps in the grid). The ring is refilled by lane 0 from a
-// producer cursor that runs NSTAGE chunks ahead of the consumer ACROSS link boundaries, so a warp never drains its
-// pipeline between links.
+// Warp w of the grid starts on link w; every further link is CLAIMED from a global cursor when the warp's producer runs
+// out of chunks, so links go to whichever warp is free first: a warp that shares its SM sub-partition with one more
+// neighbour, or that drew longer links in a ragged batch, simply takes fewer of them. The ring is refilled by lane 0 from
+// a producer cursor that runs NSTAGE chunks ahead of the consumer ACROSS link boundaries, so a warp never drains its
+// pipeline between links; the producer hands the links it chose to the consumer through a small warp-uniform FIFO.
 // =====================================================================================================================
 constexpr int kWibEthRowBytes = 112;
 
-// Dynamic shared memory of one CTA: [stages | mbarriers | hit staging | hit counters], each 16-byte aligned.
+// Dynamic shared memory of one CTA: [stages | mbarriers | hit staging | hit counters | link FIFOs], each 16-byte aligned.
 template<int WARPS, int NSTAGE, int CHUNK_TICKS>
 struct WibEthSmem
 {
@@ -1045,7 +1052,8 @@ struct WibEthSmem
   static constexpr size_t bars = align16(size_t(WARPS) * NSTAGE * kWibEthRowBytes * CHUNK_TICKS);
   static constexpr size_t hits = align16(bars + size_t(WARPS) * NSTAGE * 8);
   static constexpr size_t counts = hits + size_t(WARPS) * HitStage::kCap * 16;
-  static constexpr size_t total = align16(counts + size_t(WARPS) * 4);
+  static constexpr size_t fifo = align16(counts + size_t(WARPS) * 4);
+  static constexpr size_t total = fifo + size_t(WARPS) * 16; // 4-entry link FIFO per warp
 };
 
 template<class Algo, int WARPS, int NSTAGE, int CHUNK_TICKS, bool DUMP, int MIN_CTAS = 1>
@@ -1075,17 +1083,50 @@ wibeth_kernel(const KernelParams p)
   auto base_of = [&](uint32_t link) -> const uint8_t* { return p.frames + size_t(link) * p.units_stride * SWTPG_WIBETH_FRAME_BYTES; };
 
   // Producer cursor: the next chunk to request is pr_src; pr_left chunks remain in link pr_link. Every lane keeps the same
-  // (warp-uniform) copy, so the bookkeeping runs on the uniform datapath; only lane 0 talks to the mbarrier / copy engine.
+  // (warp-uniform) copy, so the bookkeeping runs on the uniform datapath; only lane 0 talks to the mbarrier / copy engine
+  // and to the global link cursor.
+  // FIFO of links the producer has started and the consumer has not: the producer is at most NSTAGE chunks ahead and every
+  // link it starts has >= kChunksPerUnit chunks, so at most ceil(NSTAGE / kChunksPerUnit) + 1 links are in flight.
+  constexpr uint32_t kFifo = 4; // power of two; lives in shared memory so the tick loop carries no registers for it
+  static_assert((NSTAGE + kChunksPerUnit - 1) / kChunksPerUnit + 1 <= int(kFifo), "link FIFO too short for this ring geometry");
+  volatile uint32_t* fifo = reinterpret_cast<volatile uint32_t*>(smem + L::fifo) + warp * kFifo;
+  uint32_t fifo_head = 0, fifo_n = 0;
+  auto fifo_push = [&](uint32_t link) { // whole warp, converged; every lane holds the same `link`
+    if (lane == 0)
+      fifo[(fifo_head + fifo_n) & (kFifo - 1u)] = link;
+    ++fifo_n;
+    __syncwarp();
+  };
+  auto fifo_pop = [&]() -> uint32_t {
+    const uint32_t link = fifo[fifo_head];
+    fifo_head = (fifo_head + 1u) & (kFifo - 1u);
+    --fifo_n;
+    return link;
+  };
+  bool pr_done = false; // the cursor has run past the last link
   uint32_t pr_link = first_link, pr_left = units_of(first_link) * kChunksPerUnit, pr_in_unit = 0, pr_slot = 0;
   const uint8_t* pr_src = base_of(first_link) + 32;
-  auto produce = [&]() { // request one more chunk, if any link of this warp has one left
-    if (pr_left == 0) {  // link exhausted (or empty): next link of this warp that has data
+  auto claim = [&]() -> uint32_t { // next unclaimed link (links 0 .. warps_total-1 are the warps' first links)
+    uint32_t k = 0;
+    if (lane == 0)
+      k = atomicAdd(p.link_cursor, 1u);
+    return warps_total + __shfl_sync(0xFFFFFFFFu, k, 0);
+  };
+  if (pr_left != 0)
+    fifo_push(first_link);
+  auto produce = [&]() { // request one more chunk, if any link is left for this warp (whole warp calls, converged)
+    if (__builtin_expect(pr_left == 0, 0)) { // link exhausted (or empty): claim the next link that has data
+      if (pr_done)
+        return;
       do {
-        pr_link += warps_total;
-        if (pr_link >= p.n_links)
+        pr_link = claim();
+        if (pr_link >= p.n_links) {
+          pr_done = true;
           return;
+        }
         pr_left = units_of(pr_link) * kChunksPerUnit;
       } while (pr_left == 0);
+      fifo_push(pr_link);
       pr_src = base_of(pr_link) + 32;
       pr_in_unit = 0;
     }
@@ -1123,10 +1164,9 @@ wibeth_kernel(const KernelParams p)
   ctx.stage = &hits;
 
   uint32_t stg = 0, phase = 0; // consumer position in the ring and its mbarrier phase
-  for (uint32_t link = first_link; link < p.n_links; link += warps_total) {
+  while (fifo_n != 0) { // the producer started this link NSTAGE chunks ago (or at start-up)
+    const uint32_t link = fifo_pop();
     const uint32_t n_units = units_of(link);
-    if (n_units == 0)
-      continue;
     const uint8_t* link_base = base_of(link);
     uint32_t* st = p.state + size_t(link) * kStateWordsPerGroup;
     const uint32_t flags = p.group_flags[link];
@@ -1184,6 +1224,15 @@ wibeth_kernel(const KernelParams p)
     algo.store(st, lane, k_end);
     if (lane == 0)
       p.group_flags[link] = kFlagInitialized | (k_end << 8);
+  }
+  // Last warp out re-arms the cursor for the next launch (launches of one handle are stream-ordered: state is carried).
+  if (lane == 0) {
+    const uint32_t active = min(warps_total, p.n_links);
+    __threadfence();
+    if (atomicAdd(p.link_cursor + 1, 1u) == active - 1u) {
+      p.link_cursor[0] = 0u;
+      p.link_cursor[1] = 0u;
+    }
   }
 }
 

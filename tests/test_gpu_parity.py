@@ -221,6 +221,44 @@ def test_ragged_and_empty_batches():
         assert g.counters()["units_processed"] == int(nu1.sum() + nu2.sum())
 
 
+def test_more_links_than_persistent_warps_ragged():
+    """Links are handed to the persistent warps through a device-side cursor (wibeth_kernel): more links than the GPU holds
+    warps, ragged unit counts with empty links in between, several launches on one handle (the cursor re-arms itself), and
+    two algorithms with different warps-per-SM settings. Every link's TPs and pedestals must equal the oracle's, and every
+    link must have been processed exactly once per launch (units_processed)."""
+    n_links, stride = 3300, 3
+    p = S.gen_params(53, 0.5)
+    units = S.gen_wibeth_host(p, n_links, 2 * stride)
+    rng = np.random.default_rng(7)
+    nus = [rng.integers(0, stride + 1, n_links).astype(np.uint32) for _ in range(2)]
+    nus[0][:40] = 0
+    nus[1][-5:] = 0
+    for algorithm, thr in (("SimpleThreshold", 20), ("FIR", 5)):
+        cfg = B.make_config(algorithm=S.ALGORITHMS[algorithm], threshold=thr)
+        check = list(range(0, n_links, 97)) + [n_links - 1, 2959, 2960, 2961]
+        want, ped = [], {}
+        for l in check:
+            o = B.Oracle(cfg, link_id=l)
+            want += [o.process(units[l, : nus[0][l]]), o.process(units[l, stride: stride + nus[1][l]])]
+            ped[l] = o.state()["pedestal"]
+        with S.TPGenerator(n_links, stride, algorithm=algorithm, threshold=thr, tp_capacity=1 << 22) as g:
+            g.start()
+            a = g.process_host(np.ascontiguousarray(units[:, :stride]), n_units=nus[0])
+            b = g.process_host(np.ascontiguousarray(units[:, stride:]), n_units=nus[1])
+            got = np.concatenate([a, b])
+            assert g.counters()["units_processed"] == int(nus[0].sum() + nus[1].sum())
+            for l in check:
+                if nus[0][l] + nus[1][l]:
+                    assert (g.dump_state(l)["pedestal"] == ped[l]).all(), f"{algorithm} link {l}"
+        assert_same_tps(got[np.isin(got["link"], check)], np.concatenate(want), f"{algorithm} dynamic hand-out")
+        # every link with data produced its TPs exactly once: the per-link TP count equals a second, independent run
+        with S.TPGenerator(n_links, stride, algorithm=algorithm, threshold=thr, tp_capacity=1 << 22) as g:
+            g.start()
+            a2 = g.process_host(np.ascontiguousarray(units[:, :stride]), n_units=nus[0])
+            b2 = g.process_host(np.ascontiguousarray(units[:, stride:]), n_units=nus[1])
+        assert_same_tps(np.concatenate([a2, b2]), got, f"{algorithm} run-to-run")
+
+
 def test_restart_resets_state():
     """start() = fresh ChanState + first_hit re-armed (src/wibeth/WIBEthFrameProcessor.cpp:111-154, 67-72)."""
     units = S.gen_wibeth_host(S.gen_params(44, 0.5), 2, 12)
