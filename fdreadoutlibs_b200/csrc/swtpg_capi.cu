@@ -590,6 +590,8 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
     return fail(nullptr, SWTPG_ERR_INVALID_ARG, "swtpg_config.struct_size mismatch");
   if (cfg->n_links == 0 || cfg->max_units == 0)
     return fail(nullptr, SWTPG_ERR_INVALID_ARG, "n_links and max_units must be > 0");
+  if (cfg->max_units >= (1u << kHitUnitBits))
+    return fail(nullptr, SWTPG_ERR_INVALID_ARG, "max_units must stay below 2^18 units per batch (hit records carry the unit index in 18 bits)");
   if (cfg->format != SWTPG_FORMAT_WIBETH && cfg->format != SWTPG_FORMAT_WIB2)
     return fail(nullptr, SWTPG_ERR_UNSUPPORTED, "unknown frame format");
   if (cfg->algorithm < SWTPG_ALGO_SIMPLE_THRESHOLD || cfg->algorithm > SWTPG_ALGO_FIR_IQR)

@@ -298,91 +298,134 @@ emit_wib2(const TpSink& k, uint64_t ts, int t_end, uint32_t charge, uint32_t tov
 }
 
 // ---- per-warp hit staging -----------------------------------------------------------------------------------------
-// The tick loop only parks raw hit words in a warp-private shared-memory buffer: a lane whose channel ends a hit takes a
-// slot with a shared-memory atomic (lane-divergent code, executed once per hit, no warp-wide ballots) and writes one
-// 16-byte record. The 64-bit TP arithmetic, the global cursor atomic (one per flush, not per hit) and the coalesced
-// 32-byte record stores happen in flush(), with all 32 lanes converting one record each.
-// SWTPG_PUSH_NOINLINE=1 moves this cold path out of line (the tick loop carries 32 copies of it otherwise).
-#ifndef SWTPG_PUSH_NOINLINE
-#define SWTPG_PUSH_NOINLINE 0
-#endif
-#if SWTPG_PUSH_NOINLINE
-__device__ __noinline__ void
-#else
-__device__ __forceinline__ void
-#endif
-push_hit(uint4* buf, uint32_t* cnt, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3)
-{
-  const uint32_t slot = atomicAdd(cnt, 1u);
-  buf[slot] = make_uint4(w0, w1, w2, w3);
-}
+// The tick loop only parks raw PAIR records in a warp-private shared-memory buffer: a lane on which at least one of its two
+// channels ends a hit takes a slot with a shared-memory atomic (lane-divergent code, one site per tick; ptxas aggregates
+// the atomic over the lanes that take the branch together) and writes its packed registers as they are — 20 bytes:
+//   {meta = frame channel of the low half | tick << 8 | unit << 14, charge & left, tover, peak_adc} + {peak_time}.
+// A half whose masked charge is zero produced no TP (it did not end, or its hit has hit_charge == 0, which the reference's
+// decode drops: src/wibeth/WIBEthFrameProcessor.cpp:520, src/wib2/WIB2FrameProcessor.cpp:429). Splitting pairs into
+// records, the 64-bit TP arithmetic, the global cursor atomic (one per flush, not per hit) and the 32-byte
+// record stores happen in flush(), with all 32 lanes converting one pair each (ballot-free: one warp prefix sum).
+constexpr uint32_t kHitUnitBits = 18; // units per batch must stay below 2^18 (checked by swtpg_create)
 
 struct HitStage
 {
-  static constexpr uint32_t kCap = SWTPG_HIT_CAP;     // records; a 4-tick group ends at most 2 hits per channel = 128 records,
+  static constexpr uint32_t kCap = SWTPG_HIT_CAP;     // pair records; a 4-tick group parks at most one per lane and tick = 128,
   static constexpr uint32_t kFlushAbove = kCap - 128; // so checking once per group with <= kCap-128 parked never overflows
   uint4* buf;                                 // warp-private, kCap entries
+  uint32_t* aux;                              // warp-private, kCap entries (peak_time pairs)
   uint32_t* cnt;                              // warp-private counter in shared memory
 
-  // One record: a hit of frame channel `chan` ended at tick t_end of unit `unit`. Any subset of lanes may call.
-  __device__ __forceinline__ void push(uint32_t chan, uint32_t unit, uint32_t t_end, uint32_t charge, uint32_t tover, uint32_t peak,
-                                       uint32_t ptime) const
+  static __device__ __forceinline__ uint32_t meta(uint32_t chan0, uint32_t unit, uint32_t t_end)
   {
-#if !defined(SWTPG_EXPERIMENT_NO_PUSH) // timing experiment only (no TPs come out): upper bound of what a smaller push site can gain
-    push_hit(buf, cnt, chan | (t_end << 8), unit, (charge & 0xFFFFu) | (tover << 16), (peak & 0xFFFFu) | (ptime << 16));
+    return chan0 | (t_end << 8) | (unit << 14);
+  }
+  // Any subset of lanes may call. charge_left = charge & left (per half), the other words are the packed state registers.
+  __device__ __forceinline__ void push(uint32_t m, uint32_t charge_left, uint32_t tover, uint32_t peak, uint32_t ptime) const
+  {
+#if !defined(SWTPG_EXPERIMENT_NO_PUSH) // timing experiment only (no TPs come out)
+    const uint32_t slot = atomicAdd(cnt, 1u);
+    buf[slot] = make_uint4(m, charge_left, tover, peak);
+    aux[slot] = ptime;
 #endif
   }
-  // Warp-uniform (every lane reads the same word); call after __syncwarp().
-  __device__ __forceinline__ bool nearly_full() const { return *reinterpret_cast<volatile uint32_t*>(cnt) > kFlushAbove; }
+  __device__ __forceinline__ void push(uint32_t m, uint32_t charge_left, uint32_t tover) const // finders without peak tracking
+  {
+#if !defined(SWTPG_EXPERIMENT_NO_PUSH)
+    const uint32_t slot = atomicAdd(cnt, 1u);
+    buf[slot] = make_uint4(m, charge_left, tover, 0u);
+#endif
+  }
+  // Warp-uniform (every lane reads the same word); the warp is converged at both call sites.
+  __device__ __forceinline__ uint32_t count() const { return *reinterpret_cast<volatile uint32_t*>(cnt); }
+  __device__ __forceinline__ bool must_flush() const
+  {
+    __syncwarp();
+    return count() > kFlushAbove;
+  }
 
   // Converts and writes out everything staged (see flush_hits). Whole warp calls, converged.
   template<bool WIB2_UNITS, bool WIB2_FIELDS>
   __device__ __forceinline__ void flush(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const;
 };
 
-// Hit record -> swtpg_tp. Out of line (cold: once per ~32 hits) and all-by-value, so the caller keeps its state in registers.
+// Pair records -> swtpg_tp. Out of line (cold) and all-by-value, so the caller keeps its state in registers.
 //   WIB2_UNITS : where the unit's timestamp lives — WIBEthFrame DAQEthHeader word 1 (docs/README.md:81) or
 //                WIB2Frame::get_timestamp of the superchunk's first frame (bytes 4..11, src/wib2/WIB2FrameProcessor.cpp:350-351)
 //   WIB2_FIELDS: which process_swtpg_hits derives the fields — src/wibeth/WIBEthFrameProcessor.cpp:520-545 (peak from the
 //                tracked peak) or src/wib2/WIB2FrameProcessor.cpp:429-455 (time_peak = middle of the hit, adc_peak = integral/20)
 template<bool WIB2_UNITS, bool WIB2_FIELDS>
 __device__ __noinline__ void
-flush_hits(uint4* buf, uint32_t* cnt, swtpg_tp* out, unsigned int* out_count, uint32_t out_cap, const uint8_t* link_base, uint32_t link,
-           uint32_t lane)
+flush_hits(uint4* buf, uint32_t* aux, uint32_t* cnt, swtpg_tp* out, unsigned int* out_count, uint32_t out_cap, const uint8_t* link_base,
+           uint32_t link, uint32_t lane)
 {
   __syncwarp();
   const uint32_t n = *reinterpret_cast<volatile uint32_t*>(cnt);
   if (n == 0)
     return;
-  unsigned base = 0;
-  if (lane == 0)
-    base = atomicAdd(out_count, n);
-  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  // Pass 1: how many TPs the parked pairs hold, then ONE reservation in the global list. The atomic's round trip overlaps
+  // the loads and the prefix arithmetic of the first 32 pairs: its result is only read when the first record is stored.
+  uint32_t mine = 0;
   for (uint32_t i = lane; i < n; i += 32) {
-    const uint4 r = buf[i];
-    const uint32_t chan = r.x & 0xFFu, t_end = r.x >> 8, charge = r.z & 0xFFFFu, tover = r.z >> 16, peak = r.w & 0xFFFFu, ptime = r.w >> 16;
-    uint64_t ts;
-    if constexpr (WIB2_UNITS) {
-      const uint32_t* hdr = reinterpret_cast<const uint32_t*>(link_base + size_t(r.y) * SWTPG_WIB2_SUPERCHUNK_BYTES + 4);
-      ts = uint64_t(hdr[0]) | (uint64_t(hdr[1]) << 32);
-    } else {
-      ts = *reinterpret_cast<const unsigned long long*>(link_base + size_t(r.y) * SWTPG_WIBETH_FRAME_BYTES + 8);
+    const uint32_t c = buf[i].y;
+    mine += uint32_t((c & 0xFFFFu) != 0u) + uint32_t((c >> 16) != 0u);
+  }
+  const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, mine);
+  unsigned base = 0;
+  if (total != 0 && lane == 0)
+    base = atomicAdd(out_count, total);
+  bool have_base = false;
+  uint32_t done = 0; // TPs of the pairs before this lane's (prefix over whole 32-pair rounds)
+  const uint32_t below = (1u << lane) - 1u;
+  for (uint32_t i0 = 0; i0 < n && total != 0; i0 += 32) { // whole warp: one pair record per lane
+    const uint32_t i = i0 + lane;
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t pt2 = 0u;
+    if (i < n) {
+      r = buf[i];
+      if constexpr (!WIB2_FIELDS)
+        pt2 = aux[i];
     }
-    const uint64_t t0 = ts + uint64_t(32ll * (int64_t(t_end) - int64_t(tover)));
-    const unsigned idx = base + i;
-    if (idx < out_cap) {
-      uint4* d = reinterpret_cast<uint4*>(out + idx);
-      uint64_t tp;
-      uint32_t pk;
-      if constexpr (WIB2_FIELDS) {
-        tp = (t0 + (ts + uint64_t(32ll * int64_t(t_end)))) / 2;
-        pk = (charge / 20u) & 0xFFFFu;
+    const bool have_lo = (r.y & 0xFFFFu) != 0u, have_hi = (r.y >> 16) != 0u;
+    const uint32_t b_lo = __ballot_sync(0xFFFFFFFFu, have_lo), b_hi = __ballot_sync(0xFFFFFFFFu, have_hi);
+    uint32_t idx = done + __popc(b_lo & below) + __popc(b_hi & below);
+    done += __popc(b_lo) + __popc(b_hi);
+    const uint32_t chan0 = r.x & 0xFFu, t_end = (r.x >> 8) & 0x3Fu, unit = r.x >> 14;
+    uint64_t ts = 0;
+    if (have_lo || have_hi) {
+      if constexpr (WIB2_UNITS) {
+        const uint32_t* hdr = reinterpret_cast<const uint32_t*>(link_base + size_t(unit) * SWTPG_WIB2_SUPERCHUNK_BYTES + 4);
+        ts = uint64_t(hdr[0]) | (uint64_t(hdr[1]) << 32);
       } else {
-        tp = t0 + 32ull * ptime;
-        pk = peak;
+        ts = *reinterpret_cast<const unsigned long long*>(link_base + size_t(unit) * SWTPG_WIBETH_FRAME_BYTES + 8);
       }
-      d[0] = make_uint4(uint32_t(t0), uint32_t(t0 >> 32), uint32_t(tp), uint32_t(tp >> 32));
-      d[1] = make_uint4(32u * tover, charge, pk | (chan << 16), link);
+    }
+    if (!have_base) {
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      have_base = true;
+    }
+    idx += base;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (!(h ? have_hi : have_lo))
+        continue;
+      const uint32_t charge = h ? r.y >> 16 : r.y & 0xFFFFu, tover = h ? r.z >> 16 : r.z & 0xFFFFu;
+      const uint64_t t0 = ts + uint64_t(32ll * (int64_t(t_end) - int64_t(tover)));
+      if (idx < out_cap) {
+        uint4* d = reinterpret_cast<uint4*>(out + idx);
+        uint64_t tp;
+        uint32_t pk;
+        if constexpr (WIB2_FIELDS) {
+          tp = (t0 + (ts + uint64_t(32ll * int64_t(t_end)))) / 2;
+          pk = (charge / 20u) & 0xFFFFu;
+        } else {
+          tp = t0 + 32ull * (h ? pt2 >> 16 : pt2 & 0xFFFFu);
+          pk = h ? r.w >> 16 : r.w & 0xFFFFu;
+        }
+        d[0] = make_uint4(uint32_t(t0), uint32_t(t0 >> 32), uint32_t(tp), uint32_t(tp >> 32));
+        d[1] = make_uint4(32u * tover, charge, pk | ((chan0 + uint32_t(h)) << 16), link);
+      }
+      ++idx;
     }
   }
   __syncwarp();
@@ -395,7 +438,7 @@ template<bool WIB2_UNITS, bool WIB2_FIELDS>
 __device__ __forceinline__ void
 HitStage::flush(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const
 {
-  flush_hits<WIB2_UNITS, WIB2_FIELDS>(buf, cnt, k.buf, k.count, k.cap, link_base, link, lane);
+  flush_hits<WIB2_UNITS, WIB2_FIELDS>(buf, aux, cnt, k.buf, k.count, k.cap, link_base, link, lane);
 }
 
 } // namespace swtpg

@@ -497,8 +497,9 @@ struct PackedSimpleWibEth
   }
   __device__ __forceinline__ uint32_t over_mask(uint32_t sp1) const { return gt2_mask_nonneg(sp1, thr1); } // (:97-98)
 
-  // Hit bookkeeping of one tick (:102-207). Lanes whose channel ends a hit hand it to the warp's staging buffer and
-  // reset (lane-divergent, once per hit); accepted iff hit_charge != 0 (src/wibeth/WIBEthFrameProcessor.cpp:520).
+  // Hit bookkeeping of one tick (:102-207). A lane on which a channel ends a hit parks its packed registers in the warp's
+  // staging buffer and resets (lane-divergent); accepted iff hit_charge != 0 (src/wibeth/WIBEthFrameProcessor.cpp:520),
+  // which flush() decides on the masked charge.
   __device__ __forceinline__ void hit_update(uint32_t sp1, const TickCtx& ctx, int t)
   {
     const uint32_t over = over_mask(sp1);
@@ -510,11 +511,7 @@ struct PackedSimpleWibEth
     Tn = addmax2(Tn, over, 0x80018001u);                // tover = adds(tover, 1): -tover >= -32767   (:139-140)
     prev = over;
     if (left != 0u) {                                   //                                  (:154-204)
-      const uint32_t T = neg2(Tn), PK = add2(PK1, 0xFFFFFFFFu), PT = neg2(PTn);
-      if ((left & 0xFFFFu) && (C & 0xFFFFu))
-        ctx.stage->push(ctx.chan0, ctx.unit, uint32_t(t), C & 0xFFFFu, T & 0xFFFFu, PK & 0xFFFFu, PT & 0xFFFFu);
-      if ((left >> 16) && (C >> 16))
-        ctx.stage->push(ctx.chan0 + 1u, ctx.unit, uint32_t(t), C >> 16, T >> 16, PK >> 16, PT >> 16);
+      ctx.stage->push(HitStage::meta(ctx.chan0, ctx.unit, uint32_t(t)), C & left, neg2(Tn), add2(PK1, 0xFFFFFFFFu), neg2(PTn));
       C &= ~left;
       Tn &= ~left;
       PK1 = (PK1 & ~left) | (left & 0x00010001u);
@@ -555,8 +552,7 @@ struct PackedSimpleWibEth
 #pragma unroll
     for (int g = 0; g < G; ++g)
       hit_update(sp[g], ctx, t0 + g);
-    __syncwarp();
-    if (ctx.stage->nearly_full())
+    if (ctx.stage->must_flush())
       flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
   }
 };
@@ -595,11 +591,8 @@ struct PackedSimpleWib2 : PackedSimpleWibEth
     Tn = addmax2(Tn, over, 0x80018001u);                // tover = adds(tover, 1)
     prev = over;
     if (left != 0u) {
-      const uint32_t T = neg2(Tn);
-      if ((left & 0xFFFFu) && (C & 0xFFFFu)) // accepted iff hit_charge != 0 (src/wib2/WIB2FrameProcessor.cpp:429)
-        ctx.stage->push(ctx.chan0, ctx.unit, uint32_t(t), C & 0xFFFFu, T & 0xFFFFu, 0u, 0u);
-      if ((left >> 16) && (C >> 16))
-        ctx.stage->push(ctx.chan0 + 1u, ctx.unit, uint32_t(t), C >> 16, T >> 16, 0u, 0u);
+      // accepted iff hit_charge != 0 (src/wib2/WIB2FrameProcessor.cpp:429): decided in flush on the masked charge
+      ctx.stage->push(HitStage::meta(ctx.chan0, ctx.unit, uint32_t(t)), C & left, neg2(Tn));
       C &= ~left;
       Tn &= ~left;
     }
@@ -626,8 +619,7 @@ struct PackedSimpleWib2 : PackedSimpleWibEth
 #pragma unroll
     for (int g = 0; g < G; ++g)
       hit_update(sp[g], ctx, t0 + g);
-    __syncwarp();
-    if (ctx.stage->nearly_full())
+    if (ctx.stage->must_flush())
       flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
   }
 };
@@ -743,11 +735,7 @@ struct PackedRsWibEth : PackedSimpleWibEth
     Tn = addmax2(Tn, over, 0x80018001u);
     prev = over;
     if (left != 0u) {
-      const uint32_t T = neg2(Tn), PK = add2(PK1, 0xFFFFFFFFu), PT = neg2(PTn);
-      if ((left & 0xFFFFu) && (C & 0xFFFFu))
-        ctx.stage->push(ctx.chan0, ctx.unit, uint32_t(t), C & 0xFFFFu, T & 0xFFFFu, PK & 0xFFFFu, PT & 0xFFFFu);
-      if ((left >> 16) && (C >> 16))
-        ctx.stage->push(ctx.chan0 + 1u, ctx.unit, uint32_t(t), C >> 16, T >> 16, PK >> 16, PT >> 16);
+      ctx.stage->push(HitStage::meta(ctx.chan0, ctx.unit, uint32_t(t)), C & left, neg2(Tn), add2(PK1, 0xFFFFFFFFu), neg2(PTn));
       C &= ~left;
       Tn &= ~left;
       PK1 = (PK1 & ~left) | (left & 0x00010001u);
@@ -780,8 +768,7 @@ struct PackedRsWibEth : PackedSimpleWibEth
 #pragma unroll
     for (int g = 0; g < G; ++g)
       hit_update(sp[g], lv[g], ctx, t0 + g);
-    __syncwarp();
-    if (ctx.stage->nearly_full())
+    if (ctx.stage->must_flush())
       flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
   }
 };
@@ -984,11 +971,8 @@ struct PackedFirIqr
     Tn = addmax2(Tn, over, 0x80018001u);                  // tover = adds(tover, 1)                    (:236-237)
     prev = over;
     if (left != 0u) {                                     //                                           (:251-281)
-      const uint32_t T = neg2(Tn);
-      if ((left & 0xFFFFu) && (C & 0xFFFFu))              // accepted iff hit_charge != 0 (src/wib2/WIB2FrameProcessor.cpp:429)
-        ctx.stage->push(ctx.chan0, ctx.unit, uint32_t(t), C & 0xFFFFu, T & 0xFFFFu, 0u, 0u);
-      if ((left >> 16) && (C >> 16))
-        ctx.stage->push(ctx.chan0 + 1u, ctx.unit, uint32_t(t), C >> 16, T >> 16, 0u, 0u);
+      // accepted iff hit_charge != 0 (src/wib2/WIB2FrameProcessor.cpp:429): decided in flush on the masked charge
+      ctx.stage->push(HitStage::meta(ctx.chan0, ctx.unit, uint32_t(t)), C & left, neg2(Tn));
       C &= ~left;
       Tn &= ~left;
     }
@@ -1028,8 +1012,7 @@ struct PackedFirIqr
       for (int g = 0; g < G; ++g)
         hit_update<false>(filt[g], threshold(sig3[g]), ctx, t0 + g);
     }
-    __syncwarp();
-    if (ctx.stage->nearly_full())
+    if (ctx.stage->must_flush())
       flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
   }
 };
@@ -1044,14 +1027,15 @@ struct PackedFirIqr
 // =====================================================================================================================
 constexpr int kWibEthRowBytes = 112;
 
-// Dynamic shared memory of one CTA: [stages | mbarriers | hit staging | hit counters | link FIFOs], each 16-byte aligned.
+// Dynamic shared memory of one CTA: [stages | mbarriers | hit staging (16 B + 4 B per record) | hit counters | link FIFOs].
 template<int WARPS, int NSTAGE, int CHUNK_TICKS>
 struct WibEthSmem
 {
   static constexpr size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
   static constexpr size_t bars = align16(size_t(WARPS) * NSTAGE * kWibEthRowBytes * CHUNK_TICKS);
   static constexpr size_t hits = align16(bars + size_t(WARPS) * NSTAGE * 8);
-  static constexpr size_t counts = hits + size_t(WARPS) * HitStage::kCap * 16;
+  static constexpr size_t aux = hits + size_t(WARPS) * HitStage::kCap * 16;
+  static constexpr size_t counts = aux + size_t(WARPS) * HitStage::kCap * 4;
   static constexpr size_t fifo = align16(counts + size_t(WARPS) * 4);
   static constexpr size_t total = fifo + size_t(WARPS) * 16; // 4-entry link FIFO per warp
 };
@@ -1077,6 +1061,7 @@ wibeth_kernel(const KernelParams p)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars) + warp * NSTAGE;
   HitStage hits;
   hits.buf = reinterpret_cast<uint4*>(smem + L::hits) + size_t(warp) * HitStage::kCap;
+  hits.aux = reinterpret_cast<uint32_t*>(smem + L::aux) + size_t(warp) * HitStage::kCap;
   hits.cnt = reinterpret_cast<uint32_t*>(smem + L::counts) + warp;
 
   auto units_of = [&](uint32_t link) -> uint32_t { return p.n_units ? p.n_units[link] : p.units_stride; };
@@ -1251,7 +1236,8 @@ struct Wib2Smem
   static constexpr size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
   static constexpr size_t bars = align16(size_t(NSTAGE) * SWTPG_WIB2_SUPERCHUNK_BYTES);
   static constexpr size_t hits = align16(bars + size_t(NSTAGE) * 16);
-  static constexpr size_t counts = hits + size_t(kWib2Warps) * HitStage::kCap * 16;
+  static constexpr size_t aux = hits + size_t(kWib2Warps) * HitStage::kCap * 16;
+  static constexpr size_t counts = aux + size_t(kWib2Warps) * HitStage::kCap * 4;
   static constexpr size_t total = align16(counts + size_t(kWib2Warps) * 4);
 };
 
@@ -1268,6 +1254,7 @@ wib2_kernel(const KernelParams p)
   uint64_t* empty = full + NSTAGE;
   HitStage hits;
   hits.buf = reinterpret_cast<uint4*>(smem + L::hits) + size_t(warp) * HitStage::kCap;
+  hits.aux = reinterpret_cast<uint32_t*>(smem + L::aux) + size_t(warp) * HitStage::kCap;
   hits.cnt = reinterpret_cast<uint32_t*>(smem + L::counts) + warp;
 
   auto units_of = [&](uint32_t link) -> uint32_t { return p.n_units ? p.n_units[link] : p.units_stride; };

@@ -86,7 +86,7 @@ typedef struct swtpg_config
   int32_t format;            /* swtpg_format */
   int32_t algorithm;         /* swtpg_algorithm */
   uint32_t n_links;          /* independent links owned by this handle (one reference FrameProcessor each) */
-  uint32_t max_units;        /* superchunk length: units (frames / WIB2 superchunks) per link per batch */
+  uint32_t max_units;        /* superchunk length: units (frames / WIB2 superchunks) per link per batch, < 2^18 */
   uint32_t tp_capacity;      /* device TP buffer, records per batch; 0 = sized for the worst case */
   uint32_t n_slots;          /* staging-ring depth of the streaming path (>= 2); 0 = 3 */
   uint16_t threshold;        /* tpg_threshold (ADC; sigma units for FIR_IQR) */

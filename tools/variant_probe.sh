@@ -3,5 +3,5 @@
 ARGS=$1; shift
 for v in "$@"; do
   if [ "$v" = base ]; then unset SWTPG_LIB; else export SWTPG_LIB=$PWD/build/variants/libswtpg_$v.so; fi
-  echo -n "[$v] "; python tools/perf_probe.py $ARGS 2>&1 | tail -1
+  echo -n "[$v] "; timeout 60 python tools/perf_probe.py $ARGS 2>&1 | tail -1; echo
 done
