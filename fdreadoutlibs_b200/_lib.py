@@ -75,6 +75,8 @@ EXPORTS = {
     "swtpg_process_host_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t,
                                            C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]),
     "swtpg_submit": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "swtpg_register_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "swtpg_unregister_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
     "swtpg_flush": (C.c_int, [C.c_void_p]),
     "swtpg_poll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "swtpg_sync": (C.c_int, [C.c_void_p]),

@@ -182,9 +182,18 @@ class TPGenerator:
     # -- streaming entry points --------------------------------------------------------------------------------------------
     def submit(self, link: int, unit: np.ndarray) -> bool:
         """One payload of one link. False = back-pressure (SWTPG_ERR_BUSY)."""
-        unit = np.ascontiguousarray(unit, dtype=np.uint8)
+        unit = np.ascontiguousarray(unit, dtype=np.uint8)  # a contiguous uint8 view is passed by address (zero-copy ingest relies on it)
         st = self._check(lib.swtpg_submit(self._h, link, unit.ctypes.data, unit.size), allow=(SWTPG_ERR_BUSY,))
         return st == SWTPG_OK
+
+    def register_buffer(self, buf: np.ndarray):
+        """Zero-copy ingest: payloads submitted from inside `buf` (the latency buffer) are not copied by submit(); the copy
+        engine reads them where they lie when their batch is dispatched. `buf` must stay alive and unmodified until sync()."""
+        assert buf.flags["C_CONTIGUOUS"] and buf.dtype == np.uint8
+        self._check(lib.swtpg_register_buffer(self._h, buf.ctypes.data, buf.nbytes))
+
+    def unregister_buffer(self, buf: np.ndarray):
+        self._check(lib.swtpg_unregister_buffer(self._h, buf.ctypes.data))
 
     def flush(self):
         self._check(lib.swtpg_flush(self._h))

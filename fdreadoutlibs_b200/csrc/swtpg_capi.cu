@@ -53,6 +53,9 @@ struct Slot
   std::atomic<uint64_t> batch{ 0 };      // batch index this slot currently holds
   std::atomic<uint32_t> remaining{ 0 };  // units still missing before auto-dispatch
   uint32_t n_ready = 0, n_taken = 0;
+  // zero-copy ingest (swtpg_register_buffer): where each unit of the batch lies if it was NOT copied into h_frames
+  std::vector<const uint8_t*> borrowed;    // [n_links][max_units], nullptr = staged copy
+  std::atomic<uint32_t> n_borrowed{ 0 };
 };
 
 } // namespace
@@ -92,6 +95,14 @@ struct swtpg_handle
   std::mutex dispatch_mu;
   uint64_t next_dispatch = 0; // next batch index to dispatch (batches complete in order)
   uint64_t next_poll = 0;     // next batch index to hand to poll
+
+  // host ranges registered for zero-copy ingest; link_range caches the last hit per link (touched by that link's thread only)
+  struct HostRange { uintptr_t lo = 0, hi = 0; };
+  std::vector<HostRange> ranges;
+  std::mutex ranges_mu;
+  std::unique_ptr<HostRange[]> link_range;
+  std::atomic<uint64_t> ranges_epoch{ 0 };
+  std::unique_ptr<uint64_t[]> link_range_epoch;
 
   swtpg_counters counters{};
   std::atomic<uint64_t> submit_busy{ 0 };
@@ -457,6 +468,7 @@ ensure_slots(swtpg_handle* h)
     SW_CUDA(h, cudaEventCreateWithFlags(&s->ev_kernel, cudaEventDisableTiming));
     SW_CUDA(h, cudaEventCreateWithFlags(&s->ev_count, cudaEventDisableTiming));
     SW_CUDA(h, cudaEventCreateWithFlags(&s->ev_tps, cudaEventDisableTiming));
+    s->borrowed.assign(size_t(h->cfg.n_links) * h->cfg.max_units, nullptr);
     s->batch.store(i);
     s->remaining.store(h->cfg.n_links * h->cfg.max_units);
     s->state.store(kFilling);
@@ -477,6 +489,7 @@ dispatch_slot(swtpg_handle* h, Slot& s, const uint32_t* n_units)
   uint64_t units = uint64_t(stride) * h->cfg.n_links;
   // H2D on the slot's own stream (overlaps the previous batch's kernel), kernel on the handle's compute stream
   // (state is carried: kernels must run in batch order), TP count + TPs back on the slot's stream.
+  const bool any_borrowed = s.n_borrowed.load(std::memory_order_acquire) != 0;
   if (n_units) {
     units = 0;
     for (uint32_t l = 0; l < h->cfg.n_links; ++l) {
@@ -485,6 +498,34 @@ dispatch_slot(swtpg_handle* h, Slot& s, const uint32_t* n_units)
     }
     SW_CUDA(h, cudaMemcpyAsync(s.d_nunits, s.h_nunits, size_t(h->cfg.n_links) * 4, cudaMemcpyHostToDevice, s.stream));
     d_nu = s.d_nunits;
+  }
+  if (any_borrowed) {
+    // Zero-copy ingest: the copy engine reads borrowed units where they lie (registered host memory), one async copy per
+    // contiguous run — a link's superchunk is one run unless the latency buffer wrapped inside it; staged units come from
+    // the slot's pinned buffer as before.
+    for (uint32_t l = 0; l < h->cfg.n_links; ++l) {
+      const uint32_t nu = n_units ? n_units[l] : stride;
+      const size_t row = size_t(l) * stride;
+      uint32_t u = 0;
+      while (u < nu) {
+        const uint8_t* src = s.borrowed[row + u];
+        const bool staged = src == nullptr;
+        if (staged)
+          src = s.h_frames + (row + u) * h->unit_bytes;
+        uint32_t v = u + 1;
+        while (v < nu) {
+          const uint8_t* nxt = s.borrowed[row + v];
+          if (staged ? nxt != nullptr : nxt != src + size_t(v - u) * h->unit_bytes)
+            break;
+          ++v;
+        }
+        SW_CUDA(h, cudaMemcpyAsync(s.d_frames + (row + u) * h->unit_bytes, src, size_t(v - u) * h->unit_bytes, cudaMemcpyHostToDevice,
+                                   s.stream));
+        u = v;
+      }
+    }
+    h->counters.h2d_bytes += units * h->unit_bytes;
+  } else if (n_units) {
     // ragged: copy each link's valid prefix only
     for (uint32_t l = 0; l < h->cfg.n_links; ++l)
       if (n_units[l])
@@ -681,6 +722,8 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
   SW_CUDA(hp, cudaMalloc(&h->d_nunits, size_t(cfg->n_links) * 4));
   SW_CUDA(hp, cudaMallocHost(&h->h_nunits, size_t(cfg->n_links) * 4));
   h->submitted.reset(new std::atomic<uint64_t>[cfg->n_links]);
+  h->link_range.reset(new swtpg_handle::HostRange[cfg->n_links]);
+  h->link_range_epoch.reset(new uint64_t[cfg->n_links]());
   for (uint32_t l = 0; l < cfg->n_links; ++l)
     h->submitted[l].store(0);
   *out = h.release();
@@ -694,6 +737,9 @@ swtpg_destroy(swtpg_handle* h)
     return;
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
+  for (const auto& r : h->ranges)
+    if (cudaHostUnregister(reinterpret_cast<void*>(r.lo)) != cudaSuccess)
+      cudaGetLastError();
   for (auto& s : h->slots)
     free_slot(*s);
   if (h->d_state) cudaFree(h->d_state);
@@ -729,6 +775,7 @@ swtpg_start(swtpg_handle* h)
     Slot& sl = *h->slots[i];
     sl.batch.store(i);
     sl.remaining.store(h->cfg.n_links * h->cfg.max_units);
+    sl.n_borrowed.store(0);
     sl.state.store(kFilling);
   }
   h->next_dispatch = h->next_poll = 0;
@@ -880,6 +927,31 @@ swtpg_process_host_debug(swtpg_handle* h, const void* frames, const uint32_t* n_
 }
 
 // ---- streaming path ---------------------------------------------------------------------------------------------------
+// Is [unit, unit + bytes) inside a range registered with swtpg_register_buffer? Lock-free on the hot path: every link's
+// producer thread keeps the last range it hit (a link's payloads come from one latency buffer).
+static bool
+is_registered(swtpg_handle* h, uint32_t link, const void* unit, size_t bytes)
+{
+  const uint64_t epoch = h->ranges_epoch.load(std::memory_order_acquire);
+  if (epoch == 0)
+    return false; // nothing was ever registered
+  const uintptr_t a = reinterpret_cast<uintptr_t>(unit);
+  swtpg_handle::HostRange& c = h->link_range[link];
+  if (h->link_range_epoch[link] == epoch) {
+    if (a >= c.lo && a + bytes <= c.hi)
+      return true;
+    if (c.hi == 0)
+      return false; // cached miss: this link's payloads are not in registered memory
+  }
+  std::lock_guard<std::mutex> lk(h->ranges_mu); // first payload of the link, or the set of ranges changed, or another range
+  c = swtpg_handle::HostRange{};
+  for (const auto& r : h->ranges)
+    if (a >= r.lo && a + bytes <= r.hi)
+      c = r;
+  h->link_range_epoch[link] = h->ranges_epoch.load(std::memory_order_relaxed);
+  return c.hi != 0;
+}
+
 // Copy of one payload into the pinned staging slot (csrc/stage_copy.cpp: non-temporal stores where the CPU has AVX2).
 extern "C" void swtpg_stage_copy(void* dst, const void* src, size_t bytes);
 
@@ -907,13 +979,61 @@ swtpg_submit(swtpg_handle* h, uint32_t link, const void* unit, size_t bytes)
     h->submit_busy.fetch_add(1, std::memory_order_relaxed);
     return SWTPG_ERR_BUSY; // ring full: the caller drops or retries, like a failed try_send
   }
-  swtpg_stage_copy(s.h_frames + (size_t(link) * h->cfg.max_units + u) * h->unit_bytes, unit, bytes);
+  const size_t idx = size_t(link) * h->cfg.max_units + u;
+  if (is_registered(h, link, unit, bytes)) { // zero-copy: the batch's H2D reads the unit where it lies
+    s.borrowed[idx] = static_cast<const uint8_t*>(unit);
+    s.n_borrowed.fetch_add(1, std::memory_order_relaxed);
+  } else {
+    s.borrowed[idx] = nullptr;
+    swtpg_stage_copy(s.h_frames + idx * h->unit_bytes, unit, bytes);
+  }
   h->submitted[link].store(seq + 1, std::memory_order_release);
   if (s.remaining.fetch_sub(1, std::memory_order_acq_rel) == 1) { // this unit completed the batch
     std::lock_guard<std::mutex> lk(h->dispatch_mu);
     SW_CUDA(h, cudaSetDevice(h->cfg.device));
     return dispatch_slot(h, s, nullptr);
   }
+  return SWTPG_OK;
+}
+
+swtpg_status
+swtpg_register_buffer(swtpg_handle* h, void* base, size_t bytes)
+{
+  if (!h || !base || bytes == 0)
+    return SWTPG_ERR_INVALID_ARG;
+  SW_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaError_t e = cudaHostRegister(base, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered)
+    cudaGetLastError(); // e.g. two handles (GPUs) sharing one latency buffer: fine, it is pinned
+  else
+    SW_CUDA(h, e);
+  std::lock_guard<std::mutex> lk(h->ranges_mu);
+  const uintptr_t lo = reinterpret_cast<uintptr_t>(base);
+  h->ranges.push_back({ lo, lo + bytes });
+  h->ranges_epoch.fetch_add(1, std::memory_order_release);
+  return SWTPG_OK;
+}
+
+swtpg_status
+swtpg_unregister_buffer(swtpg_handle* h, void* base)
+{
+  if (!h || !base)
+    return SWTPG_ERR_INVALID_ARG;
+  swtpg_status st = swtpg_sync(h); // no copy engine may still be reading from it
+  if (st != SWTPG_OK)
+    return st;
+  {
+    std::lock_guard<std::mutex> lk(h->ranges_mu);
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(base);
+    auto it = std::find_if(h->ranges.begin(), h->ranges.end(), [lo](const swtpg_handle::HostRange& r) { return r.lo == lo; });
+    if (it == h->ranges.end())
+      return fail(h, SWTPG_ERR_INVALID_ARG, "buffer was not registered with this handle");
+    h->ranges.erase(it);
+    h->ranges_epoch.fetch_add(1, std::memory_order_release);
+  }
+  cudaError_t e = cudaHostUnregister(base);
+  if (e != cudaSuccess)
+    cudaGetLastError(); // registered by another handle first, or already gone
   return SWTPG_OK;
 }
 
@@ -1014,6 +1134,7 @@ swtpg_poll(swtpg_handle* h, swtpg_tp* out, size_t cap, size_t* n_out)
       break; // caller's buffer is full; the rest comes with the next poll
     // recycle the slot for batch next_poll + n_slots
     s.remaining.store(h->cfg.n_links * h->cfg.max_units);
+    s.n_borrowed.store(0, std::memory_order_relaxed);
     s.batch.store(h->next_poll + h->slots.size(), std::memory_order_release);
     s.state.store(kFilling, std::memory_order_release);
     h->next_poll++;

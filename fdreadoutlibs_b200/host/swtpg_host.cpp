@@ -139,6 +139,23 @@ TpgEngine::submit(uint32_t link, const void* unit, size_t bytes)
 }
 
 void
+TpgEngine::register_latency_buffer(void* base, size_t bytes)
+{
+  std::lock_guard<std::mutex> lk(m_mu);
+  if (!m_h)
+    throw std::runtime_error("TpgEngine::register_latency_buffer before conf");
+  check(m_h, swtpg_register_buffer(m_h, base, bytes), "swtpg_register_buffer");
+}
+
+void
+TpgEngine::unregister_latency_buffer(void* base)
+{
+  std::lock_guard<std::mutex> lk(m_mu);
+  if (m_h)
+    check(m_h, swtpg_unregister_buffer(m_h, base), "swtpg_unregister_buffer");
+}
+
+void
 TpgEngine::drain(bool wait)
 {
   std::unique_lock<std::mutex> lk(m_drain_mu, std::defer_lock);
@@ -381,7 +398,8 @@ WIBEthFrameProcessor::find_hits(constframeptr fp, WIBEthFrameHandler* frame_hand
     }
     frame_handler->first_hit = false;
   }
-  // The frame is only borrowed for the duration of this call: swtpg_submit copies it into the pinned staging slot.
+  // The frame is only borrowed for the duration of this call: swtpg_submit copies it into the pinned staging slot — unless it
+  // lies in a latency buffer registered with the engine, which the copy engine then reads directly (zero-copy ingest).
   while (!m_engine->submit(frame_handler->link, fp->data, sizeof fp->data)) {
     if (!m_block) {
       ++m_frames_dropped;
@@ -980,6 +998,22 @@ uint64_t
 swtpg_host_last_daq_time(swtpg_host* h, uint32_t link)
 {
   return h->eth.empty() ? h->wib2[link]->get_last_daq_time() : h->eth[link]->get_last_daq_time();
+}
+
+// Zero-copy ingest: register / unregister the array the pushed payloads live in (the "latency buffer")
+int
+swtpg_host_register_buffer(swtpg_host* h, void* base, size_t bytes, int on)
+{
+  try {
+    if (on)
+      h->engine->register_latency_buffer(base, bytes);
+    else
+      h->engine->unregister_latency_buffer(base);
+  } catch (const std::exception& e) {
+    g_host_error = e.what();
+    return -1;
+  }
+  return 0;
 }
 
 // position -> offline channel map of a link (after its first frame)

@@ -225,6 +225,9 @@ public:
   // per-position RS memory factor of one link, by FRAME channel (src/wibeth/WIBEthFrameProcessor.cpp:437-456 + setState)
   void set_link_memory_factor(uint32_t link, const uint16_t* by_channel, uint32_t n_channels);
   bool submit(uint32_t link, const void* unit, size_t bytes); // false = back-pressure
+  // Zero-copy ingest: the latency buffer(s) the constframeptrs point into (swtpg_register_buffer). After conf().
+  void register_latency_buffer(void* base, size_t bytes);
+  void unregister_latency_buffer(void* base);
   void drain(bool wait = false);               // poll completed batches and hand TPs to their processors
   swtpg_handle* handle() { return m_h; }
   uint32_t n_links() const { return m_cfg.n_links; }

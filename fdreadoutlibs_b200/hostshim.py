@@ -47,7 +47,7 @@ EXPORTS = ["swtpg_host_tpsets_create", "swtpg_host_tpsets_destroy", "swtpg_host_
            "swtpg_host_tpsets_cutoff", "swtpg_host_tpsets_count", "swtpg_host_tpsets_get", "swtpg_host_tpsets_info",
            "swtpg_host_push_parallel", "swtpg_host_last_error", "swtpg_host_create", "swtpg_host_destroy", "swtpg_host_start", "swtpg_host_stop", "swtpg_host_push",
            "swtpg_host_take_tps", "swtpg_host_get_info", "swtpg_host_error_count", "swtpg_host_misconfigurations",
-           "swtpg_host_last_daq_time", "swtpg_host_register_channel_map"]
+           "swtpg_host_last_daq_time", "swtpg_host_register_channel_map", "swtpg_host_register_buffer"]
 
 _lib = None
 
@@ -74,6 +74,7 @@ def host_lib():
         lib.swtpg_host_last_daq_time.restype = C.c_uint64
         lib.swtpg_host_last_daq_time.argtypes = [C.c_void_p, C.c_uint32]
         lib.swtpg_host_register_channel_map.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.swtpg_host_register_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
         lib.swtpg_host_tpsets_create.restype = C.c_void_p
         lib.swtpg_host_tpsets_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32]
         lib.swtpg_host_tpsets_destroy.argtypes = [C.c_void_p]
@@ -140,6 +141,12 @@ class FrameProcessors:
         """payloads: writable uint8 [n_links, n_units, unit_bytes]; one C++ thread per link pushes its units concurrently."""
         assert payloads.dtype == np.uint8 and payloads.flags["C_CONTIGUOUS"] and payloads.flags["WRITEABLE"] and payloads.shape[0] == self.n_links
         self._check(self.lib.swtpg_host_push_parallel(self.h, payloads.ctypes.data, payloads.shape[1]))
+
+    def register_buffer(self, payloads: np.ndarray, on: bool = True):
+        """Zero-copy ingest: declare `payloads` (the array later passed to push / push_parallel) as the latency buffer, so that
+        find_hits hands the copy engine pointers instead of copying each frame. Unregister (on=False) before freeing it."""
+        assert payloads.dtype == np.uint8 and payloads.flags["C_CONTIGUOUS"]
+        self._check(self.lib.swtpg_host_register_buffer(self.h, payloads.ctypes.data, payloads.nbytes, 1 if on else 0))
 
     def take_tps(self, link: int, cap: int = 1 << 18) -> np.ndarray:
         out = np.zeros(cap, dtype=HOST_TP_DTYPE)

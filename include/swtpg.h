@@ -190,6 +190,19 @@ swtpg_status swtpg_process_host_debug(swtpg_handle* h, const void* frames, const
  * the per-hit m_tp_sink->try_send loop's source (src/wibeth/WIBEthFrameProcessor.cpp:555).
  */
 swtpg_status swtpg_submit(swtpg_handle* h, uint32_t link, const void* unit, size_t bytes);
+/*
+ * Zero-copy ingest. The constframeptr a post-processing task receives points INTO the link's latency buffer
+ * (readoutlibs IterableQueueModel / FixedRateQueueModel: one contiguous array of payloads; SURVEY.md 8b "Ownership").
+ * Registering that array here (cudaHostRegister) makes swtpg_submit record the pointer instead of copying the payload:
+ * when the batch is dispatched the copy engine reads the units where they lie, one async copy per link and contiguous
+ * run (a superchunk is one run unless the buffer wrapped inside it). Units outside every registered range are still
+ * copied, so both kinds may be mixed. Contract: a submitted unit must stay unmodified until its batch's host-to-device
+ * copy has completed — at most n_slots superchunks after the submit, milliseconds against a latency buffer's seconds of
+ * retention; swtpg_sync (or stop) ends every such borrow. Any number of ranges (one per link is typical).
+ * swtpg_unregister_buffer waits for the handle to drain first.
+ */
+swtpg_status swtpg_register_buffer(swtpg_handle* h, void* base, size_t bytes);
+swtpg_status swtpg_unregister_buffer(swtpg_handle* h, void* base);
 swtpg_status swtpg_flush(swtpg_handle* h);
 swtpg_status swtpg_poll(swtpg_handle* h, swtpg_tp* out, size_t cap, size_t* n_out);
 /* Blocks until every dispatched batch has completed (used by stop and by tests). */

@@ -300,6 +300,42 @@ def test_streaming_submit_poll_equals_batch():
     assert_same_tps(np.concatenate(got), want, "streaming")
 
 
+def test_streaming_zero_copy_from_a_registered_latency_buffer():
+    """swtpg_register_buffer: payloads submitted from inside a registered array are not copied by submit; the copy engine reads
+    them where they lie when the superchunk is dispatched. Link 0 and 1 come straight out of the registered buffer (one
+    contiguous run per superchunk), link 2 out of a ring that wraps inside a superchunk (two runs), link 3 from unregistered
+    memory (staged copy as before), link 4 alternates between registered and unregistered payloads. Same TPs as the oracle."""
+    n_links, n_units, sc = 5, 24, 8
+    units = S.gen_wibeth_host(S.gen_params(47, 0.5), n_links, n_units)
+    want, _ = B.oracle_process_links(B.make_config(threshold=20), units)
+    latency_buffer = units.copy()                       # the registered memory
+    ring = np.roll(latency_buffer[2], 3, axis=0).copy() # unit u of link 2 lives at ring[(u + 3) % n_units]
+    outside = units.copy()                              # never registered
+    got = []
+    with S.TPGenerator(n_links, sc, threshold=20, n_slots=3) as g:
+        g.register_buffer(latency_buffer)
+        g.register_buffer(ring)
+        g.start()
+        for u in range(n_units):
+            srcs = [latency_buffer[0, u], latency_buffer[1, u], ring[(u + 3) % n_units], outside[3, u],
+                    latency_buffer[4, u] if u % 3 else outside[4, u]]
+            for l, src in enumerate(srcs):
+                while not g.submit(l, src):
+                    got.append(g.poll())
+            got.append(g.poll())
+        g.flush()
+        g.sync()
+        for _ in range(8):
+            got.append(g.poll())
+        c = g.counters()
+        assert c["units_processed"] == n_links * n_units and c["h2d_bytes"] == n_links * n_units * 7200
+        g.unregister_buffer(ring)
+        g.unregister_buffer(latency_buffer)
+        with pytest.raises(S.SwtpgError):
+            g.unregister_buffer(outside)
+    assert_same_tps(np.concatenate(got), want, "zero-copy streaming")
+
+
 def test_streaming_links_out_of_step():
     """Links are fed by independent threads: one link may run a whole superchunk ahead of the others."""
     n_links, n_units, sc = 3, 8, 4

@@ -252,6 +252,25 @@ def test_wib2_frame_processor_end_to_end(algorithm, algo_id):
 
 
 @pytest.mark.gpu
+def test_zero_copy_latency_buffer_through_the_frame_processors():
+    """find_hits with the payload array registered as the latency buffer (TpgEngine::register_latency_buffer): no per-frame
+    copy on the host, identical TriggerPrimitives."""
+    n_links, n_units = 12, 40
+    units = S.gen_wibeth_host(S.gen_params(66, 0.4), n_links, n_units)
+    want, _ = B.oracle_process_links(B.make_config(threshold=25), units)
+    payloads = units.copy()
+    with H.FrameProcessors(n_links, 8, threshold=25, block_on_backpressure=True) as fp:
+        fp.register_buffer(payloads)
+        fp.start()
+        fp.push_parallel(payloads)
+        fp.stop()
+        got = [fp.take_tps(l) for l in range(n_links)]
+        fp.register_buffer(payloads, on=False)
+    for l in range(n_links):
+        assert as_tuples(got[l]) == expected_host_tps(want[want["link"] == l], l, slot=l // 8), f"link {l}"
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("block", [True, False])
 def test_one_thread_per_link_concurrently(block):
     """The reference's threading model (one post-processing thread per link, src/wibeth/WIBEthFrameProcessor.cpp:231): 24 C++
