@@ -361,6 +361,7 @@ def main():
         torch.cuda.synchronize()
         others["wib2_simple"] = timed("wib2", "SimpleThreshold", args.threshold, d_w.data_ptr(), w_links, w_units, 5664, 256 * 12, 10)
         others["wib2_fir_iqr_thr5"] = timed("wib2", "FIR", 5, d_w.data_ptr(), w_links, w_units, 5664, 256 * 12, 38)
+        others["wib2_abs_rs"] = timed("wib2", "AbsRS", args.threshold, d_w.data_ptr(), w_links, w_units, 5664, 256 * 12, 24)
         del d_w
 
     # --- the drop-in path as a readout application drives it: one C++ thread per link calling the frame processor's

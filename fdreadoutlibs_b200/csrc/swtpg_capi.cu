@@ -65,7 +65,7 @@ struct swtpg_handle
   swtpg_config cfg{};
   uint32_t unit_bytes = 0, channels = 0, ticks = 0, groups_per_link = 0, n_groups = 0;
   uint32_t tp_capacity = 0;
-  bool fast_simple = false, fast_fir = false, fast_rs = false;
+  bool fast_simple = false, fast_fir = false, fast_rs = false, fast_rs_wib2 = false;
   bool started = false;
 
   cudaStream_t stream = nullptr; // batch path + all kernels (state is carried batch to batch: kernels are ordered)
@@ -282,7 +282,8 @@ launch(const swtpg_handle* h, const KernelParams& kp, cudaStream_t s)
                               : launch_wib2<ScalarAlgo<SWTPG_ALGO_SIMPLE_THRESHOLD, true>, DUMP>(kp, s);
       case SWTPG_ALGO_FIR_IQR:
         return h->fast_fir ? launch_wib2<PackedFirIqr, DUMP>(kp, s) : launch_wib2<ScalarAlgo<SWTPG_ALGO_FIR_IQR, true>, DUMP>(kp, s);
-      case SWTPG_ALGO_ABS_RS: return launch_wib2<ScalarAlgo<SWTPG_ALGO_ABS_RS, true>, DUMP>(kp, s);
+      case SWTPG_ALGO_ABS_RS:
+        return h->fast_rs_wib2 ? launch_wib2<PackedRsIqrWib2, DUMP>(kp, s) : launch_wib2<ScalarAlgo<SWTPG_ALGO_ABS_RS, true>, DUMP>(kp, s);
       default: return cudaErrorNotSupported;
     }
   }
@@ -696,6 +697,12 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
 
   h->fast_rs = !wib2 && (cfg->algorithm == SWTPG_ALGO_ABS_RS || cfg->algorithm == SWTPG_ALGO_STANDARD_RS) && cfg->threshold <= 32767 &&
                cfg->frugal_acc_limit >= 1 && cfg->frugal_acc_limit <= 1000 && getenv("SWTPG_FORCE_SCALAR") == nullptr;
+  // WIB2 AbsRS fast path validity (see PackedRsIqrWib2); threshold >= 1 is enforced below for the algorithm as such
+  if (wib2 && cfg->algorithm == SWTPG_ALGO_ABS_RS && cfg->threshold >= 1) {
+    const uint32_t e = h->cfg.tap_exponent, mult = 1u << e;
+    const uint64_t sigma_max = (1u << 15) / (uint64_t(mult) * cfg->threshold);
+    h->fast_rs_wib2 = e >= 1 && e <= 10 && (sigma_max + 3) * cfg->threshold < 65536 && getenv("SWTPG_FORCE_SCALAR") == nullptr;
+  }
   // Packed FIR fast path validity (see PackedFirIqr): binomial taps, and (sigmaMax + 3) * multiplier * threshold < 2^16
   {
     static const int16_t kBinomial[8] = { 1, 6, 15, 20, 15, 6, 1, 0 };

@@ -925,8 +925,8 @@ struct PackedFirIqr
     Q = add2(add2(Q, a), b);
   }
 
-  // One tick: returns the filter output of this tick; sig3 = min(sigma, sigmaMax) + 3.
-  __device__ __forceinline__ uint32_t tick(uint32_t S, uint32_t& sig3)
+  // The three frugal trackers of one tick; returns s' + 1 = raw - median + 1 (updated median); sig3 = min(sigma, sigmaMax) + 3.
+  __device__ __forceinline__ uint32_t track(uint32_t S, uint32_t& sig3)
   {
     const uint32_t sg1 = addclamp2(S, Mq, 0x00020002u);               // sign(raw - median) + 1, OLD median   (:108-117)
     const uint32_t ltf = eq2_one(sg1, 0u), gtf = eq2_one(sg1, 0x00020002u);
@@ -940,8 +940,13 @@ struct PackedFirIqr
     const uint32_t dn1 = hfma2_sat_bits(T, kNegOne, kNegL);
     A = hfma2_bits(ne2_abs_one(T, kUp), T, kNegTiny);
     Mq = add2(add2(Mq, upm), dn1);
-    const uint32_t x = addmin2(add2(S, Mq), 0xFFFFFFFFu, xmax);       // min(raw - median, adcMax)           (:128,142)
     sig3 = addmin2(Q75p, Q25q, sig3max);                              // min(q75 - q25, sigmaMax) + 3        (:131-134)
+    return add2(S, Mq);
+  }
+  // One tick: returns the filter output of this tick.
+  __device__ __forceinline__ uint32_t tick(uint32_t S, uint32_t& sig3)
+  {
+    const uint32_t x = addmin2(track(S, sig3), 0xFFFFFFFFu, xmax);    // min(raw - median, adcMax)           (:128,142)
     const uint32_t filt = o2;                                         // window = samples t-8 .. t-2          (:160-201)
     cascade(x);
     return filt;
@@ -1011,6 +1016,155 @@ struct PackedFirIqr
 #pragma unroll
       for (int g = 0; g < G; ++g)
         hit_update<false>(filt[g], threshold(sig3[g]), ctx, t0 + g);
+    }
+    if (ctx.stage->must_flush())
+      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
+  }
+};
+
+// =====================================================================================================================
+// Packed fast path: WIB2 AbsRS (wib2/tpg/ProcessRSAVX2.hpp:24-330) — the IQR threshold of the FIR finder applied to an absolute
+// running sum. Per tick and channel:
+//   quartile / median trackers exactly as PackedFirIqr (every limit 10, :100-126);  s' = raw - median
+//   RS = mulhrs(RS * 8 + |s'| * 5, 32768/10)      literal factors (:29-33,:137-150), mullo / add mod 2^16
+//   RS -= median_RS after a frugal update of median_RS with RS (:152-159)
+//   sigma = min(q75 - q25, sigmaMax), sigmaMax = 2^15 / (multiplier * threshold) (:36);  over = RS > sigma * threshold (:198)
+//   charge = adds(charge, (over ? adds(RS, median_RS) : 0) >> tap_exponent) (:210-213);  tover = adds(tover, over)
+// |RS before subtraction| <= 3277 (mulhrs of a 16-bit value by 3276), so adds(RS, median_RS) is that value again and never
+// saturates. The threshold is one packed IMAD while every sigma of the warp is >= 0 (as in PackedFirIqr); a group that sees a
+// negative sigma recomputes it with the reference's 4 x int64-lane semantics. Validity (checked by the host):
+// 1 <= tap_exponent <= 10, threshold >= 1, (sigmaMax + 3) * threshold < 2^16.
+// =====================================================================================================================
+struct PackedRsIqrWib2 : PackedFirIqr
+{
+  static constexpr int kGroupUnroll = 1;
+  uint32_t RS1, MRq, AR; // RS + 1 (after median subtraction); 1 - median_RS; (acc_RS - 1) as fp16 subnormal
+
+  __device__ __forceinline__ void configure(const KernelParams& p)
+  {
+    PackedFirIqr::configure(p);
+    const uint32_t sigma_max = (1u << 15) / (mult * p.threshold); // ProcessRSAVX2.hpp:36
+    sig3max = (sigma_max + 3u) * 0x00010001u;
+    K = p.threshold;                                             // sigma * info.threshold: no multiplier (:198)
+    Kneg3 = 0u - 3u * K * 0x00010001u;
+  }
+  __device__ __forceinline__ void load(const uint32_t* st, uint32_t lane, uint32_t)
+  {
+    Mq = add2(~st[SV_MEDIAN * 32 + lane], 0x00020002u);
+    A = to_sm(add2(st[SV_ACCUM * 32 + lane], 0xFFFFFFFFu));
+    Q25q = add2(~st[SV_Q25 * 32 + lane], 0x00020002u);
+    A25 = to_sm(st[SV_A25 * 32 + lane]);
+    Q75p = add2(st[SV_Q75 * 32 + lane], 0x00020002u);
+    A75 = to_sm(st[SV_A75 * 32 + lane]);
+    prev = st[SV_PREV * 32 + lane];
+    C = st[SV_CHARGE * 32 + lane];
+    Tn = neg2(st[SV_TOVER * 32 + lane]);
+    RS1 = add2(st[SV_RS * 32 + lane], 0x00010001u);
+    MRq = add2(~st[SV_MED_RS * 32 + lane], 0x00020002u);
+    AR = to_sm(add2(st[SV_ACC_RS * 32 + lane], 0xFFFFFFFFu));
+    kphase0 = 0;
+  }
+  __device__ __forceinline__ void store(uint32_t* st, uint32_t lane, uint32_t) const
+  {
+    st[SV_MEDIAN * 32 + lane] = median();
+    st[SV_ACCUM * 32 + lane] = add2(from_sm(A), 0x00010001u);
+    st[SV_Q25 * 32 + lane] = add2(~Q25q, 0x00020002u);
+    st[SV_A25 * 32 + lane] = from_sm(A25);
+    st[SV_Q75 * 32 + lane] = add2(Q75p, 0xFFFEFFFEu);
+    st[SV_A75 * 32 + lane] = from_sm(A75);
+    st[SV_PREV * 32 + lane] = prev;
+    st[SV_CHARGE * 32 + lane] = C;
+    st[SV_TOVER * 32 + lane] = neg2(Tn);
+    st[SV_RS * 32 + lane] = add2(RS1, 0xFFFFFFFFu);
+    st[SV_MED_RS * 32 + lane] = add2(~MRq, 0x00020002u);
+    st[SV_ACC_RS * 32 + lane] = add2(from_sm(AR), 0x00010001u);
+  }
+  __device__ __forceinline__ uint32_t phase_after(uint32_t) const { return 0; }
+
+  // One tick: sp1 = s' + 1. Returns RS - median_RS + 1 and, in `raw_rs`, the running sum before the subtraction.
+  __device__ __forceinline__ uint32_t rs_step(uint32_t sp1, uint32_t& raw_rs)
+  {
+    const uint32_t x = add2(sp1, 0xFFFFFFFFu);
+    const uint32_t ax = max2(x, neg2(x));                                     // |s'|
+    // low 16 bits per half: RS * 8 + |s'| * 5, with RS = RS1 - 1 (the packed registers serve as low-half operands)
+    const uint32_t lo = uint32_t(int(RS1) * 8 + (int(ax) * 5 - 8));
+    const uint32_t hi = uint32_t(int(RS1 >> 16) * 8 + (int(ax >> 16) * 5 - 8));
+    const int r_lo = PackedRsWibEth<false>::mulhrs_low(lo), r_hi = PackedRsWibEth<false>::mulhrs_low(hi);
+    raw_rs = __byte_perm(uint32_t(r_lo), uint32_t(r_hi), 0x5410);
+    // frugal update of median_RS with the new running sum (limit 10), then subtract
+    const uint32_t sg1 = addclamp2(raw_rs, MRq, 0x00020002u);
+    const uint32_t T = hadd2_bits(AR, sg1);
+    const uint32_t upm = eq2_mask(T, kUp);
+    const uint32_t dn1 = hfma2_sat_bits(T, kNegOne, kNegL);
+    AR = hfma2_bits(ne2_abs_one(T, kUp), T, kNegTiny);
+    MRq = add2(add2(MRq, upm), dn1);
+    RS1 = add2(raw_rs, MRq);
+    return RS1;
+  }
+
+  template<bool EXACT>
+  __device__ __forceinline__ void hit_update(uint32_t lv1, uint32_t raw_rs, uint32_t thr, const TickCtx& ctx, int t)
+  {
+    const uint32_t lv = add2(lv1, 0xFFFFFFFFu);
+    uint32_t over;
+    if constexpr (EXACT)
+      over = (lo16s(lv) > lo16s(thr) ? 0xFFFFu : 0u) | (hi16s(lv) > hi16s(thr) ? 0xFFFF0000u : 0u);
+    else
+      over = gt2_mask_bf16(max2(lv, 0u), thr);            // 0 <= thr <= 32640                        (:198-200)
+    const uint32_t left = prev & ~over;
+    // (over ? adds(RS, median_RS) : 0) >> tap_exponent, arithmetic per half (the sum may be negative): offset-binary trick
+    const uint32_t u = (add2(raw_rs & over, 0x80008000u) >> shift) & shmask;
+    const uint32_t bias = (0x8000u >> shift) * 0x00010001u;
+    const uint32_t add = add2(u, neg2(bias));
+    const uint32_t Cw = add2(C, add);                     // adds_epi16: wrapping add + repair of the rare overflowing halves
+    const uint32_t ovf = ~(C ^ add) & (C ^ Cw) & 0x80008000u;
+    if (__builtin_expect(ovf != 0u, 0))
+      C = pack2(sat16(lo16s(C) + lo16s(add)), sat16(hi16s(C) + hi16s(add)));
+    else
+      C = Cw;
+    Tn = addmax2(Tn, over, 0x80018001u);                  // tover = adds(tover, 1)
+    prev = over;
+    if (left != 0u) {
+      // accepted iff hit_charge != 0 (src/wib2/WIB2FrameProcessor.cpp:429): decided in flush on the masked charge
+      ctx.stage->push(HitStage::meta(ctx.chan0, ctx.unit, uint32_t(t)), C & left, neg2(Tn));
+      C &= ~left;
+      Tn &= ~left;
+    }
+  }
+
+  template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
+  __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
+                                        uint32_t* wav_out)
+  {
+    static_assert(G == 4, "trees below are written for 4 ticks");
+    uint32_t lv[G], rs[G], sig3[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      lv[g] = rs_step(track(extract_pair(rows + g * ROW_WORDS, pp), sig3[g]), rs[g]);
+      if constexpr (DUMP) {
+        ped_out[g] = median();
+        wav_out[g] = add2(lv[g], 0xFFFFFFFFu);
+      }
+    }
+    // conservative quiet test: largest RS of the group (biased by one: still conservative) vs the threshold of its smallest sigma
+    const uint32_t mx = __vimax3_s16x2(__vimax3_s16x2(lv[0], lv[1], lv[2]), lv[3], 0u);
+    const uint32_t smin = __vimin3_s16x2(__vimin3_s16x2(sig3[0], sig3[1], sig3[2]), sig3[3], sig3[3]);
+    uint32_t neg = addmin2(smin, 0xFFFDFFFDu, 0u); // min(sigma, 0) of the group: non-zero <=> some sigma < 0
+    if (ctx.p->debug_flags & 1u)
+      neg = 0xFFFFFFFFu;
+    const uint32_t busy = gt2_mask_bf16(mx, threshold(smin)) | prev | neg;
+    if (__builtin_expect(!__any_sync(0xFFFFFFFFu, busy != 0u), 1))
+      return; // nothing but the trackers and the running sum moves outside hits
+    if (__any_sync(0xFFFFFFFFu, neg != 0u)) { // rare: carries between the positions of a 64-bit lane (H7)
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const uint32_t th = iqr_threshold_exact(add2(sig3[g], 0xFFFDFFFDu), (ctx.chan0 >> 1) & 31u, 1, thr_cfg);
+        hit_update<true>(lv[g], rs[g], th, ctx, t0 + g);
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        hit_update<false>(lv[g], rs[g], threshold(sig3[g]), ctx, t0 + g);
     }
     if (ctx.stage->must_flush())
       flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
