@@ -20,7 +20,10 @@
 #define SWTPG_GROUP_UNROLL 4
 #endif
 #ifndef SWTPG_FIR_GROUP_UNROLL
-#define SWTPG_FIR_GROUP_UNROLL 1
+#define SWTPG_FIR_GROUP_UNROLL 2
+#endif
+#ifndef SWTPG_RS_GROUP_UNROLL
+#define SWTPG_RS_GROUP_UNROLL 2
 #endif
 #ifndef SWTPG_FLOAT_ACC
 #define SWTPG_FLOAT_ACC 1
@@ -640,7 +643,7 @@ struct PackedSimpleWib2 : PackedSimpleWibEth
 template<bool STANDARD>
 struct PackedRsWibEth : PackedSimpleWibEth
 {
-  static constexpr int kGroupUnroll = 1;
+  static constexpr int kGroupUnroll = SWTPG_RS_GROUP_UNROLL;
   static constexpr int kWarpsPerSm = STANDARD ? 20 : 16; // AbsRS: 4 warps per sub-partition beat 5 by 3 % (same sweep)
   uint32_t RS1, MRq, AR;     // RS + 1 (carried value, after median subtraction); 1 - median_RS; (acc_RS - 1) as fp16 subnormal
   int f_lo, f_hi, nf_lo, nf_hi, scale;
