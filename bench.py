@@ -380,17 +380,19 @@ def main():
                 fp.start()
                 fp.push_parallel(h_units[:, :256].copy())  # warm-up: staging ring allocation, first launches
                 n_tp = 0
+                c0 = time.process_time()
                 t0 = time.perf_counter()
                 for _ in range(p_passes):  # the same buffer again and again (emulator mode keeps the timestamps running)
                     fp.push_parallel(h_units)
                     n_tp += sum(fp.take_tps(l, cap=1 << 15).size for l in range(p_links))
                 fp.stop()
                 dt = time.perf_counter() - t0
+                cpu_s = time.process_time() - c0
                 n_tp += sum(fp.take_tps(l, cap=1 << 20).size for l in range(p_links))
                 if zero_copy:
                     fp.register_buffer(h_units, on=False)
             return {"value": p_passes * p_links * p_units * SAMPLES_PER_FRAME / dt, "unit": UNIT, "tps": n_tp,
-                    "host_gbs": p_passes * p_links * p_units * FRAME_BYTES / dt / 1e9,
+                    "host_gbs": p_passes * p_links * p_units * FRAME_BYTES / dt / 1e9, "host_cpu_seconds": cpu_s, "wall_seconds": dt,
                     "real_time_apas": p_passes * p_links * p_units * SAMPLES_PER_FRAME / dt / APA_SAMPLES_PER_S}
 
         copied = run_plugin(False)
@@ -398,9 +400,12 @@ def main():
         plugin.update({"threads": p_links, "links": p_links, "frames_per_link": p_units * p_passes, "superchunk_frames": p_sc,
                        "note": "WIBEthFrameProcessor::find_hits per frame from one thread per link (C++ host shim), TriggerPrimitives out; "
                                "frames lie in a latency buffer registered with swtpg_register_buffer, so find_hits hands over pointers and "
-                               "the copy engine reads the frames where they lie",
+                               "the copy engine reads the frames where they lie. Neither wall time nor host CPU time differs measurably "
+                               "from copy_on_submit on this box: with this few links the path is bounded by the per-link serial speed of "
+                               "the kernel (one warp per link, ~2.1 GB/s = 9x real time per link, batches of one handle run in order) "
+                               "and by 2 threads per host core, not by the 7200-byte copy (profiles/r01_plugin_probe.txt)",
                        "copy_on_submit": dict(copied, note="same run without registration: every frame is copied into the pinned staging "
-                                                           "ring by its link's thread (bounded by that memcpy on the host cores)")})
+                                                           "ring by its link's thread")})
         del h_units
 
     cpu = None
