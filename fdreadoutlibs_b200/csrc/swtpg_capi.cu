@@ -236,7 +236,7 @@ launch_wibeth(const KernelParams& kp, cudaStream_t s)
   return launch_wibeth_geo<Algo, DUMP, GeoDefault>(kp, s);
 }
 
-// WIB2: one 4-warp CTA per link at a time, ring of 4 superchunks; persistent over links.
+// WIB2: one CTA (4 consumer warps + 1 producer warp) per link at a time, ring of 4 superchunks; persistent over links.
 template<class Algo, bool DUMP>
 cudaError_t
 launch_wib2(const KernelParams& kp, cudaStream_t s)
@@ -256,7 +256,7 @@ launch_wib2(const KernelParams& kp, cudaStream_t s)
     if (e != cudaSuccess)
       return e;
     int per_sm = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kWib2Warps * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, (kWib2Warps + 1) * 32, smem);
     if (e != cudaSuccess)
       return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -267,7 +267,7 @@ launch_wib2(const KernelParams& kp, cudaStream_t s)
   const unsigned max_ctas = unsigned(resident[dev]);
   const unsigned rounds = (kp.n_links + max_ctas - 1) / max_ctas;
   const unsigned grid = (kp.n_links + rounds - 1) / rounds; // every CTA walks `rounds` links (+-1)
-  k<<<grid, kWib2Warps * 32, smem, s>>>(kp);
+  k<<<grid, (kWib2Warps + 1) * 32, smem, s>>>(kp); // 4 consumer warps + the producer warp
   return cudaGetLastError();
 }
 

@@ -1379,10 +1379,13 @@ wibeth_kernel(const KernelParams p)
 }
 
 // =====================================================================================================================
-// WIB2 kernel: one CTA of 4 warps per link (256 channels), persistent over links. A superchunk (12 frames x 472 B) is one
-// 5664-byte bulk copy into a CTA-wide ring; warp w consumes channels 64w..64w+63 (112 bytes of every frame's ADC block).
-// full[s]: the copy engine's complete_tx; empty[s]: one arrival per warp. Warp 0 refills, one iteration behind its own
-// consumption so it does not wait for the slowest warp.
+// WIB2 kernel: one CTA of 4 consumer warps + 1 producer warp per link (256 channels), persistent over links. A superchunk
+// (12 frames x 472 B) is one 5664-byte bulk copy into a CTA-wide ring; consumer warp w works on channels 64w..64w+63 (112
+// bytes of every frame's ADC block). full[s]: the copy engine's complete_tx; empty[s]: one arrival per consumer warp. The
+// producer warp (one lane; it sleeps on the empty barriers and issues no other instructions) walks the same link/unit
+// sequence and refills a stage as soon as all four consumers have released it — so no consumer ever waits for another
+// consumer, only for data (before: warp 0 refilled between its own superchunks and 13 % of all warp time was spent waiting
+// on full barriers, profiles/r01_wib2_simple_ncu_full.txt).
 // =====================================================================================================================
 constexpr int kWib2FrameWords = SWTPG_WIB2_FRAME_BYTES / 4; // 118
 constexpr int kWib2Warps = 4;
@@ -1399,7 +1402,7 @@ struct Wib2Smem
 };
 
 template<class Algo, int NSTAGE, bool DUMP>
-__global__ void __launch_bounds__(kWib2Warps * 32)
+__global__ void __launch_bounds__((kWib2Warps + 1) * 32)
 wib2_kernel(const KernelParams p)
 {
   constexpr uint32_t kUnit = SWTPG_WIB2_SUPERCHUNK_BYTES;
@@ -1417,27 +1420,6 @@ wib2_kernel(const KernelParams p)
   auto units_of = [&](uint32_t link) -> uint32_t { return p.n_units ? p.n_units[link] : p.units_stride; };
   auto base_of = [&](uint32_t link) -> const uint8_t* { return p.frames + size_t(link) * p.units_stride * kUnit; };
 
-  // producer cursor (thread 0 only)
-  uint32_t pr_link = blockIdx.x, pr_left = pr_link < p.n_links ? units_of(pr_link) : 0, pr_slot = 0;
-  const uint8_t* pr_src = pr_link < p.n_links ? base_of(pr_link) : nullptr;
-  auto produce = [&]() -> bool {
-    if (pr_left == 0) {
-      do {
-        pr_link += gridDim.x;
-        if (pr_link >= p.n_links)
-          return false;
-        pr_left = units_of(pr_link);
-      } while (pr_left == 0);
-      pr_src = base_of(pr_link);
-    }
-    mbar_arrive_expect_tx(&full[pr_slot], kUnit);
-    bulk_g2s(stages + pr_slot * kUnit, pr_src, kUnit, &full[pr_slot]);
-    pr_slot = pr_slot + 1 == NSTAGE ? 0 : pr_slot + 1;
-    pr_src += kUnit;
-    --pr_left;
-    return true;
-  };
-
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) {
@@ -1446,13 +1428,30 @@ wib2_kernel(const KernelParams p)
     }
     fence_mbar_init();
   }
-  if (lane == 0)
+  if (lane == 0 && warp < kWib2Warps)
     *hits.cnt = 0u;
   __syncthreads(); // the only CTA-wide barrier: mbarriers visible before anyone waits on them
-  if (threadIdx.x == 0 && blockIdx.x < p.n_links)
-    for (int s = 0; s < NSTAGE; ++s)
-      if (!produce())
-        break;
+
+  if (warp == kWib2Warps) { // producer warp: one lane feeds the ring for every link this CTA walks
+    if (lane != 0)
+      return;
+    uint32_t slot = 0, round = 0;
+    for (uint32_t link = blockIdx.x; link < p.n_links; link += gridDim.x) {
+      const uint32_t n_units = units_of(link);
+      const uint8_t* src = base_of(link);
+      for (uint32_t unit = 0; unit < n_units; ++unit, src += kUnit) {
+        if (round != 0)
+          mbar_wait(&empty[slot], (round - 1u) & 1u); // all four consumers released the stage's previous contents
+        mbar_arrive_expect_tx(&full[slot], kUnit);
+        bulk_g2s(stages + slot * kUnit, src, kUnit, &full[slot]);
+        if (++slot == NSTAGE) {
+          slot = 0;
+          ++round;
+        }
+      }
+    }
+    return;
+  }
 
   Algo algo;
   algo.configure(p);
@@ -1465,8 +1464,6 @@ wib2_kernel(const KernelParams p)
   const uint32_t row0 = p.wib2_adc_offset / 4 + warp * 28; // word offset of this warp's 112 bytes inside a frame
 
   uint32_t stg = 0, phase = 0;       // consumer ring position / full-barrier phase
-  uint32_t prev_stg = 0, prev_phase = 0;
-  bool have_prev = false;
   for (uint32_t link = blockIdx.x; link < p.n_links; link += gridDim.x) {
     const uint32_t n_units = units_of(link);
     if (n_units == 0)
@@ -1511,15 +1508,6 @@ wib2_kernel(const KernelParams p)
       __syncwarp(); // this warp is done with the stage
       if (lane == 0)
         mbar_arrive(&empty[stg]);
-      if (threadIdx.x == 0) { // refill the stage every warp left one iteration ago
-        if (have_prev) {
-          mbar_wait(&empty[prev_stg], prev_phase);
-          produce();
-        }
-        have_prev = true;
-        prev_stg = stg;
-        prev_phase = phase;
-      }
       if (++stg == NSTAGE) {
         stg = 0;
         phase ^= 1u;
