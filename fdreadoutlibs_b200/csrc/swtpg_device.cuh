@@ -207,6 +207,15 @@ bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// One lane of the (converged) warp, chosen by the hardware: lets ptxas issue the bulk copy from uniform registers without
+// the lane-serialising loop it builds around `if (lane == 0)`.
+__device__ __forceinline__ bool
+elect_one()
+{
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xFFFFFFFF;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void
 mbar_wait(uint64_t* bar, uint32_t parity)
 {

@@ -22,6 +22,9 @@
 #ifndef SWTPG_FIR_GROUP_UNROLL
 #define SWTPG_FIR_GROUP_UNROLL 2
 #endif
+#ifndef SWTPG_ELECT
+#define SWTPG_ELECT 1
+#endif
 #ifndef SWTPG_RS_GROUP_UNROLL
 #define SWTPG_RS_GROUP_UNROLL 2
 #endif
@@ -1252,8 +1255,10 @@ wibeth_kernel(const KernelParams p)
     uint32_t k = 0;
     if (lane == 0)
       k = atomicAdd(p.link_cursor, 1u);
-    return warps_total + __shfl_sync(0xFFFFFFFFu, k, 0);
+    return warps_total + __reduce_add_sync(0xFFFFFFFFu, k); // REDUX: the result lands in a uniform register
   };
+  // same value in every lane -> uniform register, so that the producer's per-chunk bookkeeping stays on the uniform datapath
+  auto uniform = [](uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); };
   if (pr_left != 0)
     fifo_push(first_link);
   auto produce = [&]() { // request one more chunk, if any link is left for this warp (whole warp calls, converged)
@@ -1266,13 +1271,13 @@ wibeth_kernel(const KernelParams p)
           pr_done = true;
           return;
         }
-        pr_left = units_of(pr_link) * kChunksPerUnit;
+        pr_left = uniform(units_of(pr_link) * kChunksPerUnit);
       } while (pr_left == 0);
       fifo_push(pr_link);
       pr_src = base_of(pr_link) + 32;
       pr_in_unit = 0;
     }
-    if (lane == 0) {
+    if (SWTPG_ELECT ? elect_one() : lane == 0) {
       mbar_arrive_expect_tx(&bars[pr_slot], kChunkBytes);
       bulk_g2s(stages + pr_slot * kChunkBytes, pr_src, kChunkBytes, &bars[pr_slot]);
     }
