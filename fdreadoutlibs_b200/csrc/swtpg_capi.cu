@@ -65,7 +65,7 @@ struct swtpg_handle
   swtpg_config cfg{};
   uint32_t unit_bytes = 0, channels = 0, ticks = 0, groups_per_link = 0, n_groups = 0;
   uint32_t tp_capacity = 0;
-  bool fast_simple = false, fast_fir = false, fast_rs = false, fast_rs_wib2 = false;
+  bool fast_simple = false, fast_fir = false, fast_rs = false, fast_rs_wib2 = false, fast_fir_any = false;
   bool started = false;
 
   cudaStream_t stream = nullptr; // batch path + all kernels (state is carried batch to batch: kernels are ordered)
@@ -281,7 +281,9 @@ launch(const swtpg_handle* h, const KernelParams& kp, cudaStream_t s)
         return h->fast_simple ? launch_wib2<PackedSimpleWib2, DUMP>(kp, s)
                               : launch_wib2<ScalarAlgo<SWTPG_ALGO_SIMPLE_THRESHOLD, true>, DUMP>(kp, s);
       case SWTPG_ALGO_FIR_IQR:
-        return h->fast_fir ? launch_wib2<PackedFirIqr, DUMP>(kp, s) : launch_wib2<ScalarAlgo<SWTPG_ALGO_FIR_IQR, true>, DUMP>(kp, s);
+        return h->fast_fir       ? launch_wib2<PackedFirIqr, DUMP>(kp, s)
+               : h->fast_fir_any ? launch_wib2<PackedFirIqrAnyTaps, DUMP>(kp, s)
+                                 : launch_wib2<ScalarAlgo<SWTPG_ALGO_FIR_IQR, true>, DUMP>(kp, s);
       case SWTPG_ALGO_ABS_RS:
         return h->fast_rs_wib2 ? launch_wib2<PackedRsIqrWib2, DUMP>(kp, s) : launch_wib2<ScalarAlgo<SWTPG_ALGO_ABS_RS, true>, DUMP>(kp, s);
       default: return cudaErrorNotSupported;
@@ -298,7 +300,9 @@ launch(const swtpg_handle* h, const KernelParams& kp, cudaStream_t s)
         return h->fast_rs ? launch_wibeth<PackedRsWibEth<true>, DUMP>(kp, s)
                           : launch_wibeth<ScalarAlgo<SWTPG_ALGO_STANDARD_RS, false>, DUMP>(kp, s);
       case SWTPG_ALGO_FIR_IQR:
-        return h->fast_fir ? launch_wibeth<PackedFirIqr, DUMP>(kp, s) : launch_wibeth<ScalarAlgo<SWTPG_ALGO_FIR_IQR, false>, DUMP>(kp, s);
+        return h->fast_fir       ? launch_wibeth<PackedFirIqr, DUMP>(kp, s)
+               : h->fast_fir_any ? launch_wibeth<PackedFirIqrAnyTaps, DUMP>(kp, s)
+                                 : launch_wibeth<ScalarAlgo<SWTPG_ALGO_FIR_IQR, false>, DUMP>(kp, s);
     }
   }
   return cudaErrorNotSupported;
@@ -711,8 +715,10 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
       taps_ok &= h->cfg.fir_taps[i] == kBinomial[i];
     const uint32_t e = h->cfg.tap_exponent, mult = 1u << e;
     const uint64_t sigma_max = (1u << 15) / (mult * 5u);
-    h->fast_fir = cfg->algorithm == SWTPG_ALGO_FIR_IQR && taps_ok && e >= 1 && e <= 10 &&
-                  (sigma_max + 3) * mult * uint64_t(cfg->threshold) < 65536 && getenv("SWTPG_FORCE_SCALAR") == nullptr;
+    const bool range_ok = cfg->algorithm == SWTPG_ALGO_FIR_IQR && e >= 1 && e <= 10 &&
+                          (sigma_max + 3) * mult * uint64_t(cfg->threshold) < 65536 && getenv("SWTPG_FORCE_SCALAR") == nullptr;
+    h->fast_fir = range_ok && taps_ok;      // binomial cascade
+    h->fast_fir_any = range_ok && !taps_ok; // any other taps[0..6]: packed multiply-add chain (PackedFirIqrAnyTaps)
   }
 
   swtpg_handle* hp = h.get();

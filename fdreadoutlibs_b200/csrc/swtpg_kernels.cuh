@@ -989,20 +989,10 @@ struct PackedFirIqr
     }
   }
 
-  template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
-  __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
-                                        uint32_t* wav_out)
+  // Quiet test and hit bookkeeping of one 4-tick group, given its filter outputs and sigmas.
+  template<int G, bool WIB2_UNITS>
+  __device__ __forceinline__ void finish_group(const uint32_t (&filt)[G], const uint32_t (&sig3)[G], const TickCtx& ctx, int t0)
   {
-    static_assert(G == 4, "trees below are written for 4 ticks");
-    uint32_t filt[G], sig3[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      filt[g] = tick(extract_pair(rows + g * ROW_WORDS, pp), sig3[g]);
-      if constexpr (DUMP) {
-        ped_out[g] = median();
-        wav_out[g] = filt[g];
-      }
-    }
     // conservative quiet test: max filter output of the group vs the threshold of the group's smallest sigma
     const uint32_t mx = __vimax3_s16x2(__vimax3_s16x2(filt[0], filt[1], filt[2]), filt[3], 0u);
     const uint32_t smin = __vimin3_s16x2(__vimin3_s16x2(sig3[0], sig3[1], sig3[2]), sig3[3], sig3[3]);
@@ -1025,6 +1015,117 @@ struct PackedFirIqr
     }
     if (ctx.stage->must_flush())
       flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
+  }
+
+  template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
+  __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
+                                        uint32_t* wav_out)
+  {
+    static_assert(G == 4, "trees below are written for 4 ticks");
+    uint32_t filt[G], sig3[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      filt[g] = tick(extract_pair(rows + g * ROW_WORDS, pp), sig3[g]);
+      if constexpr (DUMP) {
+        ped_out[g] = median();
+        wav_out[g] = filt[g];
+      }
+    }
+    finish_group<G, WIB2_UNITS>(filt, sig3, ctx, t0);
+  }
+};
+
+// =====================================================================================================================
+// Packed FIR + IQR for ARBITRARY taps (any int16 taps[0..6], e.g. firwin_int at another multiplier, or a user-supplied filter):
+// same trackers, threshold and hit bookkeeping as PackedFirIqr, but the filter is the reference's multiply-add chain
+//   filt = sum_{j<7} taps[j] * prev_samp[(j + k) % 8]        (mullo_epi16 / add_epi16, mod 2^16; ProcessAVX2FIR.hpp:160-201)
+// on a window of the last 8 clamped samples held in registers, oldest first (w[0] = s(t-8) ... w[7] = s(t-1); the ring phase
+// only matters when the state is loaded and stored). Products are 32-bit IMADs whose low 16 bits are the wrapped result, so
+// the packed register itself is the low-half operand; a half-swapped copy of every window entry serves the high half.
+// 14 IMAD + 2 PRMT per tick instead of the binomial cascade's 6 adds.
+// =====================================================================================================================
+struct PackedFirIqrAnyTaps : PackedFirIqr
+{
+  uint32_t w[8], ws[8]; // window and its half-swapped twin
+  int tap[7];
+
+  __device__ __forceinline__ void configure(const KernelParams& p)
+  {
+    PackedFirIqr::configure(p);
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+      tap[j] = p.taps[j];
+  }
+  static __device__ __forceinline__ uint32_t swap_halves(uint32_t v) { return __byte_perm(v, v, 0x1032); }
+  __device__ __forceinline__ void load(const uint32_t* st, uint32_t lane, uint32_t flags)
+  {
+    Mq = add2(~st[SV_MEDIAN * 32 + lane], 0x00020002u);
+    A = to_sm(add2(st[SV_ACCUM * 32 + lane], 0xFFFFFFFFu));
+    Q25q = add2(~st[SV_Q25 * 32 + lane], 0x00020002u);
+    A25 = to_sm(st[SV_A25 * 32 + lane]);
+    Q75p = add2(st[SV_Q75 * 32 + lane], 0x00020002u);
+    A75 = to_sm(st[SV_A75 * 32 + lane]);
+    prev = st[SV_PREV * 32 + lane];
+    C = st[SV_CHARGE * 32 + lane];
+    Tn = neg2(st[SV_TOVER * 32 + lane]);
+    const uint32_t k = (flags >> 8) & 7u; // next slot to be written = oldest sample
+    kphase0 = k;
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i) {
+      w[i] = st[(SV_RING0 + ((k + i) & 7u)) * 32 + lane];
+      ws[i] = swap_halves(w[i]);
+    }
+  }
+  __device__ __forceinline__ void store(uint32_t* st, uint32_t lane, uint32_t k_end) const
+  {
+    st[SV_MEDIAN * 32 + lane] = median();
+    st[SV_ACCUM * 32 + lane] = add2(from_sm(A), 0x00010001u);
+    st[SV_Q25 * 32 + lane] = add2(~Q25q, 0x00020002u);
+    st[SV_A25 * 32 + lane] = from_sm(A25);
+    st[SV_Q75 * 32 + lane] = add2(Q75p, 0xFFFEFFFEu);
+    st[SV_A75 * 32 + lane] = from_sm(A75);
+    st[SV_PREV * 32 + lane] = prev;
+    st[SV_CHARGE * 32 + lane] = C;
+    st[SV_TOVER * 32 + lane] = neg2(Tn);
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i)
+      st[(SV_RING0 + ((k_end + i) & 7u)) * 32 + lane] = w[i]; // w[0] is the oldest = the slot written next
+  }
+  __device__ __forceinline__ uint32_t tick(uint32_t S, uint32_t& sig3)
+  {
+    const uint32_t x = addmin2(track(S, sig3), 0xFFFFFFFFu, xmax);    // min(raw - median, adcMax)
+    int lo = 0, hi = 0;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      lo += tap[j] * int(w[j]);   // low 16 bits: taps[j] * (low half), any upper bits are discarded below
+      hi += tap[j] * int(ws[j]);
+    }
+    const uint32_t filt = __byte_perm(uint32_t(lo), uint32_t(hi), 0x5410);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      w[j] = w[j + 1];
+      ws[j] = ws[j + 1];
+    }
+    w[7] = x;
+    ws[7] = swap_halves(x);
+    return filt;
+  }
+
+  template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
+  __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
+                                        uint32_t* wav_out)
+  {
+    static_assert(G == 4, "trees below are written for 4 ticks");
+    uint32_t filt[G], sig3[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      filt[g] = tick(extract_pair(rows + g * ROW_WORDS, pp), sig3[g]);
+      if constexpr (DUMP) {
+        ped_out[g] = median();
+        wav_out[g] = filt[g];
+      }
+    }
+    finish_group<G, WIB2_UNITS>(filt, sig3, ctx, t0);
   }
 };
 

@@ -156,6 +156,8 @@ def ref_lib():
         lib.ref_wibeth_expand.argtypes = [C.c_void_p, C.c_void_p]
         lib.ref_wib2_create.restype = C.c_void_p
         lib.ref_wib2_create.argtypes = [C.c_int, C.c_uint16, C.c_int]
+        lib.ref_wib2_create_taps.restype = C.c_void_p
+        lib.ref_wib2_create_taps.argtypes = [C.c_int, C.c_uint16, C.c_int, C.c_void_p, C.c_int]
         lib.ref_wib2_destroy.argtypes = [C.c_void_p]
         lib.ref_wib2_process.restype = C.c_long
         lib.ref_wib2_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -203,9 +205,14 @@ class ReferenceWibEth:
 class ReferenceWib2:
     """Both register selectors of one link (two WIB2FrameHandlers, src/wib2/WIB2FrameProcessor.cpp:224-225)."""
 
-    def __init__(self, impl=REF_WIB2_SIMPLE_AVX2, threshold=60, link_id=0):
+    def __init__(self, impl=REF_WIB2_SIMPLE_AVX2, threshold=60, link_id=0, fir_taps=None, tap_exponent=6):
         self.lib = ref_lib()
-        self.h = [self.lib.ref_wib2_create(impl, threshold, sel) for sel in (0, 1)]
+        if fir_taps is None:
+            self.h = [self.lib.ref_wib2_create(impl, threshold, sel) for sel in (0, 1)]
+        else:
+            taps = np.zeros(8, dtype=np.int16)
+            taps[: len(fir_taps)] = fir_taps
+            self.h = [self.lib.ref_wib2_create_taps(impl, threshold, sel, taps.ctypes.data, tap_exponent) for sel in (0, 1)]
         self.link_id = link_id
 
     def process(self, superchunks: np.ndarray, cap: int = 1 << 18, dump: bool = False):

@@ -315,6 +315,23 @@ ref_wib2_create(int impl, uint16_t threshold, int sel)
   return r;
 }
 
+// Same with caller-supplied taps and exponent (the reference's ProcessingInfo takes both; its frame processor just never
+// passes anything but firwin_int(7, 0.1, 64) and 6): pins the oracle's filter arithmetic for arbitrary taps.
+void*
+ref_wib2_create_taps(int impl, uint16_t threshold, int sel, const int16_t* taps8, int tap_exponent)
+{
+  silence_cout();
+  auto* r = new Wib2Ref;
+  r->impl = impl;
+  r->sel = sel;
+  r->taps.assign(taps8, taps8 + 8);
+  r->hits.reset(new uint16_t[100000]);
+  r->info = std::make_unique<swtpg_wib2::ProcessingInfo<swtpg_wib2::NUM_REGISTERS_PER_FRAME>>(
+    nullptr, swtpg_wib2::FRAMES_PER_MSG, 0, swtpg_wib2::NUM_REGISTERS_PER_FRAME, r->hits.get(), r->taps.data(),
+    (uint8_t)r->taps.size(), (uint8_t)tap_exponent, threshold, 0, 0);
+  return r;
+}
+
 void
 ref_wib2_destroy(void* h)
 {

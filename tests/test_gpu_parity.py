@@ -84,6 +84,42 @@ def test_against_oracle_with_state_and_dumps(algorithm, thr, L):
                 assert (sg[f] == so[f]).all(), f"link {l} state field {f}"
 
 
+ANY_TAPS = [([2, 5, 11, 17, 9, 4, 1], 6), ([-3, 7, 20, 31, 20, 7, -3], 6), ([1, 3, 8, 10, 8, 3, 1], 5), ([300, -700, 1200, 2000, 1200, -700, 300], 6)]
+
+
+@pytest.mark.parametrize("fmt", ["wibeth", "wib2"])
+@pytest.mark.parametrize("taps,exponent", ANY_TAPS)
+def test_fir_with_arbitrary_taps(fmt, taps, exponent):
+    """FIR + IQR with taps other than firwin_int(7, 0.1, 64) — another multiplier, an asymmetric filter, negative and large taps
+    whose products wrap in 16 bits — runs the packed multiply-add policy (PackedFirIqrAnyTaps), not the scalar fallback:
+    TPs, filtered-waveform dump, ring state and quartiles equal the oracle (which tests/test_oracle_vs_reference.py pins
+    against the reference's own ProcessingInfo with the same taps). Three ragged batches, so the ring phase is carried."""
+    n_links, n_units, step = 3, 40, 16
+    if fmt == "wib2":
+        units = S.gen_wib2_host(S.gen_params(52, 0.5), n_links, n_units)
+    else:
+        units = S.gen_wibeth_host(S.gen_params(52, 0.5), n_links, n_units)
+    cfg = B.make_config(fmt=fmt, algorithm=S.ALGORITHMS["FIR"], threshold=5, fir_taps=taps, tap_exponent=exponent)
+    oracles = [B.Oracle(cfg, link_id=l) for l in range(n_links)]
+    want, peds, wavs = [], [], []
+    for l in range(n_links):
+        t, p, w = oracles[l].process(units[l], dump=True, cap=1 << 21)
+        want.append(t), peds.append(p), wavs.append(w)
+    got, gp, gw = [], [], []
+    with S.TPGenerator(n_links, step, fmt=fmt, algorithm="FIR", threshold=5, fir_taps=taps, tap_exponent=exponent, tp_capacity=1 << 22) as g:
+        g.start()
+        for u in range(0, n_units, step):
+            t, p, w = g.process_host(np.ascontiguousarray(units[:, u:u + step]), debug=True, cap=1 << 22)
+            got.append(t), gp.append(p), gw.append(w)
+        assert (np.concatenate(gw, axis=1) == np.stack(wavs)).all(), "waveform dump"
+        assert (np.concatenate(gp, axis=1) == np.stack(peds)).all(), "pedestal dump"
+        assert_same_tps(np.concatenate(got), np.concatenate(want), f"{fmt} taps {taps}")
+        for l in range(n_links):
+            sg, so = g.dump_state(l), oracles[l].state()
+            for f in ["pedestal", "accum", "prev_was_over", "hit_charge", "hit_tover", "quantile25", "quantile75", "accum25", "accum75", "prev_samp"]:
+                assert (sg[f] == so[f]).all(), f"link {l} state field {f}"
+
+
 @pytest.mark.parametrize("algorithm,thr", [("SimpleThreshold", 30), ("SimpleThreshold", 2), ("SimpleThreshold", 40000), ("FIR", 5), ("FIR", 2),
                                            ("AbsRS", 60), ("AbsRS", 3), ("AbsRS", 700)])
 def test_wib2_against_oracle_with_state_and_dumps(algorithm, thr):

@@ -65,6 +65,24 @@ def test_wib2_matches_reference(seed, rate, algo, impl, flav, thr):
         assert (st["quantile25"] == sd[-1, 1]).all() and (st["quantile75"] == sd[-1, 2]).all()
 
 
+ANY_TAPS = [([2, 5, 11, 17, 9, 4, 1], 6), ([-3, 7, 20, 31, 20, 7, -3], 6), ([1, 3, 8, 10, 8, 3, 1], 5), ([300, -700, 1200, 2000, 1200, -700, 300], 6),
+            ([0, 0, 0, 64, 0, 0, 0], 6)]
+
+
+@pytest.mark.parametrize("taps,exponent", ANY_TAPS)
+@pytest.mark.parametrize("impl,flav", [(B.REF_WIB2_FIR_AVX2, 0)])
+def test_fir_arbitrary_taps_match_reference(taps, exponent, impl, flav):
+    """The reference's ProcessingInfo takes any taps / exponent (its frame processor only ever passes firwin_int(7, 0.1, 64) and
+    6): the oracle's multiply-add chain, its 16-bit wrapping (large taps) and the exponent-dependent clamps must follow it."""
+    sc = S.gen_wib2_host(S.gen_params(34, 0.5), 1, 200)[0]
+    o = B.Oracle(B.make_config(fmt="wib2", algorithm=3, threshold=5, fir_taps=taps, tap_exponent=exponent), flav)
+    r = B.ReferenceWib2(impl, 5, fir_taps=taps, tap_exponent=exponent)
+    tr, sd = r.process(sc, dump=True)
+    assert_same_tps(o.process(sc), tr, f"taps {taps} exponent {exponent}")
+    st = o.state()
+    assert (st["pedestal"] == sd[-1, 0]).all() and (st["quantile25"] == sd[-1, 1]).all() and (st["quantile75"] == sd[-1, 2]).all()
+
+
 def test_fir_threshold_64bit_lane_product():
     """`sigma * multiplier * threshold` is a 4 x int64 multiply; with a large threshold the product of one
     16-bit lane carries into its neighbour. The oracle must follow the AVX2 code there too."""

@@ -17,7 +17,9 @@ if fmt == "wib2":
 else:
     S.gen_wibeth_device(S.gen_params(2, 0.02), buf.data_ptr(), n_links, n_units)
 torch.cuda.synchronize()
-with S.TPGenerator(n_links, n_units, fmt=fmt, algorithm=algo, threshold=thr, tp_capacity=1 << 22) as g:
+import os
+taps = [int(t) for t in os.environ["SWTPG_TAPS"].split(",")] if os.environ.get("SWTPG_TAPS") else None  # FIR: other taps than firwin_int's
+with S.TPGenerator(n_links, n_units, fmt=fmt, algorithm=algo, threshold=thr, tp_capacity=1 << 22, fir_taps=taps) as g:
     g.start()
     ms = []
     for i in range(8):
