@@ -241,7 +241,10 @@ template<class Algo, bool DUMP>
 cudaError_t
 launch_wib2(const KernelParams& kp, cudaStream_t s)
 {
-  constexpr int kStages = 4;
+#ifndef SWTPG_WIB2_STAGES
+#define SWTPG_WIB2_STAGES 4
+#endif
+  constexpr int kStages = SWTPG_WIB2_STAGES;
   auto k = wib2_kernel<Algo, kStages, DUMP>;
   constexpr size_t smem = Wib2Smem<kStages>::total;
   static int resident[64];
