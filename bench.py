@@ -327,8 +327,9 @@ def main():
     if rank == 0 and not args.no_variants:
         others = {}
 
-        def timed(fmt, algorithm, thr, d_ptr, links, units, unit_bytes, samples_per_unit, state_bytes, tp_cap=1 << 22):
-            with S.TPGenerator(links, units, fmt=fmt, algorithm=algorithm, threshold=thr, device=local_rank, tp_capacity=tp_cap) as g:
+        def timed(fmt, algorithm, thr, d_ptr, links, units, unit_bytes, samples_per_unit, state_bytes, tp_cap=1 << 22, fir_taps=None):
+            with S.TPGenerator(links, units, fmt=fmt, algorithm=algorithm, threshold=thr, device=local_rank, tp_capacity=tp_cap,
+                               fir_taps=fir_taps) as g:
                 g.start()
                 for _ in range(3):
                     g.process_device(d_ptr, units)
@@ -346,6 +347,9 @@ def main():
 
         # BASELINE config[1]/[2] data already resident (SimpleThreshold workload): FIR + IQR matched filter, AbsRS, StandardRS
         others["wibeth_fir_iqr_thr5"] = timed("wibeth", "FIR", 5, d_frames.data_ptr(), n_links, frames, FRAME_BYTES, SAMPLES_PER_FRAME, 38)
+        # taps other than firwin_int(7, 0.1, 64): the packed multiply-add policy (here firwin_int's taps at multiplier 32, doubled)
+        others["wibeth_fir_iqr_other_taps"] = timed("wibeth", "FIR", 5, d_frames.data_ptr(), n_links, frames, FRAME_BYTES, SAMPLES_PER_FRAME, 38,
+                                                    fir_taps=[2, 6, 16, 20, 16, 6, 2])
         others["wibeth_abs_rs"] = timed("wibeth", "AbsRS", args.threshold, d_frames.data_ptr(), n_links, frames, FRAME_BYTES, SAMPLES_PER_FRAME, 22)
         others["wibeth_standard_rs"] = timed("wibeth", "StandardRS", args.threshold, d_frames.data_ptr(), n_links, frames, FRAME_BYTES,
                                              SAMPLES_PER_FRAME, 22)
