@@ -267,9 +267,7 @@ launch_wib2(const KernelParams& kp, cudaStream_t s)
       return e;
     resident[dev] = std::max(1, per_sm * sms);
   }
-  const unsigned max_ctas = unsigned(resident[dev]);
-  const unsigned rounds = (kp.n_links + max_ctas - 1) / max_ctas;
-  const unsigned grid = (kp.n_links + rounds - 1) / rounds; // every CTA walks `rounds` links (+-1)
+  const unsigned grid = std::min<unsigned>(kp.n_links, unsigned(resident[dev])); // persistent CTAs claim links dynamically
   k<<<grid, (kWib2Warps + 1) * 32, smem, s>>>(kp); // 4 consumer warps + the producer warp
   return cudaGetLastError();
 }

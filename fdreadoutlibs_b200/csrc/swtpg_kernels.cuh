@@ -1489,12 +1489,15 @@ wibeth_kernel(const KernelParams p)
 // (12 frames x 472 B) is one 5664-byte bulk copy into a CTA-wide ring; consumer warp w works on channels 64w..64w+63 (112
 // bytes of every frame's ADC block). full[s]: the copy engine's complete_tx; empty[s]: one arrival per consumer warp. The
 // producer warp (one lane; it sleeps on the empty barriers and issues no other instructions) walks the same link/unit
-// sequence and refills a stage as soon as all four consumers have released it — so no consumer ever waits for another
-// consumer, only for data (before: warp 0 refilled between its own superchunks and 13 % of all warp time was spent waiting
+// CTA's links — the first by block index, every further one claimed from the device-side cursor, published to the consumers
+// through a small FIFO — and refills a stage as soon as all four consumers have released it — so no consumer ever waits for
+// another consumer, only for data (before: warp 0 refilled between its own superchunks and 13 % of all warp time was spent waiting
 // on full barriers, profiles/r01_wib2_simple_ncu_full.txt).
 // =====================================================================================================================
 constexpr int kWib2FrameWords = SWTPG_WIB2_FRAME_BYTES / 4; // 118
 constexpr int kWib2Warps = 4;
+constexpr uint32_t kWib2Fifo = 8;           // links in flight: the producer is at most NSTAGE superchunks ahead (+ the end marker)
+constexpr uint32_t kNoMoreLinks = 0xFFFFFFFFu;
 
 template<int NSTAGE>
 struct Wib2Smem
@@ -1504,7 +1507,8 @@ struct Wib2Smem
   static constexpr size_t hits = align16(bars + size_t(NSTAGE) * 16);
   static constexpr size_t aux = hits + size_t(kWib2Warps) * HitStage::kCap * 16;
   static constexpr size_t counts = aux + size_t(kWib2Warps) * HitStage::kCap * 4;
-  static constexpr size_t total = align16(counts + size_t(kWib2Warps) * 4);
+  static constexpr size_t fifo = align16(counts + size_t(kWib2Warps) * 4);
+  static constexpr size_t total = fifo + kWib2Fifo * 4; // link FIFO, producer -> consumers
 };
 
 template<class Algo, int NSTAGE, bool DUMP>
@@ -1538,16 +1542,40 @@ wib2_kernel(const KernelParams p)
     *hits.cnt = 0u;
   __syncthreads(); // the only CTA-wide barrier: mbarriers visible before anyone waits on them
 
-  if (warp == kWib2Warps) { // producer warp: one lane feeds the ring for every link this CTA walks
+  volatile uint32_t* fifo = reinterpret_cast<volatile uint32_t*>(smem + L::fifo);
+  if (warp == kWib2Warps) { // producer warp: one lane feeds the ring and decides which links this CTA works on
     if (lane != 0)
       return;
-    uint32_t slot = 0, round = 0;
-    for (uint32_t link = blockIdx.x; link < p.n_links; link += gridDim.x) {
-      const uint32_t n_units = units_of(link);
+    static_assert(NSTAGE + 2 <= int(kWib2Fifo), "link FIFO too short for this ring depth");
+    uint32_t slot = 0, round = 0, pushed = 0;
+    auto wait_slot = [&]() { // all four consumers released the stage's previous contents
+      if (round != 0)
+        mbar_wait(&empty[slot], (round - 1u) & 1u);
+    };
+    uint32_t link = blockIdx.x; // the CTA's first link; every further one is claimed from the cursor (as in wibeth_kernel)
+    for (bool first = true;; first = false) {
+      uint32_t n_units = 0;
+      for (;;) {
+        if (!first)
+          link = gridDim.x + atomicAdd(p.link_cursor, 1u);
+        first = false;
+        if (link >= p.n_links)
+          break;
+        n_units = units_of(link);
+        if (n_units != 0)
+          break;
+      }
+      if (link >= p.n_links) { // end marker: a stage that completes without data
+        wait_slot();
+        fifo[pushed & (kWib2Fifo - 1u)] = kNoMoreLinks;
+        mbar_arrive(&full[slot]);
+        break;
+      }
       const uint8_t* src = base_of(link);
       for (uint32_t unit = 0; unit < n_units; ++unit, src += kUnit) {
-        if (round != 0)
-          mbar_wait(&empty[slot], (round - 1u) & 1u); // all four consumers released the stage's previous contents
+        wait_slot();
+        if (unit == 0) // published before the arrive below releases it to the consumers
+          fifo[pushed++ & (kWib2Fifo - 1u)] = link;
         mbar_arrive_expect_tx(&full[slot], kUnit);
         bulk_g2s(stages + slot * kUnit, src, kUnit, &full[slot]);
         if (++slot == NSTAGE) {
@@ -1555,6 +1583,12 @@ wib2_kernel(const KernelParams p)
           ++round;
         }
       }
+    }
+    // last CTA out re-arms the cursor for the next launch
+    __threadfence();
+    if (atomicAdd(p.link_cursor + 1, 1u) == gridDim.x - 1u) {
+      p.link_cursor[0] = 0u;
+      p.link_cursor[1] = 0u;
     }
     return;
   }
@@ -1570,10 +1604,12 @@ wib2_kernel(const KernelParams p)
   const uint32_t row0 = p.wib2_adc_offset / 4 + warp * 28; // word offset of this warp's 112 bytes inside a frame
 
   uint32_t stg = 0, phase = 0;       // consumer ring position / full-barrier phase
-  for (uint32_t link = blockIdx.x; link < p.n_links; link += gridDim.x) {
+  for (uint32_t popped = 0;; ++popped) {
+    mbar_wait(&full[stg], phase);    // first superchunk of the next link, or the end marker
+    const uint32_t link = fifo[popped & (kWib2Fifo - 1u)];
+    if (link == kNoMoreLinks)
+      break;
     const uint32_t n_units = units_of(link);
-    if (n_units == 0)
-      continue;
     const uint8_t* link_base = base_of(link);
     const uint32_t group = link * kWib2Warps + warp;
     uint32_t* st = p.state + size_t(group) * kStateWordsPerGroup;
@@ -1586,7 +1622,8 @@ wib2_kernel(const KernelParams p)
     for (uint32_t unit = 0; unit < n_units; ++unit) {
       ctx.tick_base = unit * 12u;
       ctx.unit = unit;
-      mbar_wait(&full[stg], phase);
+      if (unit != 0)
+        mbar_wait(&full[stg], phase);
       const uint32_t* sc = reinterpret_cast<const uint32_t*>(stages + stg * kUnit);
       if constexpr (!std::is_same<Algo, PackedSimpleWib2>::value)
         ctx.ts = uint64_t(sc[1]) | (uint64_t(sc[2]) << 32); // WIB2Frame::get_timestamp, first frame (:350-351)
