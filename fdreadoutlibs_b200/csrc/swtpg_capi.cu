@@ -194,44 +194,59 @@ launch_wibeth_geo(const KernelParams& kp, cudaStream_t s)
   return cudaGetLastError();
 }
 
-// SWTPG_GEO=<n> selects an alternative geometry for the packed fast path (tuning aid; default 0).
-int
-geo_choice()
+// CTA form of the WIBEth kernel (wibeth_quad_kernel): 4 consumer warps + 1 producer warp per quad of links.
+template<class Algo, bool DUMP>
+cudaError_t
+launch_wibeth_quad(const KernelParams& kp, cudaStream_t s)
 {
-  static int g = [] {
-    const char* e = getenv("SWTPG_GEO");
-    return e ? atoi(e) : 0;
-  }();
-  return g;
+  constexpr int kStages = 2, kChunk = 32;
+  auto k = wibeth_quad_kernel<Algo, kStages, kChunk, DUMP>;
+  constexpr size_t smem = WibEthQuadSmem<kStages, kChunk>::total;
+  static int resident[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess)
+    return e;
+  if (dev < 0 || dev >= 64)
+    return cudaErrorInvalidDevice;
+  if (resident[dev] == 0) {
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess)
+      return e;
+    int per_sm = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, (kQuad + 1) * 32, smem);
+    if (e != cudaSuccess)
+      return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess)
+      return e;
+    if (const char* cap = getenv("SWTPG_CTAS_PER_SM")) // tuning aid
+      per_sm = std::min(per_sm, std::max(1, atoi(cap)));
+    else if (Algo::kQuadCtasPerSm > 0) // the policy's measured optimum, if the device holds that many
+      per_sm = std::min(per_sm, Algo::kQuadCtasPerSm);
+    resident[dev] = std::max(1, per_sm * sms);
+  }
+  const unsigned quads = (kp.n_links + kQuad - 1) / kQuad;
+  const unsigned grid = std::min<unsigned>(quads, unsigned(resident[dev])); // persistent CTAs claim quads dynamically
+  k<<<grid, (kQuad + 1) * 32, smem, s>>>(kp);
+  return cudaGetLastError();
 }
 
+// Which form of the WIBEth kernel a policy runs is a measured choice (profiles/r01_quad_vs_warp.txt): the CTA form is 14 % faster
+// for FIR + IQR (ptxas needs 64 registers instead of 109 for it, so 20 consumer warps fit an SM), the one-warp-per-CTA form
+// 2-5 % faster for SimpleThreshold and the running sums (the quad's lock-step costs more than the producer bookkeeping it
+// saves). SWTPG_WIBETH_KERNEL=warp forces the latter.
 template<class Algo, bool DUMP>
 cudaError_t
 launch_wibeth(const KernelParams& kp, cudaStream_t s)
 {
-  if constexpr (std::is_same<Algo, PackedSimpleWibEth>::value && !DUMP) {
-    switch (geo_choice()) {
-      case 1: return launch_wibeth_geo<Algo, DUMP, Geo<4, 3, 32>>(kp, s);
-      case 2: return launch_wibeth_geo<Algo, DUMP, Geo<4, 2, 32>>(kp, s);
-      case 3: return launch_wibeth_geo<Algo, DUMP, Geo<8, 3, 16>>(kp, s);
-      case 4: return launch_wibeth_geo<Algo, DUMP, Geo<4, 4, 16>>(kp, s);
-      case 5: return launch_wibeth_geo<Algo, DUMP, Geo<2, 3, 16>>(kp, s);
-      case 6: return launch_wibeth_geo<Algo, DUMP, Geo<4, 4, 8>>(kp, s);
-      case 7: return launch_wibeth_geo<Algo, DUMP, Geo<4, 3, 16, 10>>(kp, s);
-      case 8: return launch_wibeth_geo<Algo, DUMP, Geo<8, 3, 16, 5>>(kp, s);
-      case 9: return launch_wibeth_geo<Algo, DUMP, Geo<4, 2, 16, 10>>(kp, s);
-      case 10: return launch_wibeth_geo<Algo, DUMP, Geo<4, 2, 32, 5>>(kp, s);
-      case 11: return launch_wibeth_geo<Algo, DUMP, Geo<2, 2, 32, 20>>(kp, s);
-      case 12: return launch_wibeth_geo<Algo, DUMP, Geo<4, 4, 16, 10>>(kp, s);
-      case 13: return launch_wibeth_geo<Algo, DUMP, Geo<4, 2, 32>>(kp, s);
-      case 14: return launch_wibeth_geo<Algo, DUMP, Geo<2, 2, 32>>(kp, s);
-      case 15: return launch_wibeth_geo<Algo, DUMP, Geo<1, 3, 16>>(kp, s);
-      case 16: return launch_wibeth_geo<Algo, DUMP, Geo<1, 3, 32>>(kp, s);
-      case 17: return launch_wibeth_geo<Algo, DUMP, Geo<1, 4, 32>>(kp, s);
-      case 18: return launch_wibeth_geo<Algo, DUMP, Geo<1, 4, 16>>(kp, s);
-      case 19: return launch_wibeth_geo<Algo, DUMP, Geo<1, 8, 8>>(kp, s);
-      default: break;
-    }
+  if constexpr (Algo::kQuadCtasPerSm > 0) {
+    static const bool warp_form = [] {
+      const char* e = getenv("SWTPG_WIBETH_KERNEL");
+      return e && std::string(e) == "warp";
+    }();
+    if (!warp_form)
+      return launch_wibeth_quad<Algo, DUMP>(kp, s);
   }
   return launch_wibeth_geo<Algo, DUMP, GeoDefault>(kp, s);
 }

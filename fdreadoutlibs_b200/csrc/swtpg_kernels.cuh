@@ -169,6 +169,7 @@ struct ScalarAlgo
 {
   static constexpr int kGroupUnroll = 1;
   static constexpr int kWarpsPerSm = 0; // persistent single-warp CTAs per SM the WIBEth launch aims for; 0 = as many as fit
+  static constexpr int kQuadCtasPerSm = 0; // WIBEth: > 0 = run wibeth_quad_kernel (CTA of 4 links + producer warp) with that many CTAs per SM
   ChanRegs c[2];
   uint32_t kphase; // FIR ring phase
 
@@ -410,6 +411,7 @@ struct PackedSimpleWibEth
 {
   static constexpr int kGroupUnroll = SWTPG_GROUP_UNROLL;
   static constexpr int kWarpsPerSm = 20; // measured best on B200 (profiles/r01_warps_sweep.txt): 5 warps per sub-partition
+  static constexpr int kQuadCtasPerSm = 0;
   uint32_t Mq, A, prev, C, Tn, PK1, PTn;
   uint32_t cUp, cDn, thr1;
 
@@ -801,6 +803,8 @@ struct PackedFirIqr
 {
   static constexpr int kGroupUnroll = SWTPG_FIR_GROUP_UNROLL;
   static constexpr int kWarpsPerSm = 12; // 3 warps per sub-partition: 3 % faster than the 16 its 128 registers allow (same sweep)
+  static constexpr int kQuadCtasPerSm = 5; // CTA form, 20 consumer warps per SM: 14 % faster than one warp per CTA for this policy
+                                           // (64 registers instead of 109; profiles/r01_quad_vs_warp.txt)
   uint32_t Mq, A, Q25q, A25, Q75p, A75; // 1 - median, (acc - 1); 1 - q25, acc25; q75 + 2, acc75   (accumulators: fp16 subnormals)
   uint32_t d1, d2, d3, d4, d5, d6, o1, o2; // cascade: d_j = previous input of stage j, o1/o2 = previous two outputs
   uint32_t prev, C, Tn;
@@ -1046,6 +1050,7 @@ struct PackedFirIqr
 // =====================================================================================================================
 struct PackedFirIqrAnyTaps : PackedFirIqr
 {
+  static constexpr int kQuadCtasPerSm = 4; // CTA form, 16 consumer warps per SM: 6 % faster than one warp per CTA
   uint32_t w[8], ws[8]; // window and its half-swapped twin
   int tap[7];
 
@@ -1480,6 +1485,225 @@ wibeth_kernel(const KernelParams p)
     if (atomicAdd(p.link_cursor + 1, 1u) == active - 1u) {
       p.link_cursor[0] = 0u;
       p.link_cursor[1] = 0u;
+    }
+  }
+}
+
+// =====================================================================================================================
+// WIBEth kernel, CTA form: 4 consumer warps + 1 producer warp work on a QUAD of 4 links in lock-step (the structure of the
+// WIB2 kernel below, where one link is four warps wide). A stage of the CTA-wide ring holds one CHUNK_TICKS-tick chunk of
+// each of the four links (four bulk copies signalled on ONE `full` barrier, released through ONE `empty` barrier with an
+// arrival per consumer), so a consumer's per-chunk bookkeeping is a barrier wait and an arrive — the ring cursor, the
+// source addresses and the link hand-out (first quad by block index, every further one claimed from the device-side cursor
+// four links at a time, published through a small FIFO) live in the producer warp, once per quad instead of once per link.
+// Ragged batches: a quad runs for the longest of its links; a consumer whose link is shorter (or absent) only keeps step.
+// =====================================================================================================================
+constexpr int kQuad = 4;
+constexpr uint32_t kQuadFifo = 4; // quads in flight: the producer is at most NSTAGE chunks ahead, a quad has >= kChunksPerUnit chunks
+
+template<int NSTAGE, int CHUNK_TICKS>
+struct WibEthQuadSmem
+{
+  static constexpr size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+  static constexpr size_t chunk = size_t(kWibEthRowBytes) * CHUNK_TICKS;
+  static constexpr size_t bars = align16(size_t(NSTAGE) * kQuad * chunk);
+  static constexpr size_t hits = align16(bars + size_t(NSTAGE) * 16);
+  static constexpr size_t aux = hits + size_t(kQuad) * HitStage::kCap * 16;
+  static constexpr size_t counts = aux + size_t(kQuad) * HitStage::kCap * 4;
+  static constexpr size_t fifo = align16(counts + size_t(kQuad) * 4);
+  static constexpr size_t total = fifo + kQuadFifo * 32; // per quad: 4 link ids, its length in units, padding
+};
+
+template<class Algo, int NSTAGE, int CHUNK_TICKS, bool DUMP>
+__global__ void __launch_bounds__((kQuad + 1) * 32)
+wibeth_quad_kernel(const KernelParams p)
+{
+  static_assert(64 % CHUNK_TICKS == 0, "chunk must divide the frame");
+  constexpr uint32_t kChunkBytes = kWibEthRowBytes * CHUNK_TICKS;
+  constexpr uint32_t kChunksPerUnit = 64 / CHUNK_TICKS;
+  static_assert((NSTAGE + kChunksPerUnit - 1) / kChunksPerUnit + 2 <= kQuadFifo, "quad FIFO too short for this ring geometry");
+  extern __shared__ __align__(128) uint8_t smem[];
+  using L = WibEthQuadSmem<NSTAGE, CHUNK_TICKS>;
+  const uint32_t warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31u;
+  uint8_t* stages = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::bars);
+  uint64_t* empty = full + NSTAGE;
+  volatile uint32_t* fifo = reinterpret_cast<volatile uint32_t*>(smem + L::fifo); // [kQuadFifo][8]: links[4], units of the longest
+  HitStage hits;
+  hits.buf = reinterpret_cast<uint4*>(smem + L::hits) + size_t(warp) * HitStage::kCap;
+  hits.aux = reinterpret_cast<uint32_t*>(smem + L::aux) + size_t(warp) * HitStage::kCap;
+  hits.cnt = reinterpret_cast<uint32_t*>(smem + L::counts) + warp;
+
+  auto units_of = [&](uint32_t link) -> uint32_t { return p.n_units ? p.n_units[link] : p.units_stride; };
+  auto base_of = [&](uint32_t link) -> const uint8_t* { return p.frames + size_t(link) * p.units_stride * SWTPG_WIBETH_FRAME_BYTES; };
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kQuad);
+    }
+    fence_mbar_init();
+  }
+  if (lane == 0 && warp < kQuad)
+    *hits.cnt = 0u;
+  __syncthreads(); // the only CTA-wide barrier: mbarriers visible before anyone waits on them
+
+  if (warp == kQuad) { // ---- producer warp (one lane) ----
+    if (lane != 0)
+      return;
+    uint32_t slot = 0, round = 0, pushed = 0;
+    auto wait_slot = [&]() { // all four consumers released the stage's previous contents
+      if (round != 0)
+        mbar_wait(&empty[slot], (round - 1u) & 1u);
+    };
+    uint32_t first_link = blockIdx.x * kQuad; // the CTA's first quad; every further one is claimed from the cursor
+    for (bool first = true;;) {
+      uint32_t nu[kQuad], longest = 0;
+      for (;;) { // next quad that has data
+        if (!first)
+          first_link = gridDim.x * kQuad + atomicAdd(p.link_cursor, uint32_t(kQuad));
+        first = false;
+        longest = 0;
+        if (first_link >= p.n_links)
+          break;
+#pragma unroll
+        for (int c = 0; c < kQuad; ++c) {
+          nu[c] = first_link + c < p.n_links ? units_of(first_link + c) : 0u;
+          longest = max(longest, nu[c]);
+        }
+        if (longest != 0)
+          break;
+      }
+      volatile uint32_t* entry = fifo + (pushed & (kQuadFifo - 1u)) * 8u;
+      if (first_link >= p.n_links) { // end marker: a stage that completes without data
+        wait_slot();
+        entry[4] = 0u;
+        entry[5] = 1u;
+        mbar_arrive(&full[slot]);
+        break;
+      }
+      const uint8_t* src0 = base_of(first_link) + 32;                             // link c of the quad: + c * link_stride
+      const size_t link_stride = size_t(p.units_stride) * SWTPG_WIBETH_FRAME_BYTES;
+      for (uint32_t unit = 0; unit < longest; ++unit) {
+        for (uint32_t ch = 0; ch < kChunksPerUnit; ++ch) {
+          wait_slot();
+          if (unit == 0 && ch == 0) { // published before the arrive below releases it to the consumers
+            entry[0] = first_link;
+            entry[4] = longest;
+            entry[5] = 0u;
+            ++pushed;
+          }
+          uint32_t bytes = 0;
+#pragma unroll
+          for (int c = 0; c < kQuad; ++c)
+            bytes += unit < nu[c] ? kChunkBytes : 0u;
+          mbar_arrive_expect_tx(&full[slot], bytes);
+          const uint8_t* src = src0 + size_t(unit) * SWTPG_WIBETH_FRAME_BYTES + ch * kChunkBytes;
+#pragma unroll
+          for (int c = 0; c < kQuad; ++c)
+            if (unit < nu[c])
+              bulk_g2s(stages + (slot * kQuad + c) * kChunkBytes, src + c * link_stride, kChunkBytes, &full[slot]);
+          if (++slot == NSTAGE) {
+            slot = 0;
+            ++round;
+          }
+        }
+      }
+    }
+    __threadfence(); // last CTA out re-arms the cursor for the next launch
+    if (atomicAdd(p.link_cursor + 1, 1u) == gridDim.x - 1u) {
+      p.link_cursor[0] = 0u;
+      p.link_cursor[1] = 0u;
+    }
+    return;
+  }
+
+  // ---- consumer warps: warp c works on link c of every quad ----
+  Algo algo;
+  algo.configure(p);
+  const PairPos pp = pair_pos(lane);
+  TickCtx ctx;
+  ctx.p = &p;
+  ctx.chan0 = 2 * lane;
+  ctx.ts = 0;
+  ctx.stage = &hits;
+
+  uint32_t stg = 0, phase = 0; // consumer position in the ring and the full barrier's phase
+  for (uint32_t popped = 0;; ++popped) {
+    mbar_wait(&full[stg], phase); // first chunk of the next quad, or the end marker
+    const volatile uint32_t* entry = fifo + (popped & (kQuadFifo - 1u)) * 8u;
+    if (entry[5] != 0u)
+      break;
+    const uint32_t link = entry[0] + warp, longest = entry[4];
+    const uint32_t n_units = link < p.n_links ? units_of(link) : 0u;
+    const uint8_t* link_base = base_of(link < p.n_links ? link : 0u);
+    uint32_t* st = p.state + size_t(link) * kStateWordsPerGroup;
+    uint32_t flags = 0;
+    bool need_seed = false;
+    if (n_units != 0) {
+      flags = p.group_flags[link];
+      algo.load(st, lane, flags);
+      need_seed = !(flags & kFlagInitialized);
+    }
+    ctx.link = link;
+    ctx.link_base = link_base;
+
+    for (uint32_t unit = 0; unit < longest; ++unit) {
+      const bool mine = unit < n_units;
+      ctx.tick_base = unit * 64u;
+      ctx.unit = unit;
+      if constexpr (!std::is_same<Algo, PackedSimpleWibEth>::value) {
+        if (mine) // DAQEthHeader word 1 = timestamp (docs/README.md:81); the packed path reads it when it flushes hits
+          ctx.ts = *reinterpret_cast<const unsigned long long*>(link_base + size_t(unit) * SWTPG_WIBETH_FRAME_BYTES + 8);
+      }
+#pragma unroll 1
+      for (int t0 = 0; t0 < 64; t0 += CHUNK_TICKS) {
+        if (unit != 0 || t0 != 0)
+          mbar_wait(&full[stg], phase);
+        if (mine) {
+          const uint32_t* rows = reinterpret_cast<const uint32_t*>(stages + (stg * kQuad + warp) * kChunkBytes);
+          if (need_seed) {
+            algo.seed(extract_pair(rows, pp));
+            need_seed = false;
+          }
+          constexpr int G = 4;
+          static_assert(CHUNK_TICKS % G == 0, "group must divide the chunk");
+          constexpr int kGroupUnroll = Algo::kGroupUnroll;
+#pragma unroll kGroupUnroll
+          for (int tt = 0; tt < CHUNK_TICKS; tt += G) {
+            uint32_t ped[G], wav[G];
+            algo.template group<G, DUMP>(rows + tt * (kWibEthRowBytes / 4), pp, ctx, t0 + tt, ped, wav);
+            if constexpr (DUMP) {
+#pragma unroll
+              for (int g = 0; g < G; ++g) {
+                const size_t o = ((size_t(link) * p.units_stride + unit) * 64 + size_t(t0 + tt + g)) * 32 + lane; // u32 = 2 channels
+                if (p.pedestal_out)
+                  reinterpret_cast<uint32_t*>(p.pedestal_out)[o] = ped[g];
+                if (p.waveform_out)
+                  reinterpret_cast<uint32_t*>(p.waveform_out)[o] = wav[g];
+              }
+            }
+          }
+        }
+        // Every lane's loads from this stage have completed (their values were consumed above), so after the warp barrier
+        // the stage can be handed back to the copy engine: a read-then-async-write hand-off needs no proxy fence.
+        __syncwarp();
+        if (lane == 0)
+          mbar_arrive(&empty[stg]);
+        if (++stg == NSTAGE) {
+          stg = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+
+    if (n_units != 0) {
+      Algo::template flush<false>(hits, p.sink, link_base, link, lane); // records carry unit indices of THIS link
+      const uint32_t k_end = algo.phase_after(n_units * 64u);
+      algo.store(st, lane, k_end);
+      if (lane == 0)
+        p.group_flags[link] = kFlagInitialized | (k_end << 8);
     }
   }
 }
