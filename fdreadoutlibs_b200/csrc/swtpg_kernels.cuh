@@ -1735,8 +1735,11 @@ struct Wib2Smem
   static constexpr size_t total = fifo + kWib2Fifo * 4; // link FIFO, producer -> consumers
 };
 
+#ifndef SWTPG_WIB2_MIN_CTAS
+#define SWTPG_WIB2_MIN_CTAS 1
+#endif
 template<class Algo, int NSTAGE, bool DUMP>
-__global__ void __launch_bounds__((kWib2Warps + 1) * 32)
+__global__ void __launch_bounds__((kWib2Warps + 1) * 32, SWTPG_WIB2_MIN_CTAS)
 wib2_kernel(const KernelParams p)
 {
   constexpr uint32_t kUnit = SWTPG_WIB2_SUPERCHUNK_BYTES;
