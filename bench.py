@@ -399,17 +399,18 @@ def main():
                     "host_gbs": p_passes * p_links * p_units * FRAME_BYTES / dt / 1e9, "host_cpu_seconds": cpu_s, "wall_seconds": dt,
                     "real_time_apas": p_passes * p_links * p_units * SAMPLES_PER_FRAME / dt / APA_SAMPLES_PER_S}
 
-        copied = run_plugin(False)
-        plugin = run_plugin(True)
+        plugin = run_plugin(False)
+        registered = run_plugin(True)
         plugin.update({"threads": p_links, "links": p_links, "frames_per_link": p_units * p_passes, "superchunk_frames": p_sc,
                        "note": "WIBEthFrameProcessor::find_hits per frame from one thread per link (C++ host shim), TriggerPrimitives out; "
-                               "frames lie in a latency buffer registered with swtpg_register_buffer, so find_hits hands over pointers and "
-                               "the copy engine reads the frames where they lie. Neither wall time nor host CPU time differs measurably "
-                               "from copy_on_submit on this box: with this few links the path is bounded by the per-link serial speed of "
-                               "the kernel (one warp per link, ~2.1 GB/s = 9x real time per link, batches of one handle run in order) "
-                               "and by 2 threads per host core, not by the 7200-byte copy (profiles/r01_plugin_probe.txt)",
-                       "copy_on_submit": dict(copied, note="same run without registration: every frame is copied into the pinned staging "
-                                                           "ring by its link's thread")})
+                               "every frame is copied into the pinned staging ring by its link's thread (the ABI's default). With this few "
+                               "links the path is bounded by the per-link serial speed of the kernel (one warp per link, ~2.1 GB/s = 9x "
+                               "real time per link; batches of one handle run in order) and by 2 threads per host core, not by the copy, "
+                               "the host link or the GPU (profiles/r01_plugin_probe.txt)",
+                       "zero_copy_registered": dict(registered, note="same run with the payload array registered as the latency buffer "
+                                                    "(swtpg_register_buffer): find_hits hands over pointers and the copy engine reads the "
+                                                    "frames where they lie, one async copy per link and superchunk. Not faster on this box "
+                                                    "(32 copies per batch instead of one); it takes the per-frame memcpy off the host cores")})
         del h_units
 
     cpu = None

@@ -11,8 +11,8 @@ cap() { # name, kernel regex, perf_probe args
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$2 -s 3 -c 1 -f -o $O/${TAG}_$1_full python tools/perf_probe.py $3 > $O/ncu_$1.log 2>&1
   tail -1 $O/ncu_$1.log
 }
-cap wibeth_simple wibeth_kernel "5920 64"
-cap wibeth_fir wibeth_kernel "5920 64 FIR 5"
-cap wibeth_absrs wibeth_kernel "5920 64 AbsRS 60"
+cap wibeth_simple wibeth_ "5920 64"
+cap wibeth_fir wibeth_ "5920 64 FIR 5"
+cap wibeth_absrs wibeth_ "5920 64 AbsRS 60"
 cap wib2_simple wib2_kernel "1480 340 SimpleThreshold 60 wib2"
 ls -la $O/${TAG}_*_full.ncu-rep $O/${TAG}_launches.csv
