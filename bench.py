@@ -265,10 +265,13 @@ def main():
 
     # --- end to end through the public API: pinned host frames in, TP list out (pinned), copies inside the timed region ---
     e2e_links = n_links
-    h_frames = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    # SWTPG_BENCH_WC=1: write-combined pinned pages (swtpg_alloc_pinned) — measured: no difference, not even with 8 GPUs ingesting at once
+    wc = os.environ.get("SWTPG_BENCH_WC", "0") != "0"
+    h_buf = S.PinnedBuffer(nbytes, write_combined=wc)
+    h_frames = torch.from_numpy(h_buf.array)
     h_frames.copy_(d_frames)
     torch.cuda.synchronize()
-    h_np = h_frames.numpy().reshape(e2e_links, frames, FRAME_BYTES)
+    h_np = h_buf.array.reshape(e2e_links, frames, FRAME_BYTES)
     tp_cap = 1 << 22
     h_tps = torch.empty(tp_cap * TP_BYTES, dtype=torch.uint8, pin_memory=True).numpy().view(S.frames.TP_DTYPE)
     # the host link's own ceiling, measured here: the same pinned buffer copied H2D with nothing else going on

@@ -219,6 +219,25 @@ class TPGenerator:
         return {n: int(getattr(c, n)) for n, _ in SwtpgCounters._fields_}
 
 
+class PinnedBuffer:
+    """Page-locked host memory from swtpg_alloc_pinned, viewed as a uint8 numpy array (`.array`). write_combined=True: the CPU
+    should only write it (frames in); reads are very slow. Freed on close() / garbage collection."""
+
+    def __init__(self, nbytes: int, write_combined: bool = False):
+        self.ptr = lib.swtpg_alloc_pinned(nbytes, 1 if write_combined else 0)
+        if not self.ptr:
+            raise MemoryError(f"swtpg_alloc_pinned({nbytes}) failed")
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            lib.swtpg_free_pinned(self.ptr)
+            self.ptr = None
+
+    __del__ = close
+
+
 def sort_tps(tps: np.ndarray) -> np.ndarray:
     """(time_start, link, channel) order via the library's host sort (swtpg_sort_tps)."""
     tps = np.ascontiguousarray(tps, dtype=F.TP_DTYPE).copy()

@@ -1240,6 +1240,25 @@ swtpg_get_counters(swtpg_handle* h, swtpg_counters* out)
   return SWTPG_OK;
 }
 
+void*
+swtpg_alloc_pinned(size_t bytes, int write_combined)
+{
+  void* p = nullptr;
+  const unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+  if (bytes == 0 || cudaHostAlloc(&p, bytes, flags) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void
+swtpg_free_pinned(void* p)
+{
+  if (p && cudaFreeHost(p) != cudaSuccess)
+    cudaGetLastError();
+}
+
 static inline bool
 tp_less(const swtpg_tp& a, const swtpg_tp& b)
 {

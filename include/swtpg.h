@@ -212,6 +212,13 @@ swtpg_status swtpg_sync(swtpg_handle* h);
 swtpg_status swtpg_dump_state(swtpg_handle* h, uint32_t link, swtpg_channel_state* out);
 swtpg_status swtpg_get_counters(swtpg_handle* h, swtpg_counters* out);
 
+/* Page-locked host memory for frame buffers handed to swtpg_process_host (or used as a latency buffer without a later
+ * swtpg_register_buffer). write_combined != 0 asks for write-combined pages: the CPU only ever WRITES frames there (reads are
+ * very slow) and the device's reads do not snoop the CPU caches, which matters when several GPUs of one host ingest at once.
+ * Returns NULL on failure. */
+void* swtpg_alloc_pinned(size_t bytes, int write_combined);
+void swtpg_free_pinned(void* p);
+
 /* Host-side ordering of a TP list by (time_start, link, channel): the order TriggerPrimitiveTypeAdapter::operator<
  * imposes downstream (include/fdreadoutlibs/TriggerPrimitiveTypeAdapter.hpp:26-29). In place. */
 void swtpg_sort_tps(swtpg_tp* tps, size_t n);
