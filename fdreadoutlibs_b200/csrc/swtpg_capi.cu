@@ -199,7 +199,11 @@ template<class Algo, bool DUMP>
 cudaError_t
 launch_wibeth_quad(const KernelParams& kp, cudaStream_t s)
 {
-  constexpr int kStages = 2, kChunk = 32;
+#ifndef SWTPG_QUAD_STAGES
+#define SWTPG_QUAD_STAGES 2
+#define SWTPG_QUAD_CHUNK 32
+#endif
+  constexpr int kStages = SWTPG_QUAD_STAGES, kChunk = SWTPG_QUAD_CHUNK;
   auto k = wibeth_quad_kernel<Algo, kStages, kChunk, DUMP>;
   constexpr size_t smem = WibEthQuadSmem<kStages, kChunk>::total;
   static int resident[64];

@@ -22,6 +22,9 @@
 #ifndef SWTPG_FIR_GROUP_UNROLL
 #define SWTPG_FIR_GROUP_UNROLL 2
 #endif
+#ifndef SWTPG_QUAD_SIMPLE
+#define SWTPG_QUAD_SIMPLE 0
+#endif
 #ifndef SWTPG_ELECT
 #define SWTPG_ELECT 1
 #endif
@@ -411,7 +414,7 @@ struct PackedSimpleWibEth
 {
   static constexpr int kGroupUnroll = SWTPG_GROUP_UNROLL;
   static constexpr int kWarpsPerSm = 20; // measured best on B200 (profiles/r01_warps_sweep.txt): 5 warps per sub-partition
-  static constexpr int kQuadCtasPerSm = 0;
+  static constexpr int kQuadCtasPerSm = SWTPG_QUAD_SIMPLE; // 0: one warp per CTA (measured faster for this policy)
   uint32_t Mq, A, prev, C, Tn, PK1, PTn;
   uint32_t cUp, cDn, thr1;
 
