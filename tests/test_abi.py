@@ -110,3 +110,34 @@ def test_sort_and_merge():
 
 def test_firwin_int_host():
     assert list(S.firwin_int(7, 0.1, 64)) == [1, 6, 15, 20, 15, 6, 1]
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/swtpg.h is the boundary a C / cgo / JNI / ctypes binding sees: it must compile as C11 and as C++17 without any
+    CUDA or C++ header, and a C program must link against the shared library and reach the host-only entry points."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi_probe.c"
+    src.write_text(
+        '#include "swtpg.h"\n#include "swtpg_framegen.h"\n#include <stdio.h>\n'
+        "int main(void) {\n"
+        "  int16_t taps[8] = {0};\n"
+        "  swtpg_config cfg = {0};\n"
+        "  cfg.struct_size = sizeof cfg;\n"
+        "  if (swtpg_abi_version() != SWTPG_ABI_VERSION) return 1;\n"
+        "  if (swtpg_firwin_int(7, 0.1, 64, taps) != 7 || taps[3] != 20) return 2;\n"
+        "  if (sizeof(swtpg_tp) != 32 || sizeof cfg != 68) return 3;\n"
+        '  printf("%s\\n", swtpg_status_string(SWTPG_ERR_BUSY));\n'
+        "  return 0;\n}\n")
+    lib_dir = os.path.join(root, "fdreadoutlibs_b200")
+    exe = tmp_path / "abi_probe"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                    "-L", lib_dir, "-lswtpg_b200", f"-Wl,-rpath,{lib_dir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.strip() != ""
+    cpp = tmp_path / "abi_probe.cpp"
+    cpp.write_text('#include "swtpg.h"\n#include "swtpg_framegen.h"\nint f() { return int(swtpg_abi_version()); }\n')
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-c", "-I", os.path.join(root, "include"), str(cpp), "-o", str(tmp_path / "abi_probe.o")],
+                   check=True)
