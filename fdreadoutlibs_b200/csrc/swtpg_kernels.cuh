@@ -173,6 +173,7 @@ struct ScalarAlgo
   static constexpr int kGroupUnroll = 1;
   static constexpr int kWarpsPerSm = 0; // persistent single-warp CTAs per SM the WIBEth launch aims for; 0 = as many as fit
   static constexpr int kQuadCtasPerSm = 0; // WIBEth: > 0 = run wibeth_quad_kernel (CTA of 4 links + producer warp) with that many CTAs per SM
+  static constexpr int kWib2MinCtas = 1;   // WIB2: minimum CTAs per SM the register allocation must allow
   ChanRegs c[2];
   uint32_t kphase; // FIR ring phase
 
@@ -415,6 +416,7 @@ struct PackedSimpleWibEth
   static constexpr int kGroupUnroll = SWTPG_GROUP_UNROLL;
   static constexpr int kWarpsPerSm = 20; // measured best on B200 (profiles/r01_warps_sweep.txt): 5 warps per sub-partition
   static constexpr int kQuadCtasPerSm = SWTPG_QUAD_SIMPLE; // 0: one warp per CTA (measured faster for this policy)
+  static constexpr int kWib2MinCtas = 5;
   uint32_t Mq, A, prev, C, Tn, PK1, PTn;
   uint32_t cUp, cDn, thr1;
 
@@ -806,6 +808,7 @@ struct PackedFirIqr
 {
   static constexpr int kGroupUnroll = SWTPG_FIR_GROUP_UNROLL;
   static constexpr int kWarpsPerSm = 12; // 3 warps per sub-partition: 3 % faster than the 16 its 128 registers allow (same sweep)
+  static constexpr int kWib2MinCtas = 5;
   static constexpr int kQuadCtasPerSm = 5; // CTA form, 20 consumer warps per SM: 14 % faster than one warp per CTA for this policy
                                            // (64 registers instead of 109; profiles/r01_quad_vs_warp.txt)
   uint32_t Mq, A, Q25q, A25, Q75p, A75; // 1 - median, (acc - 1); 1 - q25, acc25; q75 + 2, acc75   (accumulators: fp16 subnormals)
@@ -1153,6 +1156,7 @@ struct PackedFirIqrAnyTaps : PackedFirIqr
 struct PackedRsIqrWib2 : PackedFirIqr
 {
   static constexpr int kGroupUnroll = 1;
+  static constexpr int kWib2MinCtas = 1;
   uint32_t RS1, MRq, AR; // RS + 1 (after median subtraction); 1 - median_RS; (acc_RS - 1) as fp16 subnormal
 
   __device__ __forceinline__ void configure(const KernelParams& p)
@@ -1738,11 +1742,10 @@ struct Wib2Smem
   static constexpr size_t total = fifo + kWib2Fifo * 4; // link FIFO, producer -> consumers
 };
 
-#ifndef SWTPG_WIB2_MIN_CTAS
-#define SWTPG_WIB2_MIN_CTAS 1
-#endif
+// Algo::kWib2MinCtas caps the registers so that that many CTAs fit an SM (5 = 25 warps): +1 % for SimpleThreshold, +2 % for
+// FIR + IQR, -3.5 % for the running sum, which therefore leaves it at 1 (gpurun_out/var30: measured per policy).
 template<class Algo, int NSTAGE, bool DUMP>
-__global__ void __launch_bounds__((kWib2Warps + 1) * 32, SWTPG_WIB2_MIN_CTAS)
+__global__ void __launch_bounds__((kWib2Warps + 1) * 32, Algo::kWib2MinCtas)
 wib2_kernel(const KernelParams p)
 {
   constexpr uint32_t kUnit = SWTPG_WIB2_SUPERCHUNK_BYTES;
