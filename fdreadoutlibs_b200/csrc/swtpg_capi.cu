@@ -1273,41 +1273,121 @@ tp_less(const swtpg_tp& a, const swtpg_tp& b)
   return a.adc_integral < b.adc_integral;
 }
 
+// Host-side ordering of a batch's TP list. A 64-frame batch of 148 APAs carries ~0.5 M records: std::sort needs ~110 ms for
+// them, more than the batch's whole host-to-device copy. The keys are narrow, though — time_start spans the batch (a few
+// 10^5 ticks), link < n_links, channel < 256 — so (time_start - min, link, channel) packs into one 64-bit integer, and an LSD
+// radix sort of (key, index) pairs with 11-bit digits followed by one gather orders the list in ~10 ms. Ties on the key
+// (which cannot come out of one handle) are ordered like tp_less afterwards; lists whose keys do not fit fall back to std::sort.
+static unsigned
+bit_length(uint64_t v)
+{
+  unsigned b = 0;
+  while (v) {
+    ++b;
+    v >>= 1;
+  }
+  return b;
+}
+
+static void
+sort_tps_impl(swtpg_tp* a, size_t n)
+{
+  if (n < 2)
+    return;
+  if (n < 4096 || n > 0xFFFFFFFFull) {
+    std::stable_sort(a, a + n, tp_less);
+    return;
+  }
+  uint64_t tmin = a[0].time_start, tmax = a[0].time_start;
+  uint32_t lmax = 0;
+  uint16_t cmax = 0;
+  for (size_t i = 0; i < n; ++i) {
+    tmin = std::min(tmin, a[i].time_start);
+    tmax = std::max(tmax, a[i].time_start);
+    lmax = std::max(lmax, a[i].link);
+    cmax = std::max(cmax, a[i].channel);
+  }
+  const unsigned cb = bit_length(cmax), lb = bit_length(lmax), tb = bit_length(tmax - tmin), bits = cb + lb + tb;
+  if (bits > 64) {
+    std::stable_sort(a, a + n, tp_less);
+    return;
+  }
+  struct KV
+  {
+    uint64_t key;
+    uint32_t idx, pad;
+  };
+  constexpr unsigned kDigit = 11, kBuckets = 1u << kDigit, kMaxPasses = (64 + kDigit - 1) / kDigit;
+  const unsigned passes = (bits + kDigit - 1) / kDigit;
+  // scratch is kept per calling thread between calls (grow-only): a batch-sized sort per superchunk would otherwise spend most
+  // of its time faulting in 64 n bytes of fresh pages
+  thread_local std::vector<unsigned char> scratch;
+  const size_t need = 2 * n * sizeof(KV) + n * sizeof(swtpg_tp) + 64;
+  if (scratch.size() < need)
+    scratch.resize(need + need / 4);
+  unsigned char* base = scratch.data() + ((64 - (reinterpret_cast<uintptr_t>(scratch.data()) & 63)) & 63);
+  KV* kv = reinterpret_cast<KV*>(base);
+  KV* kv2 = kv + n;
+  swtpg_tp* out = reinterpret_cast<swtpg_tp*>(kv2 + n);
+  std::vector<uint32_t> hist(size_t(kMaxPasses) * kBuckets, 0u); // all digit histograms in the pass that builds the keys
+  for (size_t i = 0; i < n; ++i) {
+    const uint64_t t = a[i].time_start - tmin;
+    const uint64_t key = (tb ? t << (lb + cb) : 0) | (uint64_t(a[i].link) << cb) | a[i].channel;
+    kv[i].key = key;
+    kv[i].idx = uint32_t(i);
+    for (unsigned p = 0; p < passes; ++p)
+      ++hist[p * kBuckets + ((key >> (p * kDigit)) & (kBuckets - 1))];
+  }
+  KV *src = kv, *dst = kv2;
+  for (unsigned p = 0; p < passes; ++p) {
+    uint32_t* h = hist.data() + size_t(p) * kBuckets;
+    uint32_t sum = 0;
+    bool trivial = false;
+    for (unsigned d = 0; d < kBuckets; ++d) {
+      trivial |= h[d] == n; // every key has the same digit: nothing to do
+      const uint32_t c = h[d];
+      h[d] = sum;
+      sum += c;
+    }
+    if (trivial)
+      continue;
+    const unsigned shift = p * kDigit;
+    for (size_t i = 0; i < n; ++i)
+      dst[h[(src[i].key >> shift) & (kBuckets - 1)]++] = src[i];
+    std::swap(src, dst);
+  }
+  for (size_t i = 0; i < n; ++i)
+    out[i] = a[src[i].idx];
+  for (size_t i = 0; i < n;) { // runs of equal (time_start, link, channel): order the rest of tp_less, keeping input order on full ties
+    size_t j = i + 1;
+    while (j < n && src[j].key == src[i].key)
+      ++j;
+    if (j - i > 1)
+      std::stable_sort(out + i, out + j, tp_less);
+    i = j;
+  }
+  memcpy(a, out, n * sizeof(swtpg_tp));
+}
+
 void
 swtpg_sort_tps(swtpg_tp* tps, size_t n)
 {
   if (tps && n > 1)
-    std::sort(tps, tps + n, tp_less);
+    sort_tps_impl(tps, n);
 }
 
 void
 swtpg_merge_sorted(const swtpg_tp* const* lists, const size_t* n, size_t k, swtpg_tp* out)
 {
-  // binary-heap k-way merge keyed like swtpg_sort_tps; ties resolved by list index (stable across GPUs)
-  struct Cur { size_t list, pos; };
-  std::vector<Cur> heap;
-  auto less = [&](const Cur& a, const Cur& b) { // "a after b" for std::*_heap's max-heap convention
-    const swtpg_tp& x = lists[a.list][a.pos];
-    const swtpg_tp& y = lists[b.list][b.pos];
-    if (tp_less(y, x)) return true;
-    if (tp_less(x, y)) return false;
-    return a.list > b.list;
-  };
-  for (size_t i = 0; i < k; ++i)
+  // The lists are sorted like swtpg_sort_tps; ties are resolved by list index (stable across GPUs). Concatenating them in list
+  // order and running the stable radix sort gives exactly that order, in O(total) instead of O(total log k) comparisons.
+  size_t total = 0;
+  for (size_t i = 0; i < k; ++i) {
     if (n[i])
-      heap.push_back({ i, 0 });
-  std::make_heap(heap.begin(), heap.end(), less);
-  size_t o = 0;
-  while (!heap.empty()) {
-    std::pop_heap(heap.begin(), heap.end(), less);
-    Cur c = heap.back();
-    heap.pop_back();
-    out[o++] = lists[c.list][c.pos];
-    if (++c.pos < n[c.list]) {
-      heap.push_back(c);
-      std::push_heap(heap.begin(), heap.end(), less);
-    }
+      memcpy(out + total, lists[i], n[i] * sizeof(swtpg_tp));
+    total += n[i];
   }
+  sort_tps_impl(out, total);
 }
 
 } // extern "C"

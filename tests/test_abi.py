@@ -108,6 +108,37 @@ def test_sort_and_merge():
     assert S.merge_sorted([np.zeros(0, dtype=F.TP_DTYPE), parts[0]]).size == parts[0].size
 
 
+@pytest.mark.parametrize("n,wide", [(3000, False), (120000, False), (120000, True)])
+def test_sort_and_merge_match_a_lexicographic_sort(n, wide):
+    """swtpg_sort_tps (std::stable_sort below 4096 records, a radix sort of packed keys above, std::stable_sort again when the keys
+    do not fit 64 bits) and swtpg_merge_sorted order by (time_start, link, channel, time_over_threshold, adc_integral) — with
+    plenty of ties on the first three — exactly like numpy's lexsort, and the merge of per-GPU lists equals the sort of the union."""
+    rng = np.random.default_rng(n + wide)
+    tps = np.zeros(n, dtype=F.TP_DTYPE)
+    tps["time_start"] = 79554162068719943 + 32 * rng.integers(0, 5000, n)
+    if wide:
+        tps["time_start"][::3] += np.uint64(1) << np.uint64(62)  # key range beyond 64 bits together with link and channel
+        tps["link"][::5] = 0xFFFFFFF0
+    tps["link"] += rng.integers(0, 6000, n).astype(np.uint32)
+    tps["channel"] = rng.integers(0, 256, n)
+    tps["time_over_threshold"] = 32 * rng.integers(1, 3, n)
+    tps["adc_integral"] = rng.integers(1, 4, n)
+    tps["time_peak"] = rng.integers(0, 1 << 40, n)
+    tps["adc_peak"] = rng.integers(0, 1 << 14, n)
+    order = np.lexsort((tps["adc_integral"], tps["time_over_threshold"], tps["channel"], tps["link"], tps["time_start"]))
+    want = tps[order]
+    got = S.sort_tps(tps.copy())
+    keys = ("time_start", "link", "channel", "time_over_threshold", "adc_integral")
+    for f in keys:
+        assert (got[f] == want[f]).all(), f
+    assert (F.sort_tps(got) == F.sort_tps(tps)).all()  # same multiset of whole records
+    parts = [S.sort_tps(tps[r::5].copy()) for r in range(5)]
+    merged = S.merge_sorted(parts)
+    for f in keys:
+        assert (merged[f] == want[f]).all(), f
+    assert (F.sort_tps(merged) == F.sort_tps(tps)).all()
+
+
 def test_firwin_int_host():
     assert list(S.firwin_int(7, 0.1, 64)) == [1, 6, 15, 20, 15, 6, 1]
 
