@@ -416,6 +416,7 @@ void
 WIBEthFrameProcessor::process_swtpg_hits(const swtpg_tp* tps, size_t n)
 {
   uint64_t nhits = 0;
+  std::lock_guard<std::mutex> lk(m_rate_mu); // one lock per delivered block of records (get_info is the only other taker)
   for (size_t i = 0; i < n; ++i) {
     const swtpg_tp& r = tps[i];
     // H2: production indexes the POSITION-ordered map with the FRAME channel the AVX2 code emits (:527).
@@ -443,7 +444,6 @@ WIBEthFrameProcessor::process_swtpg_hits(const swtpg_tp* tps, size_t n)
       m_new_tps++;
       ++nhits;
     }
-    std::lock_guard<std::mutex> lk(m_rate_mu);
     m_tp_channel_rate_map[offline_channel]++;
   }
   m_tpg_hits_count += nhits;
@@ -604,6 +604,7 @@ WIB2FrameProcessor::find_hits(constframeptr fp, WIB2FrameHandler* frame_handler)
 void
 WIB2FrameProcessor::process_swtpg_hits(const swtpg_tp* tps, size_t n)
 {
+  std::lock_guard<std::mutex> lk(m_rate_mu); // one lock per delivered block of records
   uint64_t nhits = 0;
   for (size_t i = 0; i < n; ++i) {
     const swtpg_tp& r = tps[i];
@@ -627,7 +628,6 @@ WIB2FrameProcessor::process_swtpg_hits(const swtpg_tp* tps, size_t n)
       m_tps_send_failed++;
     m_new_tps++; // counted regardless of the outcome, as the reference does (:469-470)
     ++nhits;
-    std::lock_guard<std::mutex> lk(m_rate_mu);
     m_tp_channel_rate_map[offline_channel]++;
   }
   m_tpg_hits_count += nhits;
