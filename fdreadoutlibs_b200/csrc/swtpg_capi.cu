@@ -14,6 +14,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -103,6 +104,16 @@ struct swtpg_handle
   std::unique_ptr<HostRange[]> link_range;
   std::atomic<uint64_t> ranges_epoch{ 0 };
   std::unique_ptr<uint64_t[]> link_range_epoch;
+
+  // bounce pipeline of swtpg_process_host for pageable sources: per worker two pinned buffers, a stream and events
+  struct Bounce
+  {
+    uint8_t* buf[2] = { nullptr, nullptr };
+    cudaEvent_t free_ev[2] = { nullptr, nullptr };
+    cudaEvent_t done = nullptr;
+    cudaStream_t stream = nullptr;
+  };
+  std::vector<Bounce> bounce;
 
   swtpg_counters counters{};
   std::atomic<uint64_t> submit_busy{ 0 };
@@ -775,6 +786,14 @@ swtpg_destroy(swtpg_handle* h)
       cudaGetLastError();
   for (auto& s : h->slots)
     free_slot(*s);
+  for (auto& b : h->bounce) {
+    for (int i = 0; i < 2; ++i) {
+      if (b.buf[i]) cudaFreeHost(b.buf[i]);
+      if (b.free_ev[i]) cudaEventDestroy(b.free_ev[i]);
+    }
+    if (b.done) cudaEventDestroy(b.done);
+    if (b.stream) cudaStreamDestroy(b.stream);
+  }
   if (h->d_state) cudaFree(h->d_state);
   if (h->d_flags) cudaFree(h->d_flags);
   if (h->d_link_cursor) cudaFree(h->d_link_cursor);
@@ -898,6 +917,79 @@ swtpg_last_kernel_ms(swtpg_handle* h)
   return double(ms);
 }
 
+// Copy of one payload into pinned memory (csrc/stage_copy.cpp: non-temporal stores where the CPU has AVX2).
+extern "C" void swtpg_stage_copy(void* dst, const void* src, size_t bytes);
+
+// Host-to-device copy of a PAGEABLE source. cudaMemcpyAsync would stage it through the driver's own bounce buffer on one
+// thread (11 GB/s on the bench box against 55 GB/s from pinned memory); here a few worker threads copy 4 MB chunks into their
+// own pinned double buffers with non-temporal stores and queue the DMA of each chunk on their own stream, so the host copies
+// of later chunks overlap the transfers of earlier ones. The handle's stream then waits for every worker's last transfer.
+constexpr size_t kBounceChunk = size_t(4) << 20;
+constexpr size_t kBounceMinBytes = size_t(16) << 20;
+
+static bool
+is_pageable(const void* p)
+{
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+static swtpg_status
+staged_h2d(swtpg_handle* h, uint8_t* d_dst, const uint8_t* src, size_t bytes)
+{
+  if (h->bounce.empty()) {
+    const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+    const unsigned workers = std::min(8u, hw / 2);
+    std::vector<swtpg_handle::Bounce> b(workers);
+    for (auto& w : b) {
+      for (int i = 0; i < 2; ++i) {
+        SW_CUDA(h, cudaMallocHost(&w.buf[i], kBounceChunk));
+        SW_CUDA(h, cudaEventCreateWithFlags(&w.free_ev[i], cudaEventDisableTiming));
+      }
+      SW_CUDA(h, cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+      SW_CUDA(h, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    }
+    h->bounce = std::move(b);
+  }
+  const size_t n_chunks = (bytes + kBounceChunk - 1) / kBounceChunk;
+  const size_t workers = h->bounce.size();
+  std::vector<cudaError_t> err(workers, cudaSuccess);
+  std::vector<std::thread> threads;
+  const int device = h->cfg.device;
+  for (size_t t = 0; t < workers; ++t)
+    threads.emplace_back([&, t]() {
+      swtpg_handle::Bounce& w = h->bounce[t];
+      cudaError_t e = cudaSetDevice(device);
+      unsigned used = 0;
+      for (size_t c = t; c < n_chunks && e == cudaSuccess; c += workers, ++used) {
+        const int slot = int(used & 1u);
+        if (used >= 2)
+          e = cudaEventSynchronize(w.free_ev[slot]); // the transfer that last read this buffer has finished
+        if (e != cudaSuccess)
+          break;
+        const size_t off = c * kBounceChunk, len = std::min(kBounceChunk, bytes - off);
+        swtpg_stage_copy(w.buf[slot], src + off, len);
+        e = cudaMemcpyAsync(d_dst + off, w.buf[slot], len, cudaMemcpyHostToDevice, w.stream);
+        if (e == cudaSuccess)
+          e = cudaEventRecord(w.free_ev[slot], w.stream);
+      }
+      if (e == cudaSuccess)
+        e = cudaEventRecord(w.done, w.stream);
+      err[t] = e;
+    });
+  for (auto& th : threads)
+    th.join();
+  for (size_t t = 0; t < workers; ++t) {
+    SW_CUDA(h, err[t]);
+    SW_CUDA(h, cudaStreamWaitEvent(h->stream, h->bounce[t].done, 0));
+  }
+  return SWTPG_OK;
+}
+
 static swtpg_status
 process_host_impl(swtpg_handle* h, const void* frames, const uint32_t* n_units, uint32_t stride, swtpg_tp* out, size_t cap, size_t* n_out,
                   int16_t* ped_out, int16_t* wav_out, bool dump)
@@ -929,8 +1021,13 @@ process_host_impl(swtpg_handle* h, const void* frames, const uint32_t* n_units, 
     SW_CUDA(h, cudaMemsetAsync(h->d_ped, 0, dump_elems * 2, h->stream));
     SW_CUDA(h, cudaMemsetAsync(h->d_wav, 0, dump_elems * 2, h->stream));
   }
-  if (bytes)
+  if (bytes >= kBounceMinBytes && is_pageable(frames)) {
+    s = staged_h2d(h, h->d_frames, static_cast<const uint8_t*>(frames), bytes);
+    if (s != SWTPG_OK)
+      return s;
+  } else if (bytes) {
     SW_CUDA(h, cudaMemcpyAsync(h->d_frames, frames, bytes, cudaMemcpyHostToDevice, h->stream));
+  }
   h->counters.h2d_bytes += bytes;
   s = enqueue_batch(h, h->d_frames, n_units, stride, h->stream, dump);
   if (s != SWTPG_OK)
@@ -984,9 +1081,6 @@ is_registered(swtpg_handle* h, uint32_t link, const void* unit, size_t bytes)
   h->link_range_epoch[link] = h->ranges_epoch.load(std::memory_order_relaxed);
   return c.hi != 0;
 }
-
-// Copy of one payload into the pinned staging slot (csrc/stage_copy.cpp: non-temporal stores where the CPU has AVX2).
-extern "C" void swtpg_stage_copy(void* dst, const void* src, size_t bytes);
 
 swtpg_status
 swtpg_submit(swtpg_handle* h, uint32_t link, const void* unit, size_t bytes)

@@ -160,7 +160,9 @@ swtpg_status swtpg_set_rs_memory_factor(swtpg_handle* h, const uint16_t* by_link
  * m_assigned_tpg_algorithm_function + process_swtpg_hits' field arithmetic
  * (src/wibeth/WIBEthFrameProcessor.cpp:410-476,478-549; src/wib2/WIB2FrameProcessor.cpp:345-396,398-458).
  */
-/* Host buffers (pageable or pinned): H2D copy, kernel, D2H of the TP list, all inside the call. */
+/* Host buffers (pageable or pinned): H2D copy, kernel, D2H of the TP list, all inside the call. Pinned or registered sources
+ * are read by the copy engine directly; pageable sources of 16 MB and more go through a pipeline of pinned bounce buffers
+ * filled by a few worker threads (3.6x the rate of a plain cudaMemcpy from pageable memory on the bench box). */
 swtpg_status swtpg_process_host(swtpg_handle* h, const void* frames, const uint32_t* n_units, uint32_t units_stride,
                                 swtpg_tp* out, size_t cap, size_t* n_out);
 /* Frames already resident in HBM. `stream` is a cudaStream_t; NULL = the handle's own (non-blocking) stream — to run on
