@@ -9,7 +9,8 @@ from oracle import binding as B
 
 ok = True
 for fmt, algo, aid, thr in [("wibeth", "SimpleThreshold", 0, 20), ("wibeth", "AbsRS", 1, 30), ("wibeth", "StandardRS", 2, 30), ("wibeth", "FIR", 3, 5),
-                            ("wibeth", "SimpleThreshold", 0, 40000), ("wib2", "SimpleThreshold", 0, 30), ("wib2", "FIR", 3, 5)]:
+                            ("wibeth", "SimpleThreshold", 0, 40000), ("wib2", "SimpleThreshold", 0, 30), ("wib2", "FIR", 3, 5),
+                            ("wib2", "AbsRS", 1, 30)]:
     n_links, n_units = (5, 6) if fmt == "wibeth" else (3, 10)
     gen = S.gen_wibeth_host if fmt == "wibeth" else S.gen_wib2_host
     units = gen(S.gen_params(81, 0.6), n_links, n_units)
