@@ -128,6 +128,22 @@ TpgEngine::set_link_memory_factor(uint32_t link, const uint16_t* by_channel, uin
   check(m_h, swtpg_set_rs_memory_factor(m_h, m_rs_factor.data()), "swtpg_set_rs_memory_factor");
 }
 
+// Blocking back-pressure (block_on_backpressure, a test / replay aid — the reference drops instead): the staging ring is full,
+// so the GPU pipeline has to drain before this link can go on. SWTPG_HOST_BACKOFF_US > 0 sleeps that long instead of yielding,
+// which frees the core for the other links' threads when there are more threads than cores.
+static void
+backoff()
+{
+  static const int us = [] {
+    const char* e = getenv("SWTPG_HOST_BACKOFF_US");
+    return e ? atoi(e) : 0;
+  }();
+  if (us > 0)
+    std::this_thread::sleep_for(std::chrono::microseconds(us));
+  else
+    std::this_thread::yield();
+}
+
 bool
 TpgEngine::submit(uint32_t link, const void* unit, size_t bytes)
 {
@@ -406,7 +422,7 @@ WIBEthFrameProcessor::find_hits(constframeptr fp, WIBEthFrameHandler* frame_hand
       break;
     }
     m_engine->drain(false);
-    std::this_thread::yield();
+    backoff();
   }
   if ((++m_frames_since_drain & 7u) == 0) // TPs only appear once per superchunk: polling on every frame would only contend
     m_engine->drain(false);
@@ -595,7 +611,7 @@ WIB2FrameProcessor::find_hits(constframeptr fp, WIB2FrameHandler* frame_handler)
       break;
     }
     m_engine->drain(false);
-    std::this_thread::yield();
+    backoff();
   }
   if ((++m_frames_since_drain & 7u) == 0) // TPs only appear once per superchunk: polling on every frame would only contend
     m_engine->drain(false);
