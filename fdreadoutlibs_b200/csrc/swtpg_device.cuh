@@ -355,7 +355,7 @@ struct HitStage
 
   // Converts and writes out everything staged (see flush_hits). Whole warp calls, converged.
   template<bool WIB2_UNITS, bool WIB2_FIELDS>
-  __device__ __forceinline__ void flush(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const;
+  __device__ __forceinline__ void flush(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane, bool everything) const;
 };
 
 // Pair records -> swtpg_tp. Out of line (cold) and all-by-value, so the caller keeps its state in registers.
@@ -366,10 +366,14 @@ struct HitStage
 template<bool WIB2_UNITS, bool WIB2_FIELDS>
 __device__ __noinline__ void
 flush_hits(uint4* buf, uint32_t* aux, uint32_t* cnt, swtpg_tp* out, unsigned int* out_count, uint32_t out_cap, const uint8_t* link_base,
-           uint32_t link, uint32_t lane)
+           uint32_t link, uint32_t lane, bool everything)
 {
   __syncwarp();
-  const uint32_t n = *reinterpret_cast<volatile uint32_t*>(cnt);
+  const uint32_t parked = *reinterpret_cast<volatile uint32_t*>(cnt);
+  // In the middle of a link only whole rounds of 32 pairs are written out (every lane busy in every round); the tail stays
+  // parked — at most 31 records, within the room a group needs — and moves to the front of the buffer. The end of a link
+  // writes out everything.
+  const uint32_t n = everything ? parked : parked & ~31u;
   if (n == 0)
     return;
   // Pass 1: how many TPs the parked pairs hold, then ONE reservation in the global list. The atomic's round trip overlaps
@@ -438,16 +442,30 @@ flush_hits(uint4* buf, uint32_t* aux, uint32_t* cnt, swtpg_tp* out, unsigned int
     }
   }
   __syncwarp();
+  const uint32_t rest = parked - n; // < 32
+  uint4 r = make_uint4(0u, 0u, 0u, 0u);
+  uint32_t pt2 = 0u;
+  if (lane < rest) {
+    r = buf[n + lane];
+    if constexpr (!WIB2_FIELDS)
+      pt2 = aux[n + lane];
+  }
+  __syncwarp();
+  if (lane < rest) {
+    buf[lane] = r;
+    if constexpr (!WIB2_FIELDS)
+      aux[lane] = pt2;
+  }
   if (lane == 0)
-    *reinterpret_cast<volatile uint32_t*>(cnt) = 0u;
+    *reinterpret_cast<volatile uint32_t*>(cnt) = rest;
   __syncwarp();
 }
 
 template<bool WIB2_UNITS, bool WIB2_FIELDS>
 __device__ __forceinline__ void
-HitStage::flush(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane) const
+HitStage::flush(const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane, bool everything) const
 {
-  flush_hits<WIB2_UNITS, WIB2_FIELDS>(buf, aux, cnt, k.buf, k.count, k.cap, link_base, link, lane);
+  flush_hits<WIB2_UNITS, WIB2_FIELDS>(buf, aux, cnt, k.buf, k.count, k.cap, link_base, link, lane, everything);
 }
 
 } // namespace swtpg

@@ -209,7 +209,7 @@ struct ScalarAlgo
   __device__ __forceinline__ uint32_t phase_after(uint32_t ticks) const { return (kphase + ticks) & 7u; }
   __device__ __forceinline__ void configure(const KernelParams&) {}
   template<bool WIB2_UNITS>
-  static __device__ __forceinline__ void flush(const HitStage&, const TpSink&, const uint8_t*, uint32_t, uint32_t) {} // emits directly
+  static __device__ __forceinline__ void flush(const HitStage&, const TpSink&, const uint8_t*, uint32_t, uint32_t, bool = true) {} // emits directly
 
   // setState: pedestal = first sample, quartiles +-20 (wibeth/tpg/ProcessingInfo.hpp:116-144)
   __device__ __forceinline__ void seed(uint32_t S)
@@ -479,9 +479,10 @@ struct PackedSimpleWibEth
   __device__ __forceinline__ uint32_t phase_after(uint32_t) const { return 0; }
   __device__ __forceinline__ void seed(uint32_t S) { Mq = add2(~S, 0x00020002u); }
   template<bool WIB2_UNITS>
-  static __device__ __forceinline__ void flush(const HitStage& h, const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane)
+  static __device__ __forceinline__ void flush(const HitStage& h, const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane,
+                                               bool everything = true)
   {
-    h.template flush<WIB2_UNITS, false>(k, link_base, link, lane);
+    h.template flush<WIB2_UNITS, false>(k, link_base, link, lane, everything);
   }
 
   // frugal streaming median (wibeth/tpg/UtilsAVX2.hpp:38-73) + pedestal subtraction (ProcessAVX2.hpp:85): S -> s' + 1
@@ -566,7 +567,7 @@ struct PackedSimpleWibEth
     for (int g = 0; g < G; ++g)
       hit_update(sp[g], ctx, t0 + g);
     if (ctx.stage->must_flush())
-      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
+      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u, false); // whole 32-pair rounds only
   }
 };
 
@@ -580,9 +581,10 @@ struct PackedSimpleWib2 : PackedSimpleWibEth
   uint32_t shift, shmask;
 
   template<bool WIB2_UNITS>
-  static __device__ __forceinline__ void flush(const HitStage& h, const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane)
+  static __device__ __forceinline__ void flush(const HitStage& h, const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane,
+                                               bool everything = true)
   {
-    h.template flush<WIB2_UNITS, true>(k, link_base, link, lane);
+    h.template flush<WIB2_UNITS, true>(k, link_base, link, lane, everything);
   }
 
   __device__ __forceinline__ void configure(const KernelParams& p)
@@ -633,7 +635,7 @@ struct PackedSimpleWib2 : PackedSimpleWibEth
     for (int g = 0; g < G; ++g)
       hit_update(sp[g], ctx, t0 + g);
     if (ctx.stage->must_flush())
-      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
+      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u, false); // whole 32-pair rounds only
   }
 };
 
@@ -782,7 +784,7 @@ struct PackedRsWibEth : PackedSimpleWibEth
     for (int g = 0; g < G; ++g)
       hit_update(sp[g], lv[g], ctx, t0 + g);
     if (ctx.stage->must_flush())
-      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
+      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u, false); // whole 32-pair rounds only
   }
 };
 
@@ -824,9 +826,10 @@ struct PackedFirIqr
   static constexpr uint32_t kOne = 0x3C003C00u, kNegOne = 0xBC00BC00u;
 
   template<bool WIB2_UNITS>
-  static __device__ __forceinline__ void flush(const HitStage& h, const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane)
+  static __device__ __forceinline__ void flush(const HitStage& h, const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane,
+                                               bool everything = true)
   {
-    h.template flush<WIB2_UNITS, true>(k, link_base, link, lane); // FIR hit blocks carry {chan, t, charge, tover} only
+    h.template flush<WIB2_UNITS, true>(k, link_base, link, lane, everything); // FIR hit blocks carry {chan, t, charge, tover} only
   }
   __device__ __forceinline__ void configure(const KernelParams& p)
   {
@@ -1024,7 +1027,7 @@ struct PackedFirIqr
         hit_update<false>(filt[g], threshold(sig3[g]), ctx, t0 + g);
     }
     if (ctx.stage->must_flush())
-      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
+      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u, false); // whole 32-pair rounds only
   }
 
   template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
@@ -1286,7 +1289,7 @@ struct PackedRsIqrWib2 : PackedFirIqr
         hit_update<false>(lv[g], rs[g], threshold(sig3[g]), ctx, t0 + g);
     }
     if (ctx.stage->must_flush())
-      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u);
+      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u, false); // whole 32-pair rounds only
   }
 };
 
