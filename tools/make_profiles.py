@@ -72,14 +72,15 @@ if __name__ == "__main__":
         json.dump({"links": 5920, "frames": 64, "dram_bytes_per_launch": traffic,
                    "source": f"profiles/{tag}_wibeth_simple_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"},
                   open(os.path.join(PR, "dram_traffic.json"), "w"), indent=1)
-    for name in ("fir", "absrs"):
+    for name in ("fir", "absrs", "stdrs", "stress"):
         rep = os.path.join(GO, f"{tag}_wibeth_{name}_full.ncu-rep")
         if os.path.exists(rep):
             summarize(rep, os.path.join(PR, f"{tag}_wibeth_{name}_ncu_full.txt"), 5920, 64, 7200, 64)
             instruction_buckets(rep, os.path.join(PR, f"{tag}_wibeth_{name}_instruction_mix.txt"), 5920 * 64)
-    rep = os.path.join(GO, f"{tag}_wib2_simple_full.ncu-rep")
-    if os.path.exists(rep):
-        summarize(rep, os.path.join(PR, f"{tag}_wib2_simple_ncu_full.txt"), 1480 * 4, 340, 5664 / 4, 12)
+    for name in ("simple", "fir", "absrs"):
+        rep = os.path.join(GO, f"{tag}_wib2_{name}_full.ncu-rep")
+        if os.path.exists(rep):
+            summarize(rep, os.path.join(PR, f"{tag}_wib2_{name}_ncu_full.txt"), 1480 * 4, 340, 5664 / 4, 12)
     src = os.path.join(GO, f"{tag}_launches.csv")
     if os.path.exists(src):
         keep = [l for l in open(src) if l.startswith('"')]
