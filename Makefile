@@ -1,21 +1,40 @@
 # Builds everything in-tree (the .so files travel to the GPU box with the snapshot; they are git-ignored).
-#   make lib      fdreadoutlibs_b200/libswtpg_b200.so   CUDA kernels + C ABI (include/swtpg.h), sm_100a only
-#   make host     fdreadoutlibs_b200/libswtpg_host.so   C++ frame-processor shim above the C ABI (g++)
+#   make lib      fdreadoutlibs_b200/libswtpg_b200.so      CUDA kernels + C ABI (include/swtpg.h), sm_100a only
+#                 fdreadoutlibs_b200/libswtpg_framegen.so  synthetic frame generator (include/swtpg_framegen.h; test / bench utility)
+#   make host     fdreadoutlibs_b200/libswtpg_host.so      C++ frame-processor shim above the C ABI (g++)
+#   make apps     build/bin/wibeth_tpg_emulator            file-replay emulator front-end on the shim
 #   make oracle   oracle/liboracle.so and (where /root/reference exists) oracle/_ref/libswtpg_ref.so
 NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH = -gencode arch=compute_100a,code=sm_100a
 NVFLAGS = $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v --expt-relaxed-constexpr
 CSRC = fdreadoutlibs_b200/csrc
+OBJ = build/obj
 LIB = fdreadoutlibs_b200/libswtpg_b200.so
+GENLIB = fdreadoutlibs_b200/libswtpg_framegen.so
 
-all: lib host oracle
+all: lib host apps oracle
 
-lib: $(LIB)
+lib: $(LIB) $(GENLIB)
 
-$(LIB): $(CSRC)/swtpg_capi.cu $(CSRC)/framegen_capi.cu $(CSRC)/stage_copy.cpp $(CSRC)/swtpg_kernels.cuh $(CSRC)/swtpg_device.cuh $(CSRC)/framegen.h include/swtpg.h include/swtpg_framegen.h
-	g++ -O2 -std=c++17 -Wall -fPIC -c -o build_stage_copy.o $(CSRC)/stage_copy.cpp
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/swtpg_capi.cu $(CSRC)/framegen_capi.cu build_stage_copy.o 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
+# the fused kernels + launch table (slow to compile: every policy x kernel form is instantiated here)
+$(OBJ)/swtpg_capi.o: $(CSRC)/swtpg_capi.cu $(CSRC)/swtpg_kernels.cuh $(CSRC)/swtpg_device.cuh $(CSRC)/swtpg_handle.h include/swtpg.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) $(KFLAGS) -c -o $@ $(CSRC)/swtpg_capi.cu 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
 	@grep -E "error|warning: v" build_ptxas.log || true
+# the streaming engine + gather kernels
+$(OBJ)/swtpg_stream.o: $(CSRC)/swtpg_stream.cu $(CSRC)/swtpg_handle.h include/swtpg.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c -o $@ $(CSRC)/swtpg_stream.cu 2> build_ptxas_stream.log || (cat build_ptxas_stream.log; exit 1)
+# host-only pieces: staging copy, TP sort / merge, FIR tap design
+$(OBJ)/swtpg_hostutil.o: $(CSRC)/swtpg_hostutil.cpp include/swtpg.h
+	@mkdir -p $(OBJ)
+	g++ -O2 -std=c++17 -Wall -fPIC -c -o $@ $(CSRC)/swtpg_hostutil.cpp
+
+$(LIB): $(OBJ)/swtpg_capi.o $(OBJ)/swtpg_stream.o $(OBJ)/swtpg_hostutil.o
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lpthread
+
+$(GENLIB): $(CSRC)/framegen_capi.cu $(CSRC)/framegen.h include/swtpg_framegen.h include/swtpg.h
+	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall --expt-relaxed-constexpr -shared -o $@ $(CSRC)/framegen_capi.cu
 
 # Host-side C++ mirror of the reference's frame processors (plain g++; links against the C ABI only)
 HOST = fdreadoutlibs_b200/libswtpg_host.so
@@ -23,10 +42,12 @@ host: $(HOST)
 $(HOST): fdreadoutlibs_b200/host/swtpg_host.cpp fdreadoutlibs_b200/host/swtpg_host.hpp include/swtpg.h $(LIB)
 	g++ -O2 -std=c++17 -Wall -Wextra -fPIC -shared -pthread -o $@ fdreadoutlibs_b200/host/swtpg_host.cpp -Lfdreadoutlibs_b200 -lswtpg_b200 -Wl,-rpath,'$$ORIGIN'
 
+apps:
+
 oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -f $(LIB) $(HOST) build_ptxas.log
+	rm -rf $(LIB) $(GENLIB) $(HOST) $(OBJ) build_ptxas.log build_ptxas_stream.log
 	$(MAKE) -C oracle clean
-.PHONY: all lib host oracle clean
+.PHONY: all lib host apps oracle clean

@@ -1,4 +1,5 @@
-"""ctypes binding of libswtpg_b200.so (include/swtpg.h, include/swtpg_framegen.h).
+"""ctypes binding of libswtpg_b200.so (include/swtpg.h). The synthetic frame generator (include/swtpg_framegen.h) lives in
+its own small library and module, fdreadoutlibs_b200/framegen.py.
 
 The library is built in-tree by `make lib` / `__graft_entry__.build()`. There is deliberately no fallback: if the
 shared object is missing, importing this module raises, and every compute call fails when no sm_100 GPU is present.
@@ -36,6 +37,7 @@ class SwtpgConfig(C.Structure):
         ("reserved0", C.c_uint8 * 3),
         ("wib2_adc_offset", C.c_uint32),
         ("flags", C.c_uint32),
+        ("dispatch_timeout_us", C.c_uint32),
     ]
 
 
@@ -45,19 +47,7 @@ class SwtpgCounters(C.Structure):
         "h2d_bytes", "d2h_bytes")]
 
 
-class GenParams(C.Structure):
-    _fields_ = [
-        ("seed", C.c_uint64),
-        ("noise_q8", C.c_uint32),
-        ("pulse_prob_q32", C.c_uint32),
-        ("amp_min", C.c_uint16), ("amp_max", C.c_uint16),
-        ("hw_min", C.c_uint16), ("hw_max", C.c_uint16),
-        ("ped_base", C.c_uint16), ("ped_step", C.c_uint16), ("ped_mod", C.c_uint16),
-        ("bipolar", C.c_uint16),
-    ]
-
-
-# every symbol include/swtpg.h and include/swtpg_framegen.h declare
+# every symbol include/swtpg.h declares
 EXPORTS = {
     "swtpg_abi_version": (C.c_uint32, []),
     "swtpg_status_string": (C.c_char_p, [C.c_int]),
@@ -68,6 +58,7 @@ EXPORTS = {
     "swtpg_start": (C.c_int, [C.c_void_p]),
     "swtpg_stop": (C.c_int, [C.c_void_p]),
     "swtpg_set_rs_memory_factor": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "swtpg_set_link_rs_memory_factor": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "swtpg_process_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "swtpg_process_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "swtpg_fetch_tps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -75,10 +66,13 @@ EXPORTS = {
     "swtpg_process_host_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t,
                                            C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]),
     "swtpg_submit": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "swtpg_submit_wait": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint64]),
     "swtpg_register_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "swtpg_unregister_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
     "swtpg_flush": (C.c_int, [C.c_void_p]),
     "swtpg_poll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "swtpg_poll_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_uint64]),
+    "swtpg_stream_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "swtpg_sync": (C.c_int, [C.c_void_p]),
     "swtpg_dump_state": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "swtpg_get_counters": (C.c_int, [C.c_void_p, C.POINTER(SwtpgCounters)]),
@@ -87,11 +81,6 @@ EXPORTS = {
     "swtpg_sort_tps": (None, [C.c_void_p, C.c_size_t]),
     "swtpg_merge_sorted": (None, [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.c_void_p]),
     "swtpg_firwin_int": (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_void_p]),
-    "swtpg_gen_default_params": (None, [C.POINTER(GenParams), C.c_uint64, C.c_double]),
-    "swtpg_gen_wibeth_host": (C.c_int, [C.POINTER(GenParams), C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_int]),
-    "swtpg_gen_wib2_host": (C.c_int, [C.POINTER(GenParams), C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int]),
-    "swtpg_gen_wibeth_device": (C.c_int, [C.POINTER(GenParams), C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]),
-    "swtpg_gen_wib2_device": (C.c_int, [C.POINTER(GenParams), C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import frames as F
 from ._lib import (ALGO_ABS_RS, ALGO_FIR_IQR, ALGO_SIMPLE_THRESHOLD, ALGO_STANDARD_RS, FORMAT_WIB2, FORMAT_WIBETH,
-                   SWTPG_ERR_BUSY, SWTPG_ERR_OVERFLOW, SWTPG_OK, GenParams, SwtpgConfig, SwtpgCounters, lib)
+                   SWTPG_ERR_BUSY, SWTPG_ERR_OVERFLOW, SWTPG_OK, SwtpgConfig, SwtpgCounters, lib)
 
 ALGORITHMS = {
     # tpg_algorithm strings of the reference (src/wibeth/WIBEthFrameProcessor.cpp:180-197)
@@ -51,7 +51,8 @@ def _ptr(a: Optional[np.ndarray]):
 class TPGenerator:
     def __init__(self, n_links: int, max_units: int, *, fmt: str = "wibeth", algorithm: str = "SimpleThreshold", threshold: int = 60,
                  acc_limit: int = 10, rs_memory_factor: int = 8, rs_scale_factor: int = 5, fir_taps: Optional[Sequence[int]] = None,
-                 tap_exponent: int = 6, tp_capacity: int = 0, n_slots: int = 0, device: int = 0, wib2_adc_offset: int = 0):
+                 tap_exponent: int = 6, tp_capacity: int = 0, n_slots: int = 0, device: int = 0, wib2_adc_offset: int = 0,
+                 dispatch_timeout_us: int = 0):
         if algorithm not in ALGORITHMS:
             raise TPGAlgorithmInexistent(algorithm)
         cfg = SwtpgConfig()
@@ -72,6 +73,7 @@ class TPGenerator:
                 cfg.fir_taps[i] = int(t)
         cfg.tap_exponent = tap_exponent
         cfg.wib2_adc_offset = wib2_adc_offset
+        cfg.dispatch_timeout_us = dispatch_timeout_us
         self.cfg = cfg
         self.fmt = fmt
         self.n_links = n_links
@@ -119,6 +121,11 @@ class TPGenerator:
         if a is not None:
             assert a.size == self.n_links * self.channels
         self._check(lib.swtpg_set_rs_memory_factor(self._h, _ptr(a)))
+
+    def set_link_rs_memory_factor(self, link: int, by_channel: np.ndarray):
+        a = np.ascontiguousarray(by_channel, dtype=np.uint16)
+        assert a.size == self.channels
+        self._check(lib.swtpg_set_link_rs_memory_factor(self._h, link, a.ctypes.data))
 
     # -- batch entry points ----------------------------------------------------------------------------------------------
     def _nunits(self, n_units):
@@ -180,11 +187,14 @@ class TPGenerator:
         return float(lib.swtpg_last_kernel_ms(self._h))
 
     # -- streaming entry points --------------------------------------------------------------------------------------------
-    def submit(self, link: int, unit: np.ndarray) -> bool:
-        """One payload of one link. False = back-pressure (SWTPG_ERR_BUSY)."""
+    def submit(self, link: int, unit: np.ndarray, wait_us: int = 0) -> bool:
+        """One payload of one link. False = back-pressure (SWTPG_ERR_BUSY); wait_us > 0 sleeps up to that long for ring space."""
         unit = np.ascontiguousarray(unit, dtype=np.uint8)  # a contiguous uint8 view is passed by address (zero-copy ingest relies on it)
-        st = self._check(lib.swtpg_submit(self._h, link, unit.ctypes.data, unit.size), allow=(SWTPG_ERR_BUSY,))
-        return st == SWTPG_OK
+        if wait_us:
+            st = lib.swtpg_submit_wait(self._h, link, unit.ctypes.data, unit.size, wait_us)
+        else:
+            st = lib.swtpg_submit(self._h, link, unit.ctypes.data, unit.size)
+        return self._check(st, allow=(SWTPG_ERR_BUSY,)) == SWTPG_OK
 
     def register_buffer(self, buf: np.ndarray):
         """Zero-copy ingest: payloads submitted from inside `buf` (the latency buffer) are not copied by submit(); the copy
@@ -195,17 +205,42 @@ class TPGenerator:
     def unregister_buffer(self, buf: np.ndarray):
         self._check(lib.swtpg_unregister_buffer(self._h, buf.ctypes.data))
 
-    def flush(self):
-        self._check(lib.swtpg_flush(self._h))
+    def flush(self) -> bool:
+        """Dispatch everything submitted so far. False = every batch holds un-polled TPs (poll, then flush again)."""
+        return self._check(lib.swtpg_flush(self._h), allow=(SWTPG_ERR_BUSY,)) == SWTPG_OK
 
     def sync(self):
         self._check(lib.swtpg_sync(self._h))
 
-    def poll(self, cap: int = 1 << 16) -> np.ndarray:
+    def poll(self, cap: int = 1 << 16, wait_us: int = 0) -> np.ndarray:
         out = np.zeros(cap, dtype=F.TP_DTYPE)
         n = C.c_size_t(0)
-        self._check(lib.swtpg_poll(self._h, out.ctypes.data, cap, C.byref(n)))
+        if wait_us:
+            self._check(lib.swtpg_poll_wait(self._h, out.ctypes.data, cap, C.byref(n), wait_us))
+        else:
+            self._check(lib.swtpg_poll(self._h, out.ctypes.data, cap, C.byref(n)))
         return out[: n.value].copy()
+
+    def drain(self) -> np.ndarray:
+        """flush + sync + poll until nothing is left: every TP of everything submitted so far."""
+        got = []
+        while True:
+            done = self.flush()
+            self.sync()
+            while True:
+                part = self.poll()
+                got.append(part)
+                if part.size == 0 and self.stream_status()[2] == 0:
+                    break
+            if done and self.stream_status()[0] == 0:
+                break
+        return np.concatenate(got) if got else np.zeros(0, dtype=F.TP_DTYPE)
+
+    def stream_status(self):
+        """(units submitted but not dispatched, batches in flight, completed batches waiting for poll)"""
+        a, b, c = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0)
+        self._check(lib.swtpg_stream_status(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     # -- parity / monitoring -------------------------------------------------------------------------------------------------
     def dump_state(self, link: int) -> np.ndarray:
@@ -256,40 +291,5 @@ def merge_sorted(lists: Sequence[np.ndarray]) -> np.ndarray:
     return out
 
 
-# -- synthetic frames (include/swtpg_framegen.h) ------------------------------------------------------------------------------
-def gen_params(seed: int = 1, pulses_per_64_ticks: float = 0.02, **overrides) -> GenParams:
-    p = GenParams()
-    lib.swtpg_gen_default_params(C.byref(p), seed, pulses_per_64_ticks)
-    for k, v in overrides.items():
-        setattr(p, k, v)
-    return p
-
-
-def gen_wibeth_host(p: GenParams, n_links: int, n_units: int, link0: int = 0, unit0: int = 0, ts0: int = 1 << 40, n_threads: int = 8) -> np.ndarray:
-    out = np.zeros((n_links, n_units, F.WIBETH_FRAME_BYTES), dtype=np.uint8)
-    st = lib.swtpg_gen_wibeth_host(C.byref(p), link0, n_links, unit0, n_units, ts0, out.ctypes.data, n_threads)
-    if st != SWTPG_OK:
-        raise SwtpgError(st, "swtpg_gen_wibeth_host")
-    return out
-
-
-def gen_wib2_host(p: GenParams, n_links: int, n_units: int, link0: int = 0, unit0: int = 0, ts0: int = 1 << 40, adc_offset: int = 0,
-                  n_threads: int = 8) -> np.ndarray:
-    out = np.zeros((n_links, n_units, F.WIB2_SUPERCHUNK_BYTES), dtype=np.uint8)
-    st = lib.swtpg_gen_wib2_host(C.byref(p), link0, n_links, unit0, n_units, ts0, adc_offset, out.ctypes.data, n_threads)
-    if st != SWTPG_OK:
-        raise SwtpgError(st, "swtpg_gen_wib2_host")
-    return out
-
-
-def gen_wibeth_device(p: GenParams, d_ptr: int, n_links: int, n_units: int, link0: int = 0, unit0: int = 0, ts0: int = 1 << 40, stream: int = 0):
-    st = lib.swtpg_gen_wibeth_device(C.byref(p), link0, n_links, unit0, n_units, ts0, C.c_void_p(d_ptr), C.c_void_p(stream))
-    if st != SWTPG_OK:
-        raise SwtpgError(st, "swtpg_gen_wibeth_device")
-
-
-def gen_wib2_device(p: GenParams, d_ptr: int, n_links: int, n_units: int, link0: int = 0, unit0: int = 0, ts0: int = 1 << 40, adc_offset: int = 0,
-                    stream: int = 0):
-    st = lib.swtpg_gen_wib2_device(C.byref(p), link0, n_links, unit0, n_units, ts0, adc_offset, C.c_void_p(d_ptr), C.c_void_p(stream))
-    if st != SWTPG_OK:
-        raise SwtpgError(st, "swtpg_gen_wib2_device")
+# -- synthetic frames (include/swtpg_framegen.h): re-exported from their own module / library ---------------------------------
+from .framegen import GenParams, gen_params, gen_wib2_device, gen_wib2_host, gen_wibeth_device, gen_wibeth_host  # noqa: E402,F401

@@ -1,6 +1,6 @@
-// Host runtime behind include/swtpg.h: device buffers, kernel selection, the batch entry points and the pinned
-// multi-stream staging ring of the streaming path. Plain CUDA runtime; no torch, no CPU compute fallback.
-#include "../../include/swtpg.h"
+// Host runtime behind include/swtpg.h: device buffers, kernel selection and the batch entry points. The streaming path
+// (swtpg_submit ... swtpg_poll) lives in swtpg_stream.cu. Plain CUDA runtime; no torch, no CPU compute fallback.
+#include "swtpg_handle.h"
 #include "swtpg_kernels.cuh"
 
 #include <algorithm>
@@ -9,7 +9,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <deque>
 #include <memory>
 #include <mutex>
 #include <new>
@@ -19,132 +18,25 @@
 #include <vector>
 
 using namespace swtpg;
+using swtpg_internal::fail;
 
 // Layouts the ctypes binding (fdreadoutlibs_b200/_lib.py, frames.py) relies on.
 static_assert(sizeof(swtpg_tp) == 32, "swtpg_tp must stay 32 bytes (two 16-byte device stores)");
-static_assert(sizeof(swtpg_config) == 68, "swtpg_config layout changed: bump SWTPG_ABI_VERSION and the bindings");
+static_assert(sizeof(swtpg_config) == 72, "swtpg_config layout changed: bump SWTPG_ABI_VERSION and the bindings");
 static_assert(sizeof(swtpg_channel_state) == 48, "swtpg_channel_state layout changed");
 static_assert(sizeof(swtpg_counters) == 64, "swtpg_counters layout changed");
 
 namespace {
-
 thread_local std::string g_create_error;
-
-enum SlotState : int
+thread_local std::string g_error_copy;
+}
+void
+swtpg_internal::set_create_error(const char* msg)
 {
-  kFilling = 0,
-  kCopying = 1,  // H2D + kernel + count D2H enqueued
-  kFetching = 2, // TP D2H enqueued
-  kReady = 3     // TPs in h_tps, waiting for poll
-};
-
-struct Slot
-{
-  uint8_t* h_frames = nullptr; // pinned [n_links][max_units][unit_bytes]
-  uint8_t* d_frames = nullptr;
-  swtpg_tp* d_tps = nullptr;
-  swtpg_tp* h_tps = nullptr;   // pinned
-  unsigned* d_count = nullptr;
-  unsigned* h_count = nullptr; // pinned
-  uint32_t* h_nunits = nullptr; // pinned [n_links]
-  uint32_t* d_nunits = nullptr;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_count = nullptr, ev_tps = nullptr;
-  std::atomic<int> state{ kFilling };
-  std::atomic<uint64_t> batch{ 0 };      // batch index this slot currently holds
-  std::atomic<uint32_t> remaining{ 0 };  // units still missing before auto-dispatch
-  uint32_t n_ready = 0, n_taken = 0;
-  // zero-copy ingest (swtpg_register_buffer): where each unit of the batch lies if it was NOT copied into h_frames
-  std::vector<const uint8_t*> borrowed;    // [n_links][max_units], nullptr = staged copy
-  std::atomic<uint32_t> n_borrowed{ 0 };
-};
-
-} // namespace
-
-struct swtpg_handle
-{
-  swtpg_config cfg{};
-  uint32_t unit_bytes = 0, channels = 0, ticks = 0, groups_per_link = 0, n_groups = 0;
-  uint32_t tp_capacity = 0;
-  bool fast_simple = false, fast_fir = false, fast_rs = false, fast_rs_wib2 = false, fast_fir_any = false;
-  bool started = false;
-
-  cudaStream_t stream = nullptr; // batch path + all kernels (state is carried batch to batch: kernels are ordered)
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool timed = false;
-  cudaStream_t last_stream = nullptr;
-
-  uint32_t* d_state = nullptr;
-  uint32_t* d_flags = nullptr;
-  uint32_t* d_link_cursor = nullptr; // {claimed, finished}: dynamic link hand-out of the WIBEth kernel, self-resetting
-  swtpg_tp* d_tps = nullptr;
-  unsigned* d_count = nullptr;
-  unsigned* h_count = nullptr;
-  uint32_t* d_nunits = nullptr;
-  uint32_t* h_nunits = nullptr;
-  uint8_t* d_frames = nullptr;
-  size_t d_frames_bytes = 0;
-  int16_t* d_ped = nullptr;
-  int16_t* d_wav = nullptr;
-  size_t d_dump_elems = 0;
-  uint16_t* h_rs_factor = nullptr; // [n_links][channels] or null
-
-  // streaming path
-  std::vector<std::unique_ptr<Slot>> slots;
-  std::atomic<bool> slots_ready{ false };
-  std::unique_ptr<std::atomic<uint64_t>[]> submitted; // units per link
-  std::mutex dispatch_mu;
-  uint64_t next_dispatch = 0; // next batch index to dispatch (batches complete in order)
-  uint64_t next_poll = 0;     // next batch index to hand to poll
-
-  // host ranges registered for zero-copy ingest; link_range caches the last hit per link (touched by that link's thread only)
-  struct HostRange { uintptr_t lo = 0, hi = 0; };
-  std::vector<HostRange> ranges;
-  std::mutex ranges_mu;
-  std::unique_ptr<HostRange[]> link_range;
-  std::atomic<uint64_t> ranges_epoch{ 0 };
-  std::unique_ptr<uint64_t[]> link_range_epoch;
-
-  // bounce pipeline of swtpg_process_host for pageable sources: per worker two pinned buffers, a stream and events
-  struct Bounce
-  {
-    uint8_t* buf[2] = { nullptr, nullptr };
-    cudaEvent_t free_ev[2] = { nullptr, nullptr };
-    cudaEvent_t done = nullptr;
-    cudaStream_t stream = nullptr;
-  };
-  std::vector<Bounce> bounce;
-
-  swtpg_counters counters{};
-  std::atomic<uint64_t> submit_busy{ 0 };
-  mutable std::string last_error;
-};
+  g_create_error = msg;
+}
 
 namespace {
-
-#define SW_CUDA(h, call)                                                                                                          \
-  do {                                                                                                                            \
-    cudaError_t e_ = (call);                                                                                                      \
-    if (e_ != cudaSuccess) {                                                                                                      \
-      char buf_[512];                                                                                                             \
-      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);                    \
-      if (h)                                                                                                                      \
-        (h)->last_error = buf_;                                                                                                   \
-      else                                                                                                                        \
-        g_create_error = buf_;                                                                                                    \
-      return SWTPG_ERR_CUDA;                                                                                                      \
-    }                                                                                                                             \
-  } while (0)
-
-swtpg_status
-fail(swtpg_handle* h, swtpg_status s, const char* msg)
-{
-  if (h)
-    h->last_error = msg;
-  else
-    g_create_error = msg;
-  return s;
-}
 
 // ---- kernel launch table ------------------------------------------------------------------------------------------
 // Geometry of the WIBEth kernel: WARPS links per CTA, per-warp ring of NSTAGE stages of CHUNK ticks (112 B each).
@@ -157,7 +49,11 @@ struct Geo
 // Default: one link-warp per CTA with a ring of 2 stages x 32 ticks (7 KB) + 2.5 KB hit staging. Measured best of the
 // geometries below on B200 (profiles/r01_geometry_sweep.txt): the kernel is issue-bound, so deeper rings do not help, and
 // single-warp CTAs let the block scheduler spread the 20 resident warps per SM evenly over the four sub-partitions.
-using GeoDefault = Geo<1, 2, 32>;
+#ifndef SWTPG_GEO_STAGES
+#define SWTPG_GEO_STAGES 2
+#define SWTPG_GEO_CHUNK 32
+#endif
+using GeoDefault = Geo<1, SWTPG_GEO_STAGES, SWTPG_GEO_CHUNK>;
 
 template<class Algo, bool DUMP, class G>
 cudaError_t
@@ -364,7 +260,7 @@ make_params(const swtpg_handle* h, const void* d_frames, const uint32_t* d_nunit
     kp.taps[i] = h->cfg.fir_taps[i];
   kp.wib2_adc_offset = h->cfg.wib2_adc_offset;
   static const bool force_exact = [] { const char* e = getenv("SWTPG_FIR_FORCE_EXACT"); return e && atoi(e) != 0; }();
-  kp.debug_flags = force_exact ? 1u : 0u;
+  kp.debug_flags = (force_exact || h->fir_force_exact) ? 1u : 0u;
   return kp;
 }
 
@@ -389,6 +285,31 @@ reset_state(swtpg_handle* h)
   SW_CUDA(h, cudaMemsetAsync(h->d_flags, 0, size_t(h->n_groups) * 4, h->stream));
   SW_CUDA(h, cudaMemsetAsync(h->d_link_cursor, 0, 2 * sizeof(uint32_t), h->stream));
   SW_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SWTPG_OK;
+}
+
+// Rewrites the SV_RS_FACTOR rows of links [link0, link0 + n) from h->h_rs_factor (or the configured factor): ONE strided
+// asynchronous copy on the compute stream, i.e. ordered before every kernel launched after this call and after every kernel
+// launched before it. The source is pageable, so the runtime has staged it when the call returns.
+swtpg_status
+upload_rs_factor_rows(swtpg_handle* h, uint32_t link0, uint32_t n)
+{
+  const uint32_t g0 = link0 * h->groups_per_link, ng = n * h->groups_per_link;
+  std::vector<uint32_t> rows(size_t(ng) * 32);
+  for (uint32_t g = 0; g < ng; ++g) {
+    const uint32_t link = (g0 + g) / h->groups_per_link, sub = (g0 + g) % h->groups_per_link;
+    for (uint32_t lane = 0; lane < 32; ++lane) {
+      uint32_t lo = h->cfg.rs_memory_factor, hi = lo;
+      if (h->h_rs_factor) {
+        const uint16_t* f = h->h_rs_factor + size_t(link) * h->channels + sub * 64 + 2 * lane;
+        lo = f[0];
+        hi = f[1];
+      }
+      rows[size_t(g) * 32 + lane] = lo | (hi << 16);
+    }
+  }
+  SW_CUDA(h, cudaMemcpy2DAsync(h->d_state + size_t(g0) * kStateWordsPerGroup + SV_RS_FACTOR * 32, size_t(kStateWordsPerGroup) * 4, rows.data(), 128,
+                               128, ng, cudaMemcpyHostToDevice, h->stream));
   return SWTPG_OK;
 }
 
@@ -417,8 +338,12 @@ enqueue_batch(swtpg_handle* h, const void* d_frames, const uint32_t* n_units, ui
   const uint32_t* d_nu = nullptr;
   uint64_t units = 0;
   if (n_units) {
-    memcpy(h->h_nunits, n_units, size_t(h->cfg.n_links) * 4);
-    SW_CUDA(h, cudaMemcpyAsync(h->d_nunits, h->h_nunits, size_t(h->cfg.n_links) * 4, cudaMemcpyHostToDevice, s));
+    // pinned source, double-buffered: the copy that last read this buffer (two calls ago) must have finished
+    const uint32_t turn = h->nunits_turn++ & 1u;
+    SW_CUDA(h, cudaEventSynchronize(h->ev_nunits[turn]));
+    memcpy(h->h_nunits[turn], n_units, size_t(h->cfg.n_links) * 4);
+    SW_CUDA(h, cudaMemcpyAsync(h->d_nunits, h->h_nunits[turn], size_t(h->cfg.n_links) * 4, cudaMemcpyHostToDevice, s));
+    SW_CUDA(h, cudaEventRecord(h->ev_nunits[turn], s));
     d_nu = h->d_nunits;
     for (uint32_t l = 0; l < h->cfg.n_links; ++l)
       units += n_units[l];
@@ -462,135 +387,15 @@ fetch(swtpg_handle* h, cudaStream_t s, swtpg_tp* out, size_t cap, size_t* n_out)
   return SWTPG_OK;
 }
 
-void
-free_slot(Slot& s)
-{
-  if (s.h_frames) cudaFreeHost(s.h_frames);
-  if (s.d_frames) cudaFree(s.d_frames);
-  if (s.d_tps) cudaFree(s.d_tps);
-  if (s.h_tps) cudaFreeHost(s.h_tps);
-  if (s.d_count) cudaFree(s.d_count);
-  if (s.h_count) cudaFreeHost(s.h_count);
-  if (s.h_nunits) cudaFreeHost(s.h_nunits);
-  if (s.d_nunits) cudaFree(s.d_nunits);
-  if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
-  if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
-  if (s.ev_count) cudaEventDestroy(s.ev_count);
-  if (s.ev_tps) cudaEventDestroy(s.ev_tps);
-  if (s.stream) cudaStreamDestroy(s.stream);
-}
-
-// Streaming ring is allocated on first swtpg_submit (the batch entry points never need it).
-swtpg_status
-ensure_slots(swtpg_handle* h)
-{
-  if (h->slots_ready.load(std::memory_order_acquire))
-    return SWTPG_OK;
-  const uint32_t n = h->cfg.n_slots;
-  const size_t fbytes = size_t(h->cfg.n_links) * h->cfg.max_units * h->unit_bytes;
-  std::vector<std::unique_ptr<Slot>> slots;
-  for (uint32_t i = 0; i < n; ++i) {
-    auto s = std::make_unique<Slot>();
-    SW_CUDA(h, cudaMallocHost(&s->h_frames, fbytes));
-    SW_CUDA(h, cudaMalloc(&s->d_frames, fbytes));
-    SW_CUDA(h, cudaMalloc(&s->d_tps, size_t(h->tp_capacity) * sizeof(swtpg_tp)));
-    SW_CUDA(h, cudaMallocHost(&s->h_tps, size_t(h->tp_capacity) * sizeof(swtpg_tp)));
-    SW_CUDA(h, cudaMalloc(&s->d_count, sizeof(unsigned)));
-    SW_CUDA(h, cudaMallocHost(&s->h_count, sizeof(unsigned)));
-    SW_CUDA(h, cudaMallocHost(&s->h_nunits, size_t(h->cfg.n_links) * 4));
-    SW_CUDA(h, cudaMalloc(&s->d_nunits, size_t(h->cfg.n_links) * 4));
-    SW_CUDA(h, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    SW_CUDA(h, cudaEventCreateWithFlags(&s->ev_h2d, cudaEventDisableTiming));
-    SW_CUDA(h, cudaEventCreateWithFlags(&s->ev_kernel, cudaEventDisableTiming));
-    SW_CUDA(h, cudaEventCreateWithFlags(&s->ev_count, cudaEventDisableTiming));
-    SW_CUDA(h, cudaEventCreateWithFlags(&s->ev_tps, cudaEventDisableTiming));
-    s->borrowed.assign(size_t(h->cfg.n_links) * h->cfg.max_units, nullptr);
-    s->batch.store(i);
-    s->remaining.store(h->cfg.n_links * h->cfg.max_units);
-    s->state.store(kFilling);
-    slots.push_back(std::move(s));
-  }
-  h->slots = std::move(slots);
-  h->slots_ready.store(true, std::memory_order_release);
-  return SWTPG_OK;
-}
-
-// Dispatch batch `b` (its slot is full or being flushed). Caller holds dispatch_mu. n_units == nullptr: full batch.
-swtpg_status
-dispatch_slot(swtpg_handle* h, Slot& s, const uint32_t* n_units)
-{
-  const uint32_t stride = h->cfg.max_units;
-  const size_t fbytes = size_t(h->cfg.n_links) * stride * h->unit_bytes;
-  const uint32_t* d_nu = nullptr;
-  uint64_t units = uint64_t(stride) * h->cfg.n_links;
-  // H2D on the slot's own stream (overlaps the previous batch's kernel), kernel on the handle's compute stream
-  // (state is carried: kernels must run in batch order), TP count + TPs back on the slot's stream.
-  const bool any_borrowed = s.n_borrowed.load(std::memory_order_acquire) != 0;
-  if (n_units) {
-    units = 0;
-    for (uint32_t l = 0; l < h->cfg.n_links; ++l) {
-      s.h_nunits[l] = n_units[l];
-      units += n_units[l];
-    }
-    SW_CUDA(h, cudaMemcpyAsync(s.d_nunits, s.h_nunits, size_t(h->cfg.n_links) * 4, cudaMemcpyHostToDevice, s.stream));
-    d_nu = s.d_nunits;
-  }
-  if (any_borrowed) {
-    // Zero-copy ingest: the copy engine reads borrowed units where they lie (registered host memory), one async copy per
-    // contiguous run — a link's superchunk is one run unless the latency buffer wrapped inside it; staged units come from
-    // the slot's pinned buffer as before.
-    for (uint32_t l = 0; l < h->cfg.n_links; ++l) {
-      const uint32_t nu = n_units ? n_units[l] : stride;
-      const size_t row = size_t(l) * stride;
-      uint32_t u = 0;
-      while (u < nu) {
-        const uint8_t* src = s.borrowed[row + u];
-        const bool staged = src == nullptr;
-        if (staged)
-          src = s.h_frames + (row + u) * h->unit_bytes;
-        uint32_t v = u + 1;
-        while (v < nu) {
-          const uint8_t* nxt = s.borrowed[row + v];
-          if (staged ? nxt != nullptr : nxt != src + size_t(v - u) * h->unit_bytes)
-            break;
-          ++v;
-        }
-        SW_CUDA(h, cudaMemcpyAsync(s.d_frames + (row + u) * h->unit_bytes, src, size_t(v - u) * h->unit_bytes, cudaMemcpyHostToDevice,
-                                   s.stream));
-        u = v;
-      }
-    }
-    h->counters.h2d_bytes += units * h->unit_bytes;
-  } else if (n_units) {
-    // ragged: copy each link's valid prefix only
-    for (uint32_t l = 0; l < h->cfg.n_links; ++l)
-      if (n_units[l])
-        SW_CUDA(h, cudaMemcpyAsync(s.d_frames + size_t(l) * stride * h->unit_bytes, s.h_frames + size_t(l) * stride * h->unit_bytes,
-                                   size_t(n_units[l]) * h->unit_bytes, cudaMemcpyHostToDevice, s.stream));
-    h->counters.h2d_bytes += units * h->unit_bytes;
-  } else {
-    SW_CUDA(h, cudaMemcpyAsync(s.d_frames, s.h_frames, fbytes, cudaMemcpyHostToDevice, s.stream));
-    h->counters.h2d_bytes += fbytes;
-  }
-  SW_CUDA(h, cudaMemsetAsync(s.d_count, 0, sizeof(unsigned), s.stream));
-  SW_CUDA(h, cudaEventRecord(s.ev_h2d, s.stream));
-  SW_CUDA(h, cudaStreamWaitEvent(h->stream, s.ev_h2d, 0));
-  KernelParams kp = make_params(h, s.d_frames, d_nu, stride, s.d_tps, s.d_count, nullptr, nullptr);
-  SW_CUDA(h, launch<false>(h, kp, h->stream));
-  SW_CUDA(h, cudaEventRecord(s.ev_kernel, h->stream));
-  SW_CUDA(h, cudaStreamWaitEvent(s.stream, s.ev_kernel, 0));
-  SW_CUDA(h, cudaMemcpyAsync(s.h_count, s.d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, s.stream));
-  SW_CUDA(h, cudaEventRecord(s.ev_count, s.stream));
-  s.n_ready = s.n_taken = 0;
-  s.state.store(kCopying, std::memory_order_release);
-  h->counters.units_processed += units;
-  h->counters.samples_processed += units * h->channels * h->ticks;
-  h->counters.batches++;
-  h->next_dispatch++;
-  return SWTPG_OK;
-}
-
 } // namespace
+
+cudaError_t
+swtpg_internal::launch_batch_kernel(swtpg_handle* h, const void* d_frames, const uint32_t* d_nunits, uint32_t units_stride, swtpg_tp* d_tps,
+                                    unsigned* d_count, cudaStream_t s)
+{
+  const KernelParams kp = make_params(h, d_frames, d_nunits, units_stride, d_tps, d_count, nullptr, nullptr);
+  return launch<false>(h, kp, s);
+}
 
 extern "C" {
 
@@ -618,7 +423,12 @@ swtpg_status_string(swtpg_status s)
 const char*
 swtpg_last_error(const swtpg_handle* h)
 {
-  return h ? h->last_error.c_str() : g_create_error.c_str();
+  if (!h)
+    return g_create_error.c_str();
+  swtpg_handle* hh = const_cast<swtpg_handle*>(h);
+  std::lock_guard<std::mutex> lk(hh->err_mu);
+  g_error_copy = hh->last_error; // per-thread copy: another thread may fail (and rewrite the text) at any time
+  return g_error_copy.c_str();
 }
 
 int
@@ -635,26 +445,6 @@ swtpg_device_available(void)
       return 1;
   }
   return 0;
-}
-
-int
-swtpg_firwin_int(int n, double cutoff, int multiplier, int16_t* taps)
-{ // src/wib2/tpg/DesignFIR.cpp:20-68 (host, double precision; runs once per start in the reference)
-  if (n < 2 || n > 64 || !taps)
-    return -1;
-  const double pi = 3.14159265358979323846;
-  std::vector<double> v(size_t(n), 0.0);
-  double sum = 0;
-  const int alpha = n / 2;
-  for (int m = 0; m < n; ++m) {
-    const double w = 0.54 - 0.46 * std::cos(2.0 * pi * m / (n - 1));
-    const double x = cutoff * (m - alpha);
-    v[size_t(m)] = w * (x == 0 ? 1.0 : std::sin(pi * x) / (pi * x));
-    sum += v[size_t(m)];
-  }
-  for (int m = 0; m < n; ++m)
-    taps[m] = int16_t(std::round(multiplier * (v[size_t(m)] / sum)));
-  return n;
 }
 
 swtpg_status
@@ -736,7 +526,13 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
   if (wib2 && cfg->algorithm == SWTPG_ALGO_ABS_RS && cfg->threshold >= 1) {
     const uint32_t e = h->cfg.tap_exponent, mult = 1u << e;
     const uint64_t sigma_max = (1u << 15) / (uint64_t(mult) * cfg->threshold);
-    h->fast_rs_wib2 = e >= 1 && e <= 10 && (sigma_max + 3) * cfg->threshold < 65536 && getenv("SWTPG_FORCE_SCALAR") == nullptr;
+    // thresholds sigma * threshold are compared by the bf16 comparator (valid up to 32640) and built by a packed multiply-add
+    // (no carry between the halves while (sigmaMax + 3) * threshold < 2^16); outside that range every group takes the
+    // exact-threshold tier (plain signed compares on the 64-bit-lane product, like the reference's _mm256_cmpgt_epi16)
+    const bool packed_ok = e >= 1 && e <= 10 && getenv("SWTPG_FORCE_SCALAR") == nullptr;
+    const bool range_ok = (sigma_max + 3) * cfg->threshold < 65536 && sigma_max * cfg->threshold <= 32640;
+    h->fast_rs_wib2 = packed_ok;
+    h->fir_force_exact = packed_ok && !range_ok;
   }
   // Packed FIR fast path validity (see PackedFirIqr): binomial taps, and (sigmaMax + 3) * multiplier * threshold < 2^16
   {
@@ -746,10 +542,18 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
       taps_ok &= h->cfg.fir_taps[i] == kBinomial[i];
     const uint32_t e = h->cfg.tap_exponent, mult = 1u << e;
     const uint64_t sigma_max = (1u << 15) / (mult * 5u);
-    const bool range_ok = cfg->algorithm == SWTPG_ALGO_FIR_IQR && e >= 1 && e <= 10 &&
-                          (sigma_max + 3) * mult * uint64_t(cfg->threshold) < 65536 && getenv("SWTPG_FORCE_SCALAR") == nullptr;
-    h->fast_fir = range_ok && taps_ok;      // binomial cascade
-    h->fast_fir_any = range_ok && !taps_ok; // any other taps[0..6]: packed multiply-add chain (PackedFirIqrAnyTaps)
+    // The packed policies build sigma * multiplier * threshold with one multiply-add (no carry between the halves while
+    // (sigmaMax + 3) * K < 2^16) and compare through the bf16 comparator, which orders like signed int16 only up to 32640:
+    // K = multiplier * threshold with sigmaMax * K <= 32640 (threshold <= 5 at the reference's exponent 6). Beyond that the
+    // reference's _mm256_cmpgt_epi16 sees the product as a NEGATIVE int16 once a channel's IQR is large enough, so such
+    // configurations run the same packed trackers and filter with the exact-threshold tier forced on for every group.
+    const uint64_t K = uint64_t(mult) * cfg->threshold;
+    const bool packed_ok = cfg->algorithm == SWTPG_ALGO_FIR_IQR && e >= 1 && e <= 10 && getenv("SWTPG_FORCE_SCALAR") == nullptr;
+    const bool range_ok = (sigma_max + 3) * K < 65536 && sigma_max * K <= 32640;
+    h->fast_fir = packed_ok && taps_ok;      // binomial cascade
+    h->fast_fir_any = packed_ok && !taps_ok; // any other taps[0..6]: packed multiply-add chain (PackedFirIqrAnyTaps)
+    if (packed_ok && !range_ok)
+      h->fir_force_exact = true;
   }
 
   swtpg_handle* hp = h.get();
@@ -764,12 +568,10 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
   SW_CUDA(hp, cudaMalloc(&h->d_count, sizeof(unsigned)));
   SW_CUDA(hp, cudaMallocHost(&h->h_count, sizeof(unsigned)));
   SW_CUDA(hp, cudaMalloc(&h->d_nunits, size_t(cfg->n_links) * 4));
-  SW_CUDA(hp, cudaMallocHost(&h->h_nunits, size_t(cfg->n_links) * 4));
-  h->submitted.reset(new std::atomic<uint64_t>[cfg->n_links]);
-  h->link_range.reset(new swtpg_handle::HostRange[cfg->n_links]);
-  h->link_range_epoch.reset(new uint64_t[cfg->n_links]());
-  for (uint32_t l = 0; l < cfg->n_links; ++l)
-    h->submitted[l].store(0);
+  for (int i = 0; i < 2; ++i) {
+    SW_CUDA(hp, cudaMallocHost(&h->h_nunits[i], size_t(cfg->n_links) * 4));
+    SW_CUDA(hp, cudaEventCreateWithFlags(&h->ev_nunits[i], cudaEventDisableTiming));
+  }
   *out = h.release();
   return SWTPG_OK;
 }
@@ -780,12 +582,8 @@ swtpg_destroy(swtpg_handle* h)
   if (!h)
     return;
   cudaSetDevice(h->cfg.device);
+  swtpg_internal::engine_destroy(h); // joins the streaming threads, unregisters latency buffers
   cudaDeviceSynchronize();
-  for (const auto& r : h->ranges)
-    if (cudaHostUnregister(reinterpret_cast<void*>(r.lo)) != cudaSuccess)
-      cudaGetLastError();
-  for (auto& s : h->slots)
-    free_slot(*s);
   for (auto& b : h->bounce) {
     for (int i = 0; i < 2; ++i) {
       if (b.buf[i]) cudaFreeHost(b.buf[i]);
@@ -801,7 +599,10 @@ swtpg_destroy(swtpg_handle* h)
   if (h->d_count) cudaFree(h->d_count);
   if (h->h_count) cudaFreeHost(h->h_count);
   if (h->d_nunits) cudaFree(h->d_nunits);
-  if (h->h_nunits) cudaFreeHost(h->h_nunits);
+  for (int i = 0; i < 2; ++i) {
+    if (h->h_nunits[i]) cudaFreeHost(h->h_nunits[i]);
+    if (h->ev_nunits[i]) cudaEventDestroy(h->ev_nunits[i]);
+  }
   if (h->d_frames) cudaFree(h->d_frames);
   if (h->d_ped) cudaFree(h->d_ped);
   if (h->d_wav) cudaFree(h->d_wav);
@@ -821,18 +622,10 @@ swtpg_start(swtpg_handle* h)
   swtpg_status s = reset_state(h);
   if (s != SWTPG_OK)
     return s;
-  for (uint32_t l = 0; l < h->cfg.n_links; ++l)
-    h->submitted[l].store(0);
-  for (size_t i = 0; i < h->slots.size(); ++i) {
-    Slot& sl = *h->slots[i];
-    sl.batch.store(i);
-    sl.remaining.store(h->cfg.n_links * h->cfg.max_units);
-    sl.n_borrowed.store(0);
-    sl.state.store(kFilling);
-  }
-  h->next_dispatch = h->next_poll = 0;
-  h->counters = swtpg_counters{};
-  h->submit_busy.store(0);
+  s = swtpg_internal::engine_reset(h); // streaming path: idle, rings empty, undelivered TPs of the previous run dropped
+  if (s != SWTPG_OK)
+    return s;
+  h->counters.reset();
   h->timed = false;
   h->started = true;
   return SWTPG_OK;
@@ -860,24 +653,31 @@ swtpg_set_rs_memory_factor(swtpg_handle* h, const uint16_t* by_link_channel)
     h->h_rs_factor = new uint16_t[n];
     memcpy(h->h_rs_factor, by_link_channel, n * sizeof(uint16_t));
   }
-  if (h->started) { // only the factor row changes; carried state is preserved
+  if (h->started) { // only the factor rows change; carried state is preserved
     SW_CUDA(h, cudaSetDevice(h->cfg.device));
-    std::vector<uint32_t> row(32);
-    for (uint32_t g = 0; g < h->n_groups; ++g) {
-      const uint32_t link = g / h->groups_per_link, sub = g % h->groups_per_link;
-      for (uint32_t lane = 0; lane < 32; ++lane) {
-        uint32_t lo = h->cfg.rs_memory_factor, hi = lo;
-        if (h->h_rs_factor) {
-          const uint16_t* f = h->h_rs_factor + size_t(link) * h->channels + sub * 64 + 2 * lane;
-          lo = f[0];
-          hi = f[1];
-        }
-        row[lane] = lo | (hi << 16);
-      }
-      SW_CUDA(h, cudaMemcpy(h->d_state + size_t(g) * kStateWordsPerGroup + SV_RS_FACTOR * 32, row.data(), 128, cudaMemcpyHostToDevice));
-    }
+    return upload_rs_factor_rows(h, 0, h->cfg.n_links);
   }
   return SWTPG_OK;
+}
+
+swtpg_status
+swtpg_set_link_rs_memory_factor(swtpg_handle* h, uint32_t link, const uint16_t* by_channel)
+{
+  if (!h || !by_channel || link >= h->cfg.n_links)
+    return SWTPG_ERR_INVALID_ARG;
+  {
+    std::lock_guard<std::mutex> lk(h->engine_mu); // several links' threads may arrive here with their first frames
+    if (!h->h_rs_factor) {
+      const size_t n = size_t(h->cfg.n_links) * h->channels;
+      h->h_rs_factor = new uint16_t[n];
+      std::fill(h->h_rs_factor, h->h_rs_factor + n, h->cfg.rs_memory_factor);
+    }
+    memcpy(h->h_rs_factor + size_t(link) * h->channels, by_channel, size_t(h->channels) * sizeof(uint16_t));
+  }
+  if (!h->started)
+    return SWTPG_OK; // swtpg_start uploads the table
+  SW_CUDA(h, cudaSetDevice(h->cfg.device));
+  return upload_rs_factor_rows(h, link, 1);
 }
 
 swtpg_status
@@ -917,7 +717,7 @@ swtpg_last_kernel_ms(swtpg_handle* h)
   return double(ms);
 }
 
-// Copy of one payload into pinned memory (csrc/stage_copy.cpp: non-temporal stores where the CPU has AVX2).
+// Copy of one payload into pinned memory (csrc/swtpg_hostutil.cpp: non-temporal stores where the CPU has AVX2).
 extern "C" void swtpg_stage_copy(void* dst, const void* src, size_t bytes);
 
 // Host-to-device copy of a PAGEABLE source. cudaMemcpyAsync would stage it through the driver's own bounce buffer on one
@@ -1056,230 +856,16 @@ swtpg_process_host_debug(swtpg_handle* h, const void* frames, const uint32_t* n_
   return process_host_impl(h, frames, n_units, units_stride, out, cap, n_out, pedestal_out, waveform_out, true);
 }
 
-// ---- streaming path ---------------------------------------------------------------------------------------------------
-// Is [unit, unit + bytes) inside a range registered with swtpg_register_buffer? Lock-free on the hot path: every link's
-// producer thread keeps the last range it hit (a link's payloads come from one latency buffer).
-static bool
-is_registered(swtpg_handle* h, uint32_t link, const void* unit, size_t bytes)
-{
-  const uint64_t epoch = h->ranges_epoch.load(std::memory_order_acquire);
-  if (epoch == 0)
-    return false; // nothing was ever registered
-  const uintptr_t a = reinterpret_cast<uintptr_t>(unit);
-  swtpg_handle::HostRange& c = h->link_range[link];
-  if (h->link_range_epoch[link] == epoch) {
-    if (a >= c.lo && a + bytes <= c.hi)
-      return true;
-    if (c.hi == 0)
-      return false; // cached miss: this link's payloads are not in registered memory
-  }
-  std::lock_guard<std::mutex> lk(h->ranges_mu); // first payload of the link, or the set of ranges changed, or another range
-  c = swtpg_handle::HostRange{};
-  for (const auto& r : h->ranges)
-    if (a >= r.lo && a + bytes <= r.hi)
-      c = r;
-  h->link_range_epoch[link] = h->ranges_epoch.load(std::memory_order_relaxed);
-  return c.hi != 0;
-}
-
-swtpg_status
-swtpg_submit(swtpg_handle* h, uint32_t link, const void* unit, size_t bytes)
-{
-  if (!h || !unit)
-    return SWTPG_ERR_INVALID_ARG;
-  if (!h->started)
-    return fail(h, SWTPG_ERR_STATE, "swtpg_start has not been called");
-  if (link >= h->cfg.n_links || bytes != h->unit_bytes)
-    return fail(h, SWTPG_ERR_INVALID_ARG, "bad link index or unit size");
-  if (!h->slots_ready.load(std::memory_order_acquire)) {
-    std::lock_guard<std::mutex> lk(h->dispatch_mu);
-    SW_CUDA(h, cudaSetDevice(h->cfg.device));
-    swtpg_status s = ensure_slots(h);
-    if (s != SWTPG_OK)
-      return s;
-  }
-  const uint64_t seq = h->submitted[link].load(std::memory_order_relaxed); // one producer thread per link
-  const uint64_t batch = seq / h->cfg.max_units;
-  const uint32_t u = uint32_t(seq % h->cfg.max_units);
-  Slot& s = *h->slots[batch % h->slots.size()];
-  if (s.batch.load(std::memory_order_acquire) != batch || s.state.load(std::memory_order_acquire) != kFilling) {
-    h->submit_busy.fetch_add(1, std::memory_order_relaxed);
-    return SWTPG_ERR_BUSY; // ring full: the caller drops or retries, like a failed try_send
-  }
-  const size_t idx = size_t(link) * h->cfg.max_units + u;
-  if (is_registered(h, link, unit, bytes)) { // zero-copy: the batch's H2D reads the unit where it lies
-    s.borrowed[idx] = static_cast<const uint8_t*>(unit);
-    s.n_borrowed.fetch_add(1, std::memory_order_relaxed);
-  } else {
-    s.borrowed[idx] = nullptr;
-    swtpg_stage_copy(s.h_frames + idx * h->unit_bytes, unit, bytes);
-  }
-  h->submitted[link].store(seq + 1, std::memory_order_release);
-  if (s.remaining.fetch_sub(1, std::memory_order_acq_rel) == 1) { // this unit completed the batch
-    std::lock_guard<std::mutex> lk(h->dispatch_mu);
-    SW_CUDA(h, cudaSetDevice(h->cfg.device));
-    return dispatch_slot(h, s, nullptr);
-  }
-  return SWTPG_OK;
-}
-
-swtpg_status
-swtpg_register_buffer(swtpg_handle* h, void* base, size_t bytes)
-{
-  if (!h || !base || bytes == 0)
-    return SWTPG_ERR_INVALID_ARG;
-  SW_CUDA(h, cudaSetDevice(h->cfg.device));
-  cudaError_t e = cudaHostRegister(base, bytes, cudaHostRegisterPortable);
-  if (e == cudaErrorHostMemoryAlreadyRegistered)
-    cudaGetLastError(); // e.g. two handles (GPUs) sharing one latency buffer: fine, it is pinned
-  else
-    SW_CUDA(h, e);
-  std::lock_guard<std::mutex> lk(h->ranges_mu);
-  const uintptr_t lo = reinterpret_cast<uintptr_t>(base);
-  h->ranges.push_back({ lo, lo + bytes });
-  h->ranges_epoch.fetch_add(1, std::memory_order_release);
-  return SWTPG_OK;
-}
-
-swtpg_status
-swtpg_unregister_buffer(swtpg_handle* h, void* base)
-{
-  if (!h || !base)
-    return SWTPG_ERR_INVALID_ARG;
-  swtpg_status st = swtpg_sync(h); // no copy engine may still be reading from it
-  if (st != SWTPG_OK)
-    return st;
-  {
-    std::lock_guard<std::mutex> lk(h->ranges_mu);
-    const uintptr_t lo = reinterpret_cast<uintptr_t>(base);
-    auto it = std::find_if(h->ranges.begin(), h->ranges.end(), [lo](const swtpg_handle::HostRange& r) { return r.lo == lo; });
-    if (it == h->ranges.end())
-      return fail(h, SWTPG_ERR_INVALID_ARG, "buffer was not registered with this handle");
-    h->ranges.erase(it);
-    h->ranges_epoch.fetch_add(1, std::memory_order_release);
-  }
-  cudaError_t e = cudaHostUnregister(base);
-  if (e != cudaSuccess)
-    cudaGetLastError(); // registered by another handle first, or already gone
-  return SWTPG_OK;
-}
-
-swtpg_status
-swtpg_flush(swtpg_handle* h)
-{
-  if (!h)
-    return SWTPG_ERR_INVALID_ARG;
-  if (!h->started)
-    return fail(h, SWTPG_ERR_STATE, "swtpg_start has not been called");
-  if (!h->slots_ready.load(std::memory_order_acquire))
-    return SWTPG_OK;
-  std::lock_guard<std::mutex> lk(h->dispatch_mu);
-  SW_CUDA(h, cudaSetDevice(h->cfg.device));
-  // Must not race with swtpg_submit. Closes the oldest partially filled batch (and any later one that links running
-  // ahead already started), then realigns every link to the next batch boundary.
-  for (;;) {
-    const uint64_t b = h->next_dispatch;
-    Slot& s = *h->slots[b % h->slots.size()];
-    if (s.batch.load() != b || s.state.load() != kFilling)
-      break;
-    std::vector<uint32_t> nu(h->cfg.n_links);
-    uint64_t total = 0;
-    for (uint32_t l = 0; l < h->cfg.n_links; ++l) {
-      const uint64_t seq = h->submitted[l].load();
-      const uint64_t lo = b * h->cfg.max_units;
-      nu[l] = seq <= lo ? 0u : uint32_t(std::min<uint64_t>(seq - lo, h->cfg.max_units));
-      total += nu[l];
-    }
-    if (total == 0)
-      break;
-    for (uint32_t l = 0; l < h->cfg.n_links; ++l)
-      if (h->submitted[l].load() < (b + 1) * h->cfg.max_units)
-        h->submitted[l].store((b + 1) * h->cfg.max_units);
-    swtpg_status st = dispatch_slot(h, s, nu.data());
-    if (st != SWTPG_OK)
-      return st;
-  }
-  return SWTPG_OK;
-}
-
-swtpg_status
-swtpg_poll(swtpg_handle* h, swtpg_tp* out, size_t cap, size_t* n_out)
-{
-  if (n_out)
-    *n_out = 0;
-  if (!h || (!out && cap))
-    return SWTPG_ERR_INVALID_ARG;
-  if (!h->slots_ready.load(std::memory_order_acquire))
-    return SWTPG_OK;
-  std::lock_guard<std::mutex> lk(h->dispatch_mu);
-  SW_CUDA(h, cudaSetDevice(h->cfg.device));
-  size_t n = 0;
-  swtpg_status ret = SWTPG_OK;
-  for (;;) {
-    Slot& s = *h->slots[h->next_poll % h->slots.size()];
-    if (s.batch.load() != h->next_poll)
-      break;
-    int st = s.state.load(std::memory_order_acquire);
-    if (st == kCopying) {
-      if (cudaEventQuery(s.ev_count) != cudaSuccess) {
-        cudaGetLastError();
-        break;
-      }
-      const unsigned found = *s.h_count;
-      const unsigned stored = std::min<unsigned>(found, h->tp_capacity);
-      h->counters.tps_emitted += found;
-      if (found > stored) {
-        h->counters.tps_dropped_overflow += found - stored;
-        ret = SWTPG_ERR_OVERFLOW;
-        h->last_error = "device TP buffer overflow: raise swtpg_config.tp_capacity";
-      }
-      s.n_ready = stored;
-      s.n_taken = 0;
-      if (stored)
-        SW_CUDA(h, cudaMemcpyAsync(s.h_tps, s.d_tps, size_t(stored) * sizeof(swtpg_tp), cudaMemcpyDeviceToHost, s.stream));
-      SW_CUDA(h, cudaEventRecord(s.ev_tps, s.stream));
-      h->counters.d2h_bytes += size_t(stored) * sizeof(swtpg_tp) + sizeof(unsigned);
-      s.state.store(kFetching);
-      st = kFetching;
-    }
-    if (st == kFetching) {
-      if (cudaEventQuery(s.ev_tps) != cudaSuccess) {
-        cudaGetLastError();
-        break;
-      }
-      s.state.store(kReady);
-      st = kReady;
-    }
-    if (st != kReady)
-      break;
-    const uint32_t take = uint32_t(std::min<size_t>(cap - n, s.n_ready - s.n_taken));
-    if (take)
-      memcpy(out + n, s.h_tps + s.n_taken, size_t(take) * sizeof(swtpg_tp));
-    n += take;
-    s.n_taken += take;
-    if (s.n_taken < s.n_ready)
-      break; // caller's buffer is full; the rest comes with the next poll
-    // recycle the slot for batch next_poll + n_slots
-    s.remaining.store(h->cfg.n_links * h->cfg.max_units);
-    s.n_borrowed.store(0, std::memory_order_relaxed);
-    s.batch.store(h->next_poll + h->slots.size(), std::memory_order_release);
-    s.state.store(kFilling, std::memory_order_release);
-    h->next_poll++;
-  }
-  if (n_out)
-    *n_out = n;
-  return ret;
-}
-
 swtpg_status
 swtpg_sync(swtpg_handle* h)
 {
   if (!h)
     return SWTPG_ERR_INVALID_ARG;
   SW_CUDA(h, cudaSetDevice(h->cfg.device));
+  swtpg_status s = swtpg_internal::engine_quiesce(h); // streaming path: every dispatched batch has delivered its TPs to the ready queue
+  if (s != SWTPG_OK)
+    return s;
   SW_CUDA(h, cudaStreamSynchronize(h->stream));
-  for (auto& s : h->slots)
-    SW_CUDA(h, cudaStreamSynchronize(s->stream));
   if (h->last_stream && h->last_stream != h->stream)
     SW_CUDA(h, cudaStreamSynchronize(h->last_stream));
   return SWTPG_OK;
@@ -1333,8 +919,14 @@ swtpg_get_counters(swtpg_handle* h, swtpg_counters* out)
 {
   if (!h || !out)
     return SWTPG_ERR_INVALID_ARG;
-  *out = h->counters;
-  out->submit_busy = h->submit_busy.load();
+  out->units_processed = h->counters.units_processed.load();
+  out->samples_processed = h->counters.samples_processed.load();
+  out->tps_emitted = h->counters.tps_emitted.load();
+  out->tps_dropped_overflow = h->counters.tps_dropped_overflow.load();
+  out->batches = h->counters.batches.load();
+  out->submit_busy = h->counters.submit_busy.load();
+  out->h2d_bytes = h->counters.h2d_bytes.load();
+  out->d2h_bytes = h->counters.d2h_bytes.load();
   return SWTPG_OK;
 }
 
@@ -1355,133 +947,6 @@ swtpg_free_pinned(void* p)
 {
   if (p && cudaFreeHost(p) != cudaSuccess)
     cudaGetLastError();
-}
-
-static inline bool
-tp_less(const swtpg_tp& a, const swtpg_tp& b)
-{
-  if (a.time_start != b.time_start) return a.time_start < b.time_start;
-  if (a.link != b.link) return a.link < b.link;
-  if (a.channel != b.channel) return a.channel < b.channel;
-  if (a.time_over_threshold != b.time_over_threshold) return a.time_over_threshold < b.time_over_threshold;
-  return a.adc_integral < b.adc_integral;
-}
-
-// Host-side ordering of a batch's TP list. A 64-frame batch of 148 APAs carries ~0.5 M records: std::sort needs ~110 ms for
-// them, more than the batch's whole host-to-device copy. The keys are narrow, though — time_start spans the batch (a few
-// 10^5 ticks), link < n_links, channel < 256 — so (time_start - min, link, channel) packs into one 64-bit integer, and an LSD
-// radix sort of (key, index) pairs with 11-bit digits followed by one gather orders the list in ~10 ms. Ties on the key
-// (which cannot come out of one handle) are ordered like tp_less afterwards; lists whose keys do not fit fall back to std::sort.
-static unsigned
-bit_length(uint64_t v)
-{
-  unsigned b = 0;
-  while (v) {
-    ++b;
-    v >>= 1;
-  }
-  return b;
-}
-
-static void
-sort_tps_impl(swtpg_tp* a, size_t n)
-{
-  if (n < 2)
-    return;
-  if (n < 4096 || n > 0xFFFFFFFFull) {
-    std::stable_sort(a, a + n, tp_less);
-    return;
-  }
-  uint64_t tmin = a[0].time_start, tmax = a[0].time_start;
-  uint32_t lmax = 0;
-  uint16_t cmax = 0;
-  for (size_t i = 0; i < n; ++i) {
-    tmin = std::min(tmin, a[i].time_start);
-    tmax = std::max(tmax, a[i].time_start);
-    lmax = std::max(lmax, a[i].link);
-    cmax = std::max(cmax, a[i].channel);
-  }
-  const unsigned cb = bit_length(cmax), lb = bit_length(lmax), tb = bit_length(tmax - tmin), bits = cb + lb + tb;
-  if (bits > 64) {
-    std::stable_sort(a, a + n, tp_less);
-    return;
-  }
-  struct KV
-  {
-    uint64_t key;
-    uint32_t idx, pad;
-  };
-  constexpr unsigned kDigit = 11, kBuckets = 1u << kDigit, kMaxPasses = (64 + kDigit - 1) / kDigit;
-  const unsigned passes = (bits + kDigit - 1) / kDigit;
-  // scratch is kept per calling thread between calls (grow-only): a batch-sized sort per superchunk would otherwise spend most
-  // of its time faulting in 64 n bytes of fresh pages
-  thread_local std::vector<unsigned char> scratch;
-  const size_t need = 2 * n * sizeof(KV) + n * sizeof(swtpg_tp) + 64;
-  if (scratch.size() < need)
-    scratch.resize(need + need / 4);
-  unsigned char* base = scratch.data() + ((64 - (reinterpret_cast<uintptr_t>(scratch.data()) & 63)) & 63);
-  KV* kv = reinterpret_cast<KV*>(base);
-  KV* kv2 = kv + n;
-  swtpg_tp* out = reinterpret_cast<swtpg_tp*>(kv2 + n);
-  std::vector<uint32_t> hist(size_t(kMaxPasses) * kBuckets, 0u); // all digit histograms in the pass that builds the keys
-  for (size_t i = 0; i < n; ++i) {
-    const uint64_t t = a[i].time_start - tmin;
-    const uint64_t key = (tb ? t << (lb + cb) : 0) | (uint64_t(a[i].link) << cb) | a[i].channel;
-    kv[i].key = key;
-    kv[i].idx = uint32_t(i);
-    for (unsigned p = 0; p < passes; ++p)
-      ++hist[p * kBuckets + ((key >> (p * kDigit)) & (kBuckets - 1))];
-  }
-  KV *src = kv, *dst = kv2;
-  for (unsigned p = 0; p < passes; ++p) {
-    uint32_t* h = hist.data() + size_t(p) * kBuckets;
-    uint32_t sum = 0;
-    bool trivial = false;
-    for (unsigned d = 0; d < kBuckets; ++d) {
-      trivial |= h[d] == n; // every key has the same digit: nothing to do
-      const uint32_t c = h[d];
-      h[d] = sum;
-      sum += c;
-    }
-    if (trivial)
-      continue;
-    const unsigned shift = p * kDigit;
-    for (size_t i = 0; i < n; ++i)
-      dst[h[(src[i].key >> shift) & (kBuckets - 1)]++] = src[i];
-    std::swap(src, dst);
-  }
-  for (size_t i = 0; i < n; ++i)
-    out[i] = a[src[i].idx];
-  for (size_t i = 0; i < n;) { // runs of equal (time_start, link, channel): order the rest of tp_less, keeping input order on full ties
-    size_t j = i + 1;
-    while (j < n && src[j].key == src[i].key)
-      ++j;
-    if (j - i > 1)
-      std::stable_sort(out + i, out + j, tp_less);
-    i = j;
-  }
-  memcpy(a, out, n * sizeof(swtpg_tp));
-}
-
-void
-swtpg_sort_tps(swtpg_tp* tps, size_t n)
-{
-  if (tps && n > 1)
-    sort_tps_impl(tps, n);
-}
-
-void
-swtpg_merge_sorted(const swtpg_tp* const* lists, const size_t* n, size_t k, swtpg_tp* out)
-{
-  // The lists are sorted like swtpg_sort_tps; ties are resolved by list index (stable across GPUs). Concatenating them in list
-  // order and running the stable radix sort gives exactly that order, in O(total) instead of O(total log k) comparisons.
-  size_t total = 0;
-  for (size_t i = 0; i < k; ++i) {
-    if (n[i])
-      memcpy(out + total, lists[i], n[i] * sizeof(swtpg_tp));
-    total += n[i];
-  }
-  sort_tps_impl(out, total);
 }
 
 } // extern "C"

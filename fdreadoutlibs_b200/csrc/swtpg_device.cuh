@@ -231,6 +231,50 @@ mbar_wait(uint64_t* bar, uint32_t parity)
                : "memory");
 }
 
+// Wait of a PRODUCER warp's lane on an `empty` barrier. A producer has nothing to do until its consumers release a stage
+// (microseconds), and a spinning try_wait loop issues SYNCS + BRA + YIELD every ~15 cycles on a sub-partition that the
+// consumer warps need (measured round 1: 30 % of all issued warp-instructions of the CTA-form kernels were this loop).
+//   SWTPG_PRODUCER_WAIT = 0  spin (round-1 behaviour)
+//                       = 1  try_wait with a suspend-time hint: the hardware parks the thread until the phase completes
+//                       = 2  test_wait + nanosleep back-off
+#ifndef SWTPG_PRODUCER_WAIT
+#define SWTPG_PRODUCER_WAIT 0
+#endif
+#ifndef SWTPG_PRODUCER_SLEEP_NS
+#define SWTPG_PRODUCER_SLEEP_NS 200
+#endif
+__device__ __forceinline__ bool
+mbar_test(uint64_t* bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok)
+               : "r"(smem_u32(bar)), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void
+mbar_wait_producer(uint64_t* bar, uint32_t parity)
+{
+#if SWTPG_PRODUCER_WAIT == 1
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "WAIT_%=:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+               "@p bra DONE_%=;\n"
+               "bra WAIT_%=;\n"
+               "DONE_%=:\n"
+               "}" ::"r"(smem_u32(bar)),
+               "r"(parity), "r"(1000000u)
+               : "memory");
+#elif SWTPG_PRODUCER_WAIT == 2
+  while (!mbar_test(bar, parity))
+    __nanosleep(SWTPG_PRODUCER_SLEEP_NS);
+#else
+  mbar_wait(bar, parity);
+#endif
+}
+
 // ---- 14-bit pair extraction ---------------------------------------------------------------------------------------
 // Lane l's pair occupies bits [28 l, 28 l + 28) of the 896-bit little-endian row (channel c at bits [14c, 14c+14):
 // fddetdataformats get_adc; reference unpack: wibeth/tpg/FrameExpand.hpp:84-186). Word index and shift are per-lane

@@ -1313,7 +1313,7 @@ struct WibEthSmem
   static constexpr size_t aux = hits + size_t(WARPS) * HitStage::kCap * 16;
   static constexpr size_t counts = aux + size_t(WARPS) * HitStage::kCap * 4;
   static constexpr size_t fifo = align16(counts + size_t(WARPS) * 4);
-  static constexpr size_t total = fifo + size_t(WARPS) * 16; // 4-entry link FIFO per warp
+  static constexpr size_t total = fifo + size_t(WARPS) * 32; // 8-entry link FIFO per warp
 };
 
 template<class Algo, int WARPS, int NSTAGE, int CHUNK_TICKS, bool DUMP, int MIN_CTAS = 1>
@@ -1348,7 +1348,7 @@ wibeth_kernel(const KernelParams p)
   // and to the global link cursor.
   // FIFO of links the producer has started and the consumer has not: the producer is at most NSTAGE chunks ahead and every
   // link it starts has >= kChunksPerUnit chunks, so at most ceil(NSTAGE / kChunksPerUnit) + 1 links are in flight.
-  constexpr uint32_t kFifo = 4; // power of two; lives in shared memory so the tick loop carries no registers for it
+  constexpr uint32_t kFifo = 8; // power of two; lives in shared memory so the tick loop carries no registers for it
   static_assert((NSTAGE + kChunksPerUnit - 1) / kChunksPerUnit + 1 <= int(kFifo), "link FIFO too short for this ring geometry");
   volatile uint32_t* fifo = reinterpret_cast<volatile uint32_t*>(smem + L::fifo) + warp * kFifo;
   uint32_t fifo_head = 0, fifo_n = 0;
@@ -1565,7 +1565,7 @@ wibeth_quad_kernel(const KernelParams p)
     uint32_t slot = 0, round = 0, pushed = 0;
     auto wait_slot = [&]() { // all four consumers released the stage's previous contents
       if (round != 0)
-        mbar_wait(&empty[slot], (round - 1u) & 1u);
+        mbar_wait_producer(&empty[slot], (round - 1u) & 1u);
     };
     uint32_t first_link = blockIdx.x * kQuad; // the CTA's first quad; every further one is claimed from the cursor
     for (bool first = true;;) {
@@ -1786,7 +1786,7 @@ wib2_kernel(const KernelParams p)
     uint32_t slot = 0, round = 0, pushed = 0;
     auto wait_slot = [&]() { // all four consumers released the stage's previous contents
       if (round != 0)
-        mbar_wait(&empty[slot], (round - 1u) & 1u);
+        mbar_wait_producer(&empty[slot], (round - 1u) & 1u);
     };
     uint32_t link = blockIdx.x; // the CTA's first link; every further one is claimed from the cursor (as in wibeth_kernel)
     for (bool first = true;; first = false) {

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <ctime>
 #include <thread>
 
 namespace swtpg {
@@ -101,8 +102,20 @@ TpgEngine::start()
   std::lock_guard<std::mutex> lk(m_mu);
   if (!m_h)
     throw std::runtime_error("TpgEngine::start before conf");
-  if (m_started++ == 0)
+  if (m_started++ == 0) {
     check(m_h, swtpg_start(m_h), "swtpg_start");
+    m_delivery_quit = false;
+    m_delivery = std::thread([this] { // hands TPs to the links' processors as batches complete; asleep in between
+      while (!m_delivery_quit.load(std::memory_order_acquire)) {
+        try {
+          std::lock_guard<std::mutex> dl(m_drain_mu);
+          deliver_once(2000);
+        } catch (const std::exception&) {
+          return; // the next call into the engine (submit / stop) reports the failure
+        }
+      }
+    });
+  }
 }
 
 void
@@ -113,41 +126,24 @@ TpgEngine::stop()
     if (m_started == 0 || --m_started != 0)
       return;
   }
-  check(m_h, swtpg_flush(m_h), "swtpg_flush");
-  drain(true);
+  m_delivery_quit.store(true, std::memory_order_release);
+  if (m_delivery.joinable())
+    m_delivery.join();
+  drain(true); // flush the ragged tail, deliver everything that is left
   check(m_h, swtpg_stop(m_h), "swtpg_stop");
 }
 
 void
-TpgEngine::set_link_memory_factor(uint32_t link, const uint16_t* by_channel, uint32_t n_channels)
+TpgEngine::set_link_memory_factor(uint32_t link, const uint16_t* by_channel, uint32_t)
 {
-  std::lock_guard<std::mutex> lk(m_mu);
-  if (m_rs_factor.empty())
-    m_rs_factor.assign(size_t(m_cfg.n_links) * n_channels, m_cfg.rs_memory_factor);
-  std::copy(by_channel, by_channel + n_channels, m_rs_factor.begin() + long(size_t(link) * n_channels));
-  check(m_h, swtpg_set_rs_memory_factor(m_h, m_rs_factor.data()), "swtpg_set_rs_memory_factor");
-}
-
-// Blocking back-pressure (block_on_backpressure, a test / replay aid — the reference drops instead): the staging ring is full,
-// so the GPU pipeline has to drain before this link can go on. SWTPG_HOST_BACKOFF_US > 0 sleeps that long instead of yielding,
-// which frees the core for the other links' threads when there are more threads than cores.
-static void
-backoff()
-{
-  static const int us = [] {
-    const char* e = getenv("SWTPG_HOST_BACKOFF_US");
-    return e ? atoi(e) : 0;
-  }();
-  if (us > 0)
-    std::this_thread::sleep_for(std::chrono::microseconds(us));
-  else
-    std::this_thread::yield();
+  // one small asynchronous copy for this link's rows, ordered on the compute stream; no engine-wide lock, no other link waits
+  check(m_h, swtpg_set_link_rs_memory_factor(m_h, link, by_channel), "swtpg_set_link_rs_memory_factor");
 }
 
 bool
-TpgEngine::submit(uint32_t link, const void* unit, size_t bytes)
+TpgEngine::submit(uint32_t link, const void* unit, size_t bytes, uint64_t wait_us)
 {
-  const swtpg_status s = swtpg_submit(m_h, link, unit, bytes);
+  const swtpg_status s = wait_us ? swtpg_submit_wait(m_h, link, unit, bytes, wait_us) : swtpg_submit(m_h, link, unit, bytes);
   if (s == SWTPG_ERR_BUSY)
     return false;
   check(m_h, s, "swtpg_submit");
@@ -171,6 +167,41 @@ TpgEngine::unregister_latency_buffer(void* base)
     check(m_h, swtpg_unregister_buffer(m_h, base), "swtpg_unregister_buffer");
 }
 
+// One poll (sleeping up to wait_us for a completed batch) and the hand-over of its records: a counting sort by link, then one
+// process_swtpg_hits call per link that has any. Caller holds m_drain_mu.
+size_t
+TpgEngine::deliver_once(uint64_t wait_us)
+{
+  size_t n = 0;
+  const swtpg_status s = wait_us ? swtpg_poll_wait(m_h, m_buf.data(), m_buf.size(), &n, wait_us) : swtpg_poll(m_h, m_buf.data(), m_buf.size(), &n);
+  if (s != SWTPG_OK && s != SWTPG_ERR_OVERFLOW)
+    check(m_h, s, "swtpg_poll");
+  if (n == 0)
+    return 0;
+  const size_t n_links = m_procs.size();
+  m_link_count.assign(n_links + 1, 0u);
+  for (size_t i = 0; i < n; ++i)
+    if (m_buf[i].link < n_links)
+      ++m_link_count[m_buf[i].link + 1];
+  for (size_t l = 0; l < n_links; ++l)
+    m_link_count[l + 1] += m_link_count[l];
+  m_sorted.resize(m_buf.size());
+  {
+    std::vector<uint32_t>& at = m_link_count; // running write positions: at[l] ends up as the END of link l's block
+    for (size_t i = 0; i < n; ++i)
+      if (m_buf[i].link < n_links)
+        m_sorted[at[m_buf[i].link]++] = m_buf[i];
+  }
+  size_t begin = 0;
+  for (size_t l = 0; l < n_links; ++l) {
+    const size_t end = m_link_count[l];
+    if (end > begin && m_procs[l])
+      m_procs[l]->process_swtpg_hits(m_sorted.data() + begin, end - begin);
+    begin = end;
+  }
+  return n;
+}
+
 void
 TpgEngine::drain(bool wait)
 {
@@ -178,35 +209,27 @@ TpgEngine::drain(bool wait)
   if (wait)
     lk.lock();
   else if (!lk.try_lock())
-    return; // another link's thread is draining
-  auto deliver = [&]() -> size_t {
-    size_t n = 0;
-    const swtpg_status s = swtpg_poll(m_h, m_buf.data(), m_buf.size(), &n);
-    if (s != SWTPG_OK && s != SWTPG_ERR_OVERFLOW)
-      check(m_h, s, "swtpg_poll");
-    // route by link: records of one link are handed over in one call
-    std::sort(m_buf.begin(), m_buf.begin() + long(n), [](const swtpg_tp& a, const swtpg_tp& b) { return a.link < b.link; });
-    for (size_t i = 0; i < n;) {
-      size_t j = i;
-      while (j < n && m_buf[j].link == m_buf[i].link)
-        ++j;
-      FrameProcessorBase* p = m_buf[i].link < m_procs.size() ? m_procs[m_buf[i].link] : nullptr;
-      if (p)
-        p->process_swtpg_hits(m_buf.data() + i, j - i);
-      i = j;
-    }
-    return n;
-  };
+    return; // the delivery thread (or another caller) is at it
   if (!wait) {
-    for (int pass = 0; pass < 4 && deliver(); ++pass) {
+    for (int pass = 0; pass < 4 && deliver_once(0); ++pass) {
     }
     return;
   }
-  // stop(): every dispatched batch must be delivered. A poll may only have *started* a batch's TP copy, so alternate
-  // sync and poll until two polls in a row bring nothing.
-  for (int idle = 0; idle < 2;) {
-    check(m_h, swtpg_sync(m_h), "swtpg_sync");
-    idle = deliver() ? 0 : idle + 1;
+  // stop(): everything submitted must come out. The loop ends on the library's own bookkeeping — nothing pending, nothing in
+  // flight, nothing ready — never on "a poll brought no records" (a batch without TPs is still a batch in flight).
+  for (;;) {
+    const swtpg_status fs = swtpg_flush(m_h); // BUSY: every batch waits to be polled — deliver, then flush again
+    if (fs != SWTPG_OK && fs != SWTPG_ERR_BUSY)
+      check(m_h, fs, "swtpg_flush");
+    if (fs == SWTPG_OK)
+      check(m_h, swtpg_sync(m_h), "swtpg_sync");
+    while (deliver_once(0)) {
+    }
+    uint64_t pending = 0;
+    uint32_t in_flight = 0, ready = 0;
+    check(m_h, swtpg_stream_status(m_h, &pending, &in_flight, &ready), "swtpg_stream_status");
+    if (fs == SWTPG_OK && pending == 0 && in_flight == 0 && ready == 0)
+      return;
   }
 }
 
@@ -320,17 +343,20 @@ WIBEthFrameProcessor::get_info(RawDataProcessorInfo& info)
     info.num_tps_suppressed_too_long = m_tps_suppressed_too_long.exchange(0);
     info.num_tps_send_failed = m_tps_send_failed.exchange(0);
     info.num_frames_dropped_busy = m_frames_dropped.exchange(0);
-    // the ten channels with the most TPs since the last call, then reset (:263-284)
-    std::lock_guard<std::mutex> lk(m_rate_mu);
-    std::vector<std::pair<uint32_t, int>> v(m_tp_channel_rate_map.begin(), m_tp_channel_rate_map.end());
-    std::stable_sort(v.begin(), v.end(), [](const auto& x, const auto& y) { return x.second > y.second; });
-    info.n_top = uint32_t(std::min<size_t>(10, v.size()));
-    for (uint32_t i = 0; i < info.n_top; ++i) {
-      info.top_channels[i] = v[i].first;
-      info.top_channel_tps[i] = uint32_t(v[i].second);
+    // the ten channels with the most TPs since the last call, then reset (:263-284): the reference keeps a std::map keyed by
+    // offline channel and sorts its pairs by count; ties keep the map's (ascending channel) order
+    if (m_maps_ready.load(std::memory_order_acquire)) {
+      std::map<uint32_t, int> rate;
+      for (uint32_t c = 0; c < 64; ++c)
+        rate[m_offline_of_channel[c]] += int(m_tp_channel_rate[c].exchange(0, std::memory_order_relaxed));
+      std::vector<std::pair<uint32_t, int>> v(rate.begin(), rate.end());
+      std::stable_sort(v.begin(), v.end(), [](const auto& x, const auto& y) { return x.second > y.second; });
+      info.n_top = uint32_t(std::min<size_t>(10, v.size()));
+      for (uint32_t i = 0; i < info.n_top; ++i) {
+        info.top_channels[i] = v[i].first;
+        info.top_channel_tps[i] = uint32_t(v[i].second);
+      }
     }
-    for (auto& el : m_tp_channel_rate_map)
-      el.second = 0;
   }
   m_t0 = now;
 }
@@ -397,13 +423,15 @@ WIBEthFrameProcessor::find_hits(constframeptr fp, WIBEthFrameHandler* frame_hand
     m_det_id = uint32_t(hdr->det_id);
     if (hdr->crate_id != m_crate_no || hdr->slot_id != m_slot_no || hdr->stream_id != m_stream_id)
       m_misconf.push_back({ uint32_t(hdr->crate_id), uint32_t(hdr->slot_id), uint32_t(hdr->stream_id), m_crate_no, m_slot_no, m_stream_id });
-    {
-      std::lock_guard<std::mutex> lk(m_rate_mu);
-      for (uint32_t p = 0; p < 64; ++p) {
-        m_register_channels[p] = frame_handler->register_channel_map[p];
-        m_tp_channel_rate_map[m_register_channels[p]] = 0;
-      }
+    for (uint32_t p = 0; p < 64; ++p)
+      m_register_channels[p] = frame_handler->register_channel_map[p];
+    for (uint32_t c = 0; c < 64; ++c) { // per FRAME channel: the offline channel a record of that channel is reported with, masked or not
+      // H2: production indexes the POSITION-ordered map with the FRAME channel the AVX2 code emits (:527)
+      m_offline_of_channel[c] = m_correct_lookup ? m_channel_map(hdr->crate_id, hdr->slot_id, hdr->stream_id, c) : m_register_channels[c];
+      m_masked[c] = m_channel_mask_set.count(m_offline_of_channel[c]) ? 1 : 0;
+      m_tp_channel_rate[c].store(0, std::memory_order_relaxed);
     }
+    m_maps_ready.store(true, std::memory_order_release);
     if (m_enable_simple_threshold_on_collection) { // collection channels run with R = 0, i.e. a plain threshold (:441-450)
       uint16_t factor[64];
       for (uint32_t c = 0; c < 64; ++c) {
@@ -416,31 +444,28 @@ WIBEthFrameProcessor::find_hits(constframeptr fp, WIBEthFrameHandler* frame_hand
   }
   // The frame is only borrowed for the duration of this call: swtpg_submit copies it into the pinned staging slot — unless it
   // lies in a latency buffer registered with the engine, which the copy engine then reads directly (zero-copy ingest).
-  while (!m_engine->submit(frame_handler->link, fp->data, sizeof fp->data)) {
-    if (!m_block) {
+  // Non-blocking by default, like the reference's try_send: a full ring drops the frame and counts it. With
+  // block_on_backpressure the thread SLEEPS until the completion thread has freed ring space (swtpg_submit_wait). TPs come
+  // back through the engine's delivery thread (process_swtpg_hits below), never through this thread.
+  if (!m_block) {
+    if (!m_engine->submit(frame_handler->link, fp->data, sizeof fp->data))
       ++m_frames_dropped;
-      break;
+  } else {
+    while (!m_engine->submit(frame_handler->link, fp->data, sizeof fp->data, 100000)) {
     }
-    m_engine->drain(false);
-    backoff();
   }
-  if ((++m_frames_since_drain & 7u) == 0) // TPs only appear once per superchunk: polling on every frame would only contend
-    m_engine->drain(false);
 }
 
 void
 WIBEthFrameProcessor::process_swtpg_hits(const swtpg_tp* tps, size_t n)
 {
   uint64_t nhits = 0;
-  std::lock_guard<std::mutex> lk(m_rate_mu); // one lock per delivered block of records (get_info is the only other taker)
   for (size_t i = 0; i < n; ++i) {
     const swtpg_tp& r = tps[i];
-    // H2: production indexes the POSITION-ordered map with the FRAME channel the AVX2 code emits (:527).
-    uint32_t offline_channel = m_register_channels[r.channel & 63u];
-    if (m_correct_lookup)
-      offline_channel = m_channel_map(m_crate_no, m_slot_no, m_stream_id, r.channel);
-    if (m_channel_mask_set.find(offline_channel) != m_channel_mask_set.end())
+    const uint32_t c = r.channel & 63u;
+    if (m_masked[c]) // offline channel in tpg_channel_mask (:528)
       continue;
+    const uint32_t offline_channel = m_offline_of_channel[c];
     TriggerPrimitiveTypeAdapter tp;
     tp.tp.time_start = r.time_start;
     tp.tp.time_peak = r.time_peak;
@@ -460,7 +485,7 @@ WIBEthFrameProcessor::process_swtpg_hits(const swtpg_tp* tps, size_t n)
       m_new_tps++;
       ++nhits;
     }
-    m_tp_channel_rate_map[offline_channel]++;
+    m_tp_channel_rate[c].fetch_add(1, std::memory_order_relaxed);
   }
   m_tpg_hits_count += nhits;
 }
@@ -548,16 +573,18 @@ WIB2FrameProcessor::get_info(RawDataProcessorInfo& info)
     info.num_tps_suppressed_too_long = m_tps_suppressed_too_long.exchange(0);
     info.num_tps_send_failed = m_tps_send_failed.exchange(0);
     info.num_frames_dropped_busy = m_frames_dropped.exchange(0);
-    std::lock_guard<std::mutex> lk(m_rate_mu);
-    std::vector<std::pair<uint32_t, int>> v(m_tp_channel_rate_map.begin(), m_tp_channel_rate_map.end());
-    std::stable_sort(v.begin(), v.end(), [](const auto& x, const auto& y) { return x.second > y.second; });
-    info.n_top = uint32_t(std::min<size_t>(10, v.size()));
-    for (uint32_t i = 0; i < info.n_top; ++i) {
-      info.top_channels[i] = v[i].first;
-      info.top_channel_tps[i] = uint32_t(v[i].second);
+    if (m_maps_ready.load(std::memory_order_acquire)) {
+      std::map<uint32_t, int> rate;
+      for (uint32_t c = 0; c < 256; ++c)
+        rate[m_register_channels[c]] += int(m_tp_channel_rate[c].exchange(0, std::memory_order_relaxed));
+      std::vector<std::pair<uint32_t, int>> v(rate.begin(), rate.end());
+      std::stable_sort(v.begin(), v.end(), [](const auto& x, const auto& y) { return x.second > y.second; });
+      info.n_top = uint32_t(std::min<size_t>(10, v.size()));
+      for (uint32_t i = 0; i < info.n_top; ++i) {
+        info.top_channels[i] = v[i].first;
+        info.top_channel_tps[i] = uint32_t(v[i].second);
+      }
     }
-    for (auto& el : m_tp_channel_rate_map)
-      el.second = 0;
   }
   m_t0 = now;
 }
@@ -596,37 +623,35 @@ WIB2FrameProcessor::find_hits(constframeptr fp, WIB2FrameHandler* frame_handler)
   if (frame_handler->first_hit) {
     const WIB2Header* h = fp->header();
     m_det_id = h->detector_id;
-    std::lock_guard<std::mutex> lk(m_rate_mu);
     // WIB2's AVX2 code emits the register POSITION and the map is position-ordered (src/wib2/WIB2FrameProcessor.cpp:367-368),
     // so the reported channel is the true offline channel of the frame channel: a frame-channel-ordered map is equivalent.
     for (uint32_t c = 0; c < 256; ++c) {
       m_register_channels[c] = m_channel_map(h->crate, h->slot, h->link, c);
-      m_tp_channel_rate_map[m_register_channels[c]] = 0;
+      m_masked[c] = m_channel_mask_set.count(m_register_channels[c]) ? 1 : 0;
+      m_tp_channel_rate[c].store(0, std::memory_order_relaxed);
     }
+    m_maps_ready.store(true, std::memory_order_release);
     frame_handler->first_hit = false;
   }
-  while (!m_engine->submit(frame_handler->link, fp->data, sizeof fp->data)) {
-    if (!m_block) {
+  if (!m_block) {
+    if (!m_engine->submit(frame_handler->link, fp->data, sizeof fp->data))
       ++m_frames_dropped;
-      break;
+  } else {
+    while (!m_engine->submit(frame_handler->link, fp->data, sizeof fp->data, 100000)) {
     }
-    m_engine->drain(false);
-    backoff();
   }
-  if ((++m_frames_since_drain & 7u) == 0) // TPs only appear once per superchunk: polling on every frame would only contend
-    m_engine->drain(false);
 }
 
 void
 WIB2FrameProcessor::process_swtpg_hits(const swtpg_tp* tps, size_t n)
 {
-  std::lock_guard<std::mutex> lk(m_rate_mu); // one lock per delivered block of records
   uint64_t nhits = 0;
   for (size_t i = 0; i < n; ++i) {
     const swtpg_tp& r = tps[i];
-    const uint32_t offline_channel = m_register_channels[r.channel & 255u];
-    if (m_channel_mask_set.find(offline_channel) != m_channel_mask_set.end())
+    const uint32_t c = r.channel & 255u;
+    if (m_masked[c])
       continue;
+    const uint32_t offline_channel = m_register_channels[c];
     TriggerPrimitiveTypeAdapter tp;
     tp.tp.time_start = r.time_start;
     tp.tp.time_peak = r.time_peak;
@@ -644,7 +669,7 @@ WIB2FrameProcessor::process_swtpg_hits(const swtpg_tp* tps, size_t n)
       m_tps_send_failed++;
     m_new_tps++; // counted regardless of the outcome, as the reference does (:469-470)
     ++nhits;
-    m_tp_channel_rate_map[offline_channel]++;
+    m_tp_channel_rate[c].fetch_add(1, std::memory_order_relaxed);
   }
   m_tpg_hits_count += nhits;
 }
@@ -785,7 +810,9 @@ struct swtpg_host_conf
   uint32_t channel_mask[16];
   uint32_t n_mask;
   uint16_t crate_id, slot_id, first_link_id;
-  uint8_t enable_tpg, emulator_mode, correct_channel_lookup, reversed_map, enable_simple_threshold_on_collection, block_on_backpressure, pad[2];
+  uint8_t enable_tpg, emulator_mode, correct_channel_lookup, reversed_map, enable_simple_threshold_on_collection, block_on_backpressure;
+  uint8_t count_only_sink; // 1: tp_out only counts what it accepts (throughput runs: no queue growth)
+  uint8_t pad;
   uint32_t sink_capacity; // per link; try_send fails beyond it (0 = unbounded)
 };
 
@@ -807,6 +834,8 @@ struct swtpg_host
   std::vector<std::vector<TriggerPrimitiveTypeAdapter>> queues;
   std::vector<std::unique_ptr<std::mutex>> qmu;
   uint32_t sink_capacity = 0;
+  bool count_only = false;
+  std::atomic<uint64_t> accepted{ 0 };
   std::string error;
 };
 
@@ -827,6 +856,7 @@ swtpg_host_create(const swtpg_host_conf* c)
     auto h = std::make_unique<swtpg_host>();
     h->engine = std::make_shared<TpgEngine>(c->device, swtpg_format(c->format), c->n_links, c->superchunk_units);
     h->sink_capacity = c->sink_capacity;
+    h->count_only = c->count_only_sink != 0;
     h->queues.resize(c->n_links);
     h->regs.resize(c->n_links); // the processors keep REFERENCES to these unique_ptrs (as the reference's model does): no reallocation later
     for (uint32_t l = 0; l < c->n_links; ++l) {
@@ -851,6 +881,10 @@ swtpg_host_create(const swtpg_host_conf* c)
       rc.block_on_backpressure = c->block_on_backpressure != 0;
       swtpg_host* hp = h.get();
       auto sink = [hp, l](TriggerPrimitiveTypeAdapter&& tp) {
+        if (hp->count_only) {
+          hp->accepted.fetch_add(1, std::memory_order_relaxed);
+          return true;
+        }
         std::lock_guard<std::mutex> lk(*hp->qmu[l]);
         if (hp->sink_capacity && hp->queues[l].size() >= hp->sink_capacity)
           return false;
@@ -970,6 +1004,97 @@ swtpg_host_push_parallel(swtpg_host* h, void* payloads, uint32_t n_units)
       return -1;
     }
   return 0;
+}
+
+// A readout host the way it is built: a FEW consumer threads, each serving many links. Thread t owns links t, t + T, ...; it
+// walks them round-robin, `burst` consecutive payloads per link and turn, each through the pre-process tasks (sequence /
+// timestamp checks) and the post-process task (find_hits). pace > 0 runs against the clock: payload g of every link is due
+// g * period / pace after the start (period = one payload's worth of detector time: 2048 ticks of 16 ns for a WIBEth frame,
+// 12 x 32 ticks for a WIB2 superchunk), a burst is pushed when its last payload is due, and the thread SLEEPS until then —
+// so the CPU time it reports is the work, not the waiting. `passes` walks over the same payload array again (emulator mode
+// keeps the timestamps running). Fills wall seconds and the feeder threads' summed CPU seconds.
+struct swtpg_host_feed_stats
+{
+  double wall_s, feeder_cpu_s;
+  uint64_t payloads, late_bursts;
+};
+
+int
+swtpg_host_push_feeders(swtpg_host* h, void* payloads, uint32_t n_units, uint32_t n_threads, uint32_t burst, double pace, uint32_t passes,
+                        swtpg_host_feed_stats* out)
+{
+  const size_t n_links = h->eth.empty() ? h->wib2.size() : h->eth.size();
+  const bool eth = !h->eth.empty();
+  const size_t unit_bytes = eth ? sizeof(DUNEWIBEthTypeAdapter) : sizeof(DUNEWIBSuperChunkTypeAdapter);
+  const double period_s = (eth ? 2048.0 : 12.0 * 32.0) / 62.5e6;
+  n_threads = std::max<uint32_t>(1, std::min<uint32_t>(n_threads, uint32_t(n_links)));
+  burst = std::max<uint32_t>(1, std::min(burst, n_units));
+  std::vector<std::thread> threads;
+  std::vector<std::string> errors(n_threads);
+  std::vector<double> cpu(n_threads, 0.0);
+  std::vector<uint64_t> late(n_threads, 0);
+  const auto t_start = std::chrono::steady_clock::now() + std::chrono::milliseconds(2);
+  for (uint32_t t = 0; t < n_threads; ++t)
+    threads.emplace_back([=, &errors, &cpu, &late]() {
+      try {
+        for (uint32_t pass = 0; pass < passes; ++pass)
+          for (uint32_t u0 = 0; u0 < n_units; u0 += burst) {
+            const uint32_t u1 = std::min(n_units, u0 + burst);
+            if (pace > 0) {
+              const double due_s = (double(pass) * n_units + u1) * period_s / pace;
+              const auto due = t_start + std::chrono::duration_cast<std::chrono::steady_clock::duration>(std::chrono::duration<double>(due_s));
+              if (std::chrono::steady_clock::now() < due)
+                std::this_thread::sleep_until(due);
+              else
+                ++late[t];
+            }
+            for (size_t l = t; l < n_links; l += n_threads)
+              for (uint32_t u = u0; u < u1; ++u) {
+                char* p = static_cast<char*>(payloads) + (l * n_units + u) * unit_bytes;
+                if (eth) {
+                  auto* fp = reinterpret_cast<DUNEWIBEthTypeAdapter*>(p);
+                  h->eth[l]->preprocess_item(fp);
+                  h->eth[l]->postprocess_item(fp);
+                } else {
+                  auto* fp = reinterpret_cast<DUNEWIBSuperChunkTypeAdapter*>(p);
+                  h->wib2[l]->preprocess_item(fp);
+                  h->wib2[l]->postprocess_item(fp);
+                }
+              }
+          }
+        timespec ts{};
+        clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+        cpu[t] = double(ts.tv_sec) + 1e-9 * double(ts.tv_nsec);
+      } catch (const std::exception& e) {
+        errors[t] = e.what();
+      }
+    });
+  for (auto& th : threads)
+    th.join();
+  const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+  for (auto& e : errors)
+    if (!e.empty()) {
+      g_host_error = e;
+      return -1;
+    }
+  if (out) {
+    out->wall_s = wall;
+    out->feeder_cpu_s = 0;
+    out->late_bursts = 0;
+    for (uint32_t t = 0; t < n_threads; ++t) {
+      out->feeder_cpu_s += cpu[t];
+      out->late_bursts += late[t];
+    }
+    out->payloads = uint64_t(passes) * n_units * n_links;
+  }
+  return 0;
+}
+
+// TPs accepted by the count-only sinks so far
+uint64_t
+swtpg_host_tp_count(swtpg_host* h)
+{
+  return h->accepted.load();
 }
 
 size_t

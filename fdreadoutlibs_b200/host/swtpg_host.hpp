@@ -25,6 +25,7 @@
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace swtpg {
@@ -36,13 +37,19 @@ struct TriggerPrimitive
 {
   enum class Type : uint32_t { kUnknown = 0, kTPC = 1, kPDS = 2 };
   enum class Algorithm : uint32_t { kUnknown = 0, kTPCDefault = 1, kSimpleThreshold = 2, kAbsRunningSum = 3, kRunningSum = 4 };
+  uint16_t version = 1;
   uint64_t time_start = 0, time_peak = 0, time_over_threshold = 0;
   uint32_t channel = 0, adc_integral = 0;
   uint16_t adc_peak = 0, detid = 0;
   Type type = Type::kUnknown;
   Algorithm algorithm = Algorithm::kUnknown;
-  uint16_t version = 1, flag = 0;
+  uint16_t flag = 0;
 };
+// trgdataformats is not part of the snapshot; its TriggerPrimitive is a 56-byte record — the 16-bit version
+// first (padded to 8), three 64-bit times, channel and adc_integral (32 bit), adc_peak and detid (16 bit), the two 32-bit enums
+// and the 16-bit flag word (restated from memory of trgdataformats/TriggerPrimitive.hpp). Same members, same order, so the
+// restatement must come out at the same size; the byte layout itself stays unpinned (parity is asserted on field tuples).
+static_assert(sizeof(TriggerPrimitive) == 56, "TriggerPrimitive restatement drifted from the 56-byte record of trgdataformats");
 // include/fdreadoutlibs/TriggerPrimitiveTypeAdapter.hpp:19-71: ordering by (time_start, channel)
 struct TriggerPrimitiveTypeAdapter
 {
@@ -224,11 +231,15 @@ public:
   void stop();                                 // flush + drain; the last processor to stop ends the run
   // per-position RS memory factor of one link, by FRAME channel (src/wibeth/WIBEthFrameProcessor.cpp:437-456 + setState)
   void set_link_memory_factor(uint32_t link, const uint16_t* by_channel, uint32_t n_channels);
-  bool submit(uint32_t link, const void* unit, size_t bytes); // false = back-pressure
+  // false = back-pressure (the link's ring is full). wait_us > 0: sleep up to that long for room first (swtpg_submit_wait)
+  bool submit(uint32_t link, const void* unit, size_t bytes, uint64_t wait_us = 0);
   // Zero-copy ingest: the latency buffer(s) the constframeptrs point into (swtpg_register_buffer). After conf().
   void register_latency_buffer(void* base, size_t bytes);
   void unregister_latency_buffer(void* base);
-  void drain(bool wait = false);               // poll completed batches and hand TPs to their processors
+  // TPs of completed batches -> process_swtpg_hits of their links' processors. While the engine runs this is the job of its
+  // own delivery thread (swtpg_poll_wait: asleep until a batch completes), so no link thread ever polls or contends for it;
+  // drain(true) is what stop() uses: flush, then deliver until the library reports nothing pending, in flight or ready.
+  void drain(bool wait = false);
   swtpg_handle* handle() { return m_h; }
   uint32_t n_links() const { return m_cfg.n_links; }
 
@@ -239,8 +250,11 @@ private:
   std::vector<FrameProcessorBase*> m_procs;
   std::mutex m_mu, m_drain_mu;
   uint32_t m_started = 0;
-  std::vector<swtpg_tp> m_buf;
-  std::vector<uint16_t> m_rs_factor; // [n_links][channels]
+  std::vector<swtpg_tp> m_buf, m_sorted;
+  std::vector<uint32_t> m_link_count;
+  std::thread m_delivery;
+  std::atomic<bool> m_delivery_quit{ false };
+  size_t deliver_once(uint64_t wait_us);
 };
 
 class FrameProcessorBase
@@ -301,10 +315,14 @@ private:
   std::set<uint32_t> m_channel_mask_set;
   uint32_t m_crate_no = 0, m_slot_no = 0, m_stream_id = 0, m_det_id = 0;
   std::array<uint32_t, 64> m_register_channels{};
-  std::map<uint32_t, int> m_tp_channel_rate_map;
+  // m_tp_channel_rate_map of the reference (:263-284), kept as one counter per FRAME channel (the key of every record) and
+  // turned into (offline channel -> count) pairs in get_info; the channel mask likewise is looked up once per channel
+  std::array<std::atomic<uint32_t>, 64> m_tp_channel_rate{};
+  std::array<uint32_t, 64> m_offline_of_channel{};
+  std::array<uint8_t, 64> m_masked{};
+  std::atomic<bool> m_maps_ready{ false };
   std::mutex m_rate_mu;
   std::vector<LinkMisconfiguration> m_misconf;
-  uint32_t m_frames_since_drain = 0;
 
   uint64_t m_previous_ts = 0, m_current_ts = 0;
   uint16_t m_previous_seq_id = 0, m_current_seq_id = 0;
@@ -355,8 +373,9 @@ private:
   std::set<uint32_t> m_channel_mask_set;
   uint32_t m_crate_no = 0, m_slot_no = 0, m_link = 0, m_det_id = 0;
   std::array<uint32_t, 256> m_register_channels{};
-  uint32_t m_frames_since_drain = 0;
-  std::map<uint32_t, int> m_tp_channel_rate_map;
+  std::array<std::atomic<uint32_t>, 256> m_tp_channel_rate{};
+  std::array<uint8_t, 256> m_masked{};
+  std::atomic<bool> m_maps_ready{ false };
   std::mutex m_rate_mu;
   uint64_t m_previous_ts = 0, m_current_ts = 0;
   bool m_first_ts_missmatch = true;

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define SWTPG_ABI_VERSION 1u
+#define SWTPG_ABI_VERSION 2u
 
 /* Frame geometry restated from the reference (sizes pinned by static_asserts there). */
 #define SWTPG_WIBETH_FRAME_BYTES 7200u /* include/fdreadoutlibs/DUNEWIBEthTypeAdapter.hpp:20-22,98 */
@@ -98,6 +98,8 @@ typedef struct swtpg_config
   uint8_t reserved0[3];
   uint32_t wib2_adc_offset;  /* byte offset of adc_words inside a WIB2 frame; 0 = 20 */
   uint32_t flags;            /* SWTPG_FLAG_* */
+  uint32_t dispatch_timeout_us; /* streaming path: units that have waited this long are dispatched even if no link has a full
+                                   superchunk yet (a stalled or dead link never holds the others back); 0 = 5000 */
 } swtpg_config;
 
 #define SWTPG_FLAG_NONE 0u
@@ -149,6 +151,10 @@ swtpg_status swtpg_stop(swtpg_handle* h);
 /* Per-position RS memory factor of AbsRS / StandardRS, by frame channel: [n_links][channels]
  * (src/wibeth/WIBEthFrameProcessor.cpp:437-456). NULL = cfg.rs_memory_factor everywhere. Call before the first unit. */
 swtpg_status swtpg_set_rs_memory_factor(swtpg_handle* h, const uint16_t* by_link_channel);
+/* The same for ONE link: by_channel[channels]. This is what a frame processor calls from find_hits on its first frame
+ * (WIBEthFrameProcessor.cpp:437-456 runs per link): one small asynchronous copy ordered on the compute stream, thread-safe
+ * against the other links' calls and against batches in flight. */
+swtpg_status swtpg_set_link_rs_memory_factor(swtpg_handle* h, uint32_t link, const uint16_t* by_channel);
 
 /*
  * Batch entry points. `frames` is link-major: unit u of link l starts at ((l * units_stride) + u) * unit_bytes.
@@ -184,31 +190,52 @@ swtpg_status swtpg_process_host_debug(swtpg_handle* h, const void* frames, const
 
 /*
  * Streaming entry points: what a FrameProcessor's post-processing thread calls once per payload.
- * swtpg_submit copies one unit of `link` into the pinned staging slot being filled (the reference's constframeptr
- * is only borrowed for the duration of find_hits). When every link of the handle has delivered cfg.max_units
- * units — or on swtpg_flush — the slot is dispatched: async H2D, kernel, async D2H of the TP list, on the slot's
- * stream. Never blocks: SWTPG_ERR_BUSY when all slots are in flight. One thread per link, any number of links
- * concurrently. swtpg_poll hands back the TPs of completed batches, oldest first, without blocking; it replaces
- * the per-hit m_tp_sink->try_send loop's source (src/wibeth/WIBEthFrameProcessor.cpp:555).
+ *
+ * Every link owns a ring of n_slots * max_units pending units. swtpg_submit appends one unit of `link` to that link's ring —
+ * the payload's address if it lies in a latency buffer registered with swtpg_register_buffer (zero-copy), else a copy of it
+ * in the link's pinned staging ring (the reference's constframeptr is only borrowed for the duration of find_hits) — and
+ * returns; it takes no lock and never blocks: SWTPG_ERR_BUSY when that link's ring is full (the reference's failed try_send).
+ * One producer thread per link at a time, any number of links concurrently.
+ *
+ * A dispatcher thread inside the library turns pending units into batches: as soon as ANY link has a full superchunk
+ * (cfg.max_units units), or pending units have waited cfg.dispatch_timeout_us, or on swtpg_flush, every link contributes what
+ * it has delivered so far (0 .. max_units units: batches are ragged, per-link state is carried from batch to batch exactly as
+ * ProcessingInfo carries it from frame to frame). So links advance independently; a silent link does not hold back the TPs
+ * of the others. A batch is: ONE gather kernel that pulls the units out of pinned host memory through a per-unit pointer
+ * table (no per-link copy calls) -> the fused TPG kernel -> the TP list back to pinned host memory. A completion thread frees
+ * the ring space of a batch as soon as its gather has finished (which also ends the borrow of zero-copy units) and queues
+ * the batch's TPs; swtpg_poll hands them out, oldest batch first. It replaces the per-hit m_tp_sink->try_send loop's source
+ * (src/wibeth/WIBEthFrameProcessor.cpp:555). At most n_slots batches exist at a time: un-polled TPs back-pressure the ring.
  */
 swtpg_status swtpg_submit(swtpg_handle* h, uint32_t link, const void* unit, size_t bytes);
+/* Like swtpg_submit, but waits (sleeping, not spinning) up to timeout_us for room in the link's ring; SWTPG_ERR_BUSY on
+ * time-out. For file replay and emulators, where stalling the source is right and dropping frames is not. */
+swtpg_status swtpg_submit_wait(swtpg_handle* h, uint32_t link, const void* unit, size_t bytes, uint64_t timeout_us);
 /*
  * Zero-copy ingest. The constframeptr a post-processing task receives points INTO the link's latency buffer
  * (readoutlibs IterableQueueModel / FixedRateQueueModel: one contiguous array of payloads; SURVEY.md 8b "Ownership").
- * Registering that array here (cudaHostRegister) makes swtpg_submit record the pointer instead of copying the payload:
- * when the batch is dispatched the copy engine reads the units where they lie, one async copy per link and contiguous
- * run (a superchunk is one run unless the buffer wrapped inside it). Units outside every registered range are still
- * copied, so both kinds may be mixed. Contract: a submitted unit must stay unmodified until its batch's host-to-device
- * copy has completed — at most n_slots superchunks after the submit, milliseconds against a latency buffer's seconds of
- * retention; swtpg_sync (or stop) ends every such borrow. Any number of ranges (one per link is typical).
- * swtpg_unregister_buffer waits for the handle to drain first.
+ * Registering that array here (cudaHostRegister, mapped) makes swtpg_submit record the payload's address instead of copying
+ * it: the batch's gather kernel reads the unit where it lies, over the host link. Units outside every registered range (or
+ * not 16-byte aligned) are still copied, so both kinds may be mixed. Contract: a submitted unit must stay unmodified until
+ * its batch's gather has completed — at most n_slots superchunks after the submit, milliseconds against a latency buffer's
+ * seconds of retention; swtpg_flush + swtpg_sync (or stop) end every such borrow. Any number of ranges (one per link is
+ * typical). swtpg_unregister_buffer flushes and waits for the handle to drain first.
  */
 swtpg_status swtpg_register_buffer(swtpg_handle* h, void* base, size_t bytes);
 swtpg_status swtpg_unregister_buffer(swtpg_handle* h, void* base);
+/* Dispatches everything submitted so far (ragged batch), returns when it has been handed to the device. Safe against
+ * concurrent swtpg_submit calls (units submitted meanwhile may or may not be included). SWTPG_ERR_BUSY if all n_slots
+ * batches hold TPs nobody has polled yet: poll, then flush again. */
 swtpg_status swtpg_flush(swtpg_handle* h);
+/* TPs of completed batches, oldest first, without blocking. *n_out = records written (<= cap); call again for more. */
 swtpg_status swtpg_poll(swtpg_handle* h, swtpg_tp* out, size_t cap, size_t* n_out);
+/* The same, but sleeps up to timeout_us until at least one completed batch is available. */
+swtpg_status swtpg_poll_wait(swtpg_handle* h, swtpg_tp* out, size_t cap, size_t* n_out, uint64_t timeout_us);
 /* Blocks until every dispatched batch has completed (used by stop and by tests). */
 swtpg_status swtpg_sync(swtpg_handle* h);
+/* Streaming path bookkeeping: units submitted but not yet dispatched, batches dispatched but not yet completed, completed
+ * batches waiting for swtpg_poll. Any pointer may be NULL. */
+swtpg_status swtpg_stream_status(swtpg_handle* h, uint64_t* units_pending, uint32_t* batches_in_flight, uint32_t* batches_ready);
 
 /* Carried state of one link, by frame channel (ChanState parity). out has SWTPG_*_CHANNELS entries. */
 swtpg_status swtpg_dump_state(swtpg_handle* h, uint32_t link, swtpg_channel_state* out);

@@ -1,5 +1,5 @@
 /*
- * swtpg_framegen.h — synthetic WIBEth / WIB2 frame generator exported by libswtpg_b200.so.
+ * swtpg_framegen.h — synthetic WIBEth / WIB2 frame generator exported by libswtpg_framegen.so (its own small library).
  *
  * Test / benchmark utility, NOT a reference interface (the reference replays recorded files through an emulator that
  * is absent from the snapshot, docs/README.md:20-48). Host and device variants produce byte-identical frames

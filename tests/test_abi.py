@@ -8,34 +8,38 @@ import numpy as np
 import pytest
 
 import fdreadoutlibs_b200 as S
-from fdreadoutlibs_b200 import _lib
+from fdreadoutlibs_b200 import _lib, framegen
 from fdreadoutlibs_b200 import frames as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    names = set()
-    for hdr in ("swtpg.h", "swtpg_framegen.h"):
-        text = open(os.path.join(ROOT, "include", hdr)).read()
-        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-        names |= set(re.findall(r"\b(swtpg_[a-z0-9_]+)\s*\(", text))
-    return names
+def declared_symbols(hdr):
+    text = open(os.path.join(ROOT, "include", hdr)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"\b(swtpg_[a-z0-9_]+)\s*\(", text))
 
 
 def test_every_declared_symbol_is_exported_and_bound():
-    names = declared_symbols()
-    assert len(names) >= 25
+    """include/swtpg.h <-> libswtpg_b200.so, include/swtpg_framegen.h <-> libswtpg_framegen.so (the generator is a test / bench
+    utility in its own library, so that CPU-side checkers never map the CUDA product library)."""
+    names = declared_symbols("swtpg.h")
+    assert len(names) >= 28
     for n in sorted(names):
-        assert hasattr(_lib.lib, n), f"{n} declared in include/ but not exported by libswtpg_b200.so"
-    assert names == set(_lib.EXPORTS), f"binding and headers differ: {names ^ set(_lib.EXPORTS)}"
+        assert hasattr(_lib.lib, n), f"{n} declared in include/swtpg.h but not exported by libswtpg_b200.so"
+    assert names == set(_lib.EXPORTS), f"binding and header differ: {names ^ set(_lib.EXPORTS)}"
+    gen = declared_symbols("swtpg_framegen.h")
+    for n in sorted(gen):
+        assert hasattr(framegen.lib, n), f"{n} declared in include/swtpg_framegen.h but not exported by libswtpg_framegen.so"
+        assert not hasattr(_lib.lib, n), f"{n}: the generator must not live in the product library"
+    assert gen == set(framegen.EXPORTS), f"binding and header differ: {gen ^ set(framegen.EXPORTS)}"
 
 
 def test_abi_version_and_layouts():
-    assert _lib.lib.swtpg_abi_version() == 1
+    assert _lib.lib.swtpg_abi_version() == 2
     assert F.TP_DTYPE.itemsize == 32
-    assert C.sizeof(_lib.SwtpgConfig) == 68  # static_assert'ed on the C side (swtpg_capi.cu)
-    assert C.sizeof(_lib.GenParams) == 32
+    assert C.sizeof(_lib.SwtpgConfig) == 72  # static_assert'ed on the C side (swtpg_capi.cu)
+    assert C.sizeof(framegen.GenParams) == 32
     assert F.STATE_DTYPE.itemsize == 48
     assert _lib.lib.swtpg_status_string(3) == b"busy (back-pressure)"
 
@@ -159,7 +163,7 @@ def test_header_is_plain_c_and_links(tmp_path):
         "  cfg.struct_size = sizeof cfg;\n"
         "  if (swtpg_abi_version() != SWTPG_ABI_VERSION) return 1;\n"
         "  if (swtpg_firwin_int(7, 0.1, 64, taps) != 7 || taps[3] != 20) return 2;\n"
-        "  if (sizeof(swtpg_tp) != 32 || sizeof cfg != 68) return 3;\n"
+        "  if (sizeof(swtpg_tp) != 32 || sizeof cfg != 72) return 3;\n"
         '  printf("%s\\n", swtpg_status_string(SWTPG_ERR_BUSY));\n'
         "  return 0;\n}\n")
     lib_dir = os.path.join(root, "fdreadoutlibs_b200")

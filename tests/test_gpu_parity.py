@@ -1,5 +1,7 @@
 """GPU (B200): parity of the CUDA path — always called through the C ABI (include/swtpg.h) — against the CPU oracle and the
 reference-generated golden vectors. Bit-exact: TP field tuples, carried state, pedestal and waveform dumps."""
+import time
+
 import numpy as np
 import pytest
 
@@ -373,24 +375,114 @@ def test_streaming_zero_copy_from_a_registered_latency_buffer():
 
 
 def test_streaming_links_out_of_step():
-    """Links are fed by independent threads: one link may run a whole superchunk ahead of the others."""
+    """Links are fed by independent threads and advance independently: a link that runs superchunks ahead of the others gets its
+    TPs while the others are still silent (batches are ragged; there is no all-links barrier), and nothing is lost or
+    reordered per link when the stragglers arrive."""
     n_links, n_units, sc = 3, 8, 4
     units = S.gen_wibeth_host(S.gen_params(46, 0.5), n_links, n_units)
-    want, _ = B.oracle_process_links(B.make_config(threshold=20), units)
-    got = []
+    cfg = B.make_config(threshold=20)
+    want, _ = B.oracle_process_links(cfg, units)
+    want0 = B.Oracle(cfg, link_id=0).process(units[0])
     with S.TPGenerator(n_links, sc, threshold=20, n_slots=2) as g:
         g.start()
-        for u in range(n_units):  # link 0 first, all of it
-            assert g.submit(0, units[0, u])
-        assert not g.submit(0, units[0, 0])  # third superchunk of link 0: both slots still filling -> BUSY, not blocked
+        for u in range(n_units):  # link 0 first, all of it; links 1 and 2 deliver nothing yet
+            assert g.submit(0, units[0, u], wait_us=2_000_000)
+        first = g.drain()
+        assert_same_tps(first, want0, "link 0 alone")
         for l in (1, 2):
             for u in range(n_units):
+                assert g.submit(l, units[l, u], wait_us=2_000_000)
+        rest = g.drain()
+        assert g.counters()["units_processed"] == n_links * n_units
+    assert_same_tps(np.concatenate([first, rest]), want, "out of step")
+
+
+def test_streaming_back_pressure_is_busy_not_blocking():
+    """Nobody polls: after n_slots batches hold un-polled TPs the dispatcher stalls, the link's ring (n_slots superchunks)
+    fills up and swtpg_submit answers BUSY instead of blocking; flush reports the same condition. Polling releases everything."""
+    n_slots, sc = 2, 4
+    units = S.gen_wibeth_host(S.gen_params(48, 0.5), 1, 6 * sc)
+    want = B.Oracle(B.make_config(threshold=20)).process(units[0])
+    got = []
+    with S.TPGenerator(1, sc, threshold=20, n_slots=n_slots) as g:
+        g.start()
+        accepted = 0
+        for u in range(units.shape[1]):
+            for _ in range(200):  # up to 200 ms per unit for batches to be dispatched and rings to be released
+                if g.submit(0, units[0, u]):
+                    accepted += 1
+                    break
+                time.sleep(0.001)
+            else:
+                break
+        assert n_slots * sc <= accepted <= 2 * n_slots * sc, accepted  # n_slots batches + at most one ring of pending units
+        assert accepted < units.shape[1]
+        assert g.counters()["submit_busy"] > 0
+        assert not g.flush()  # every batch waits to be polled
+        got.append(g.drain())
+        for u in range(accepted, units.shape[1]):
+            assert g.submit(0, units[0, u], wait_us=2_000_000)
+        got.append(g.drain())
+    assert_same_tps(np.concatenate(got), want, "after back-pressure")
+
+
+def test_streaming_partial_superchunks_go_out_after_the_timeout():
+    """No link ever fills a superchunk and nobody flushes: pending units are dispatched after dispatch_timeout_us."""
+    n_links, n_units = 4, 5
+    units = S.gen_wibeth_host(S.gen_params(49, 0.5), n_links, n_units)
+    want, _ = B.oracle_process_links(B.make_config(threshold=20), units)
+    got = []
+    with S.TPGenerator(n_links, 64, threshold=20, dispatch_timeout_us=20_000) as g:
+        g.start()
+        for u in range(n_units):
+            for l in range(n_links):
                 assert g.submit(l, units[l, u])
+        deadline = time.time() + 5.0
+        while g.counters()["units_processed"] < n_links * n_units and time.time() < deadline:
+            got.append(g.poll(wait_us=50_000))
+        assert g.counters()["units_processed"] == n_links * n_units
         g.sync()
         for _ in range(4):
             got.append(g.poll())
-        assert g.counters()["submit_busy"] == 1
-    assert_same_tps(np.concatenate(got), want, "out of step")
+    assert_same_tps(np.concatenate(got), want, "time-out dispatch")
+
+
+def test_streaming_concurrent_feeders_and_flushes():
+    """Feeder threads submit while another thread keeps flushing (a watchdog): flush is safe against concurrent submits."""
+    import threading
+
+    n_links, n_units, sc = 12, 96, 8
+    units = S.gen_wibeth_host(S.gen_params(50, 0.3), n_links, n_units)
+    want, _ = B.oracle_process_links(B.make_config(threshold=25), units)
+    got, stop = [], threading.Event()
+    with S.TPGenerator(n_links, sc, threshold=25, n_slots=3) as g:
+        g.start()
+
+        def feed(t):
+            for u in range(n_units):
+                for l in range(t, n_links, 3):
+                    assert g.submit(l, units[l, u], wait_us=5_000_000)
+
+        def watchdog():
+            while not stop.is_set():
+                g.flush()
+                time.sleep(0.0005)
+
+        def poller():
+            while not stop.is_set():
+                got.append(g.poll(wait_us=2000))
+
+        th = [threading.Thread(target=feed, args=(t,)) for t in range(3)] + [threading.Thread(target=watchdog), threading.Thread(target=poller)]
+        for t in th:
+            t.start()
+        for t in th[:3]:
+            t.join()
+        stop.set()
+        for t in th[3:]:
+            t.join()
+        got.append(g.drain())
+        assert g.counters()["units_processed"] == n_links * n_units
+    assert_same_tps(np.concatenate(got), want, "concurrent feeders + flushes")
 
 
 def test_tp_buffer_overflow_is_reported():

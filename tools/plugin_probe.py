@@ -1,25 +1,44 @@
-"""Plug-in streaming path probe (tuning aid): python tools/plugin_probe.py LINKS SUPERCHUNK ZERO_COPY [SLOTS]"""
-import sys, time
+"""Plug-in streaming path probe (tuning aid / profiles/r02_plugin_probe.txt):
+  python tools/plugin_probe.py LINKS SUPERCHUNK ZERO_COPY THREADS [BURST] [PACE] [UNITS] [PASSES]
+THREADS feeder threads serve LINKS links round-robin through WIBEthFrameProcessor (sequence_check, timestamp_check, find_hits);
+ZERO_COPY=1 registers the payload array as the latency buffer; PACE > 0 runs against the clock at that multiple of real time."""
+import resource
+import sys
+import time
+
 sys.path.insert(0, '.')
 import numpy as np
+
 import fdreadoutlibs_b200 as S
 from fdreadoutlibs_b200 import hostshim as H
-links, sc, zc = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-units, passes = 2048, 4
-h = S.gen_wibeth_host(S.gen_params(2, 0.02), links, units, n_threads=8)
-with H.FrameProcessors(links, sc, threshold=60, emulator_mode=True, block_on_backpressure=True) as fp:
+
+links, sc, zc, threads = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+burst = int(sys.argv[5]) if len(sys.argv) > 5 else 16
+pace = float(sys.argv[6]) if len(sys.argv) > 6 else 0.0
+units = int(sys.argv[7]) if len(sys.argv) > 7 else 1024
+passes = int(sys.argv[8]) if len(sys.argv) > 8 else 4
+buf = S.PinnedBuffer(links * units * 7200) if zc == 2 else None  # 2: cudaHostAlloc'ed latency buffer instead of cudaHostRegister
+h = S.gen_wibeth_host(S.gen_params(2, 0.02), links, units, n_threads=8, out=None if buf is None else buf.array)
+with H.FrameProcessors(links, sc, threshold=60, emulator_mode=True, block_on_backpressure=pace == 0, count_only_sink=True) as fp:
     if zc:
         fp.register_buffer(h)
     fp.start()
-    fp.push_parallel(h[:, :256].copy())
-    c0, t0 = time.process_time(), time.perf_counter()
-    n = 0
-    for _ in range(passes):
-        fp.push_parallel(h)
-        n += sum(fp.take_tps(l, cap=1 << 15).size for l in range(links))
+    fp.push_feeders(h[:, :128].copy(), n_threads=threads, burst=burst)  # warm-up: engine creation, first launches
+    time.sleep(0.05)
+    r0, t0 = resource.getrusage(resource.RUSAGE_SELF), time.perf_counter()
+    st = fp.push_feeders(h, n_threads=threads, burst=burst, pace=pace, passes=passes)
+    t_feed = time.perf_counter() - t0
     fp.stop()
-    dt, cpu = time.perf_counter() - t0, time.process_time() - c0
+    dt = time.perf_counter() - t0
+    r1 = resource.getrusage(resource.RUSAGE_SELF)
+    cpu = (r1.ru_utime - r0.ru_utime) + (r1.ru_stime - r0.ru_stime)
+    dropped = sum(fp.get_info(l)["num_frames_dropped_busy"] for l in range(links))
+    tps = fp.tp_count()
     if zc:
         fp.register_buffer(h, on=False)
-print(f"links={links} sc={sc} zero_copy={zc}: {passes*links*units*7200/dt/1e9:.1f} GB/s  wall {dt*1e3:.0f} ms  cpu {cpu*1e3:.0f} ms  ({cpu/dt:.1f} cores busy)  "
-      f"{dt/(passes*units*links)*1e6*min(links,16):.2f} us/frame/core", flush=True)
+n = passes * links * units
+apas = links / 40
+print(f"links={links} sc={sc} zero_copy={zc} threads={threads} burst={burst} pace={pace}: {n*7200/dt/1e9:.1f} GB/s ({n*4096/dt/1e9:.1f} Gsamples/s = "
+      f"{n*4096/dt/5e9:.2f} real-time APAs)  wall {dt*1e3:.0f} ms (feed {t_feed*1e3:.0f})  process cpu {cpu*1e3:.0f} ms = {cpu/dt:.2f} cores busy, "
+      f"feeders {st['feeder_cpu_s']/dt:.2f} cores = {st['feeder_cpu_s']/n*1e6:.3f} us/frame  host core-s per APA-s {cpu/dt/ (n*4096/dt/5e9):.3f}  "
+      f"tps={tps} dropped={dropped} late_bursts={st['late_bursts']}", flush=True)
