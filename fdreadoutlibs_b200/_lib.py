@@ -44,7 +44,7 @@ class SwtpgConfig(C.Structure):
 class SwtpgCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "units_processed", "samples_processed", "tps_emitted", "tps_dropped_overflow", "batches", "submit_busy",
-        "h2d_bytes", "d2h_bytes")]
+        "h2d_bytes", "d2h_bytes", "units_zero_copy", "units_staged")]
 
 
 # every symbol include/swtpg.h declares

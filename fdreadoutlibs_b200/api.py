@@ -205,9 +205,10 @@ class TPGenerator:
     def unregister_buffer(self, buf: np.ndarray):
         self._check(lib.swtpg_unregister_buffer(self._h, buf.ctypes.data))
 
-    def flush(self) -> bool:
-        """Dispatch everything submitted so far. False = every batch holds un-polled TPs (poll, then flush again)."""
-        return self._check(lib.swtpg_flush(self._h), allow=(SWTPG_ERR_BUSY,)) == SWTPG_OK
+    def flush(self, busy_ok: bool = False) -> bool:
+        """Dispatch everything submitted so far. SWTPG_ERR_BUSY — every batch holds un-polled TPs: poll, then flush again —
+        raises unless busy_ok, in which case it is reported as False (drain() loops on it)."""
+        return self._check(lib.swtpg_flush(self._h), allow=(SWTPG_ERR_BUSY,) if busy_ok else ()) == SWTPG_OK
 
     def sync(self):
         self._check(lib.swtpg_sync(self._h))
@@ -225,7 +226,7 @@ class TPGenerator:
         """flush + sync + poll until nothing is left: every TP of everything submitted so far."""
         got = []
         while True:
-            done = self.flush()
+            done = self.flush(busy_ok=True)
             self.sync()
             while True:
                 part = self.poll()

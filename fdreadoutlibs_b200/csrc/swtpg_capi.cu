@@ -24,7 +24,7 @@ using swtpg_internal::fail;
 static_assert(sizeof(swtpg_tp) == 32, "swtpg_tp must stay 32 bytes (two 16-byte device stores)");
 static_assert(sizeof(swtpg_config) == 72, "swtpg_config layout changed: bump SWTPG_ABI_VERSION and the bindings");
 static_assert(sizeof(swtpg_channel_state) == 48, "swtpg_channel_state layout changed");
-static_assert(sizeof(swtpg_counters) == 64, "swtpg_counters layout changed");
+static_assert(sizeof(swtpg_counters) == 80, "swtpg_counters layout changed");
 
 namespace {
 thread_local std::string g_create_error;
@@ -147,10 +147,27 @@ launch_wibeth_quad(const KernelParams& kp, cudaStream_t s)
 // for FIR + IQR (ptxas needs 64 registers instead of 109 for it, so 20 consumer warps fit an SM), the one-warp-per-CTA form
 // 2-5 % faster for SimpleThreshold and the running sums (the quad's lock-step costs more than the producer bookkeeping it
 // saves). SWTPG_WIBETH_KERNEL=warp forces the latter.
+// WIBEth SimpleThreshold, the production algorithm, runs the software-pipelined form of its policy (prefetch + deferred quiet
+// test, PackedSimpleT<true>) on the one-warp-per-CTA kernel with 16 persistent warps per SM. Measured against the straight-line
+// form (profiles/r02_simple_pipeline_sweep.txt): faster at every link count below a full GPU — a warp that has its scheduler
+// (almost) to itself runs at the speed of its dependent chain: 40 links +18 %, 750 links +12 %, 3000 links +7 % — and equal
+// at 5920 links, where its 88 registers (against 70) want 4 warps per sub-partition instead of 5: 66.3 % of the HBM peak
+// against 64.6 %. A deeper ring (4 stages) never helps: not even a lone warp is bound by the copy engine's latency.
+// SWTPG_SIMPLE_PIPE=0 selects the straight-line form (tuning aid).
+template<bool DUMP>
+cudaError_t
+launch_wibeth_simple(const KernelParams& kp, cudaStream_t s)
+{
+  static const bool straight = [] { const char* e = getenv("SWTPG_SIMPLE_PIPE"); return e && atoi(e) == 0; }();
+  return straight ? launch_wibeth_geo<PackedSimpleWibEth, DUMP, GeoDefault>(kp, s) : launch_wibeth_geo<PackedSimpleWibEthPipe, DUMP, GeoDefault>(kp, s);
+}
+
 template<class Algo, bool DUMP>
 cudaError_t
 launch_wibeth(const KernelParams& kp, cudaStream_t s)
 {
+  if constexpr (std::is_same<Algo, PackedSimpleWibEth>::value && Algo::kQuadCtasPerSm == 0)
+    return launch_wibeth_simple<DUMP>(kp, s);
   if constexpr (Algo::kQuadCtasPerSm > 0) {
     static const bool warp_form = [] {
       const char* e = getenv("SWTPG_WIBETH_KERNEL");
@@ -396,6 +413,8 @@ swtpg_internal::launch_batch_kernel(swtpg_handle* h, const void* d_frames, const
   const KernelParams kp = make_params(h, d_frames, d_nunits, units_stride, d_tps, d_count, nullptr, nullptr);
   return launch<false>(h, kp, s);
 }
+
+extern "C" void swtpg_internal_ingest_counts(swtpg_handle* h, uint64_t* zero_copy, uint64_t* staged); // swtpg_stream.cu
 
 extern "C" {
 
@@ -927,6 +946,7 @@ swtpg_get_counters(swtpg_handle* h, swtpg_counters* out)
   out->submit_busy = h->counters.submit_busy.load();
   out->h2d_bytes = h->counters.h2d_bytes.load();
   out->d2h_bytes = h->counters.d2h_bytes.load();
+  swtpg_internal_ingest_counts(h, &out->units_zero_copy, &out->units_staged);
   return SWTPG_OK;
 }
 

@@ -310,6 +310,23 @@ extract_pair(const uint32_t* row, const PairPos& pp)
 #endif
 }
 
+// The same pair with 0x4000 subtracted from each half (bits 14 and 15 forced to one: S - 16384 in two's complement), at the same
+// cost — SHF + shift + 2 LOP3. The packed SimpleThreshold / running-sum policies keep "16385 - median" instead of "1 - median",
+// so that the median register never passes through 0x0000 / 0xFFFF and its +-1 steps can be ONE 32-bit three-input add
+// (no carry or borrow ever crosses the halves); the bias cancels in S' + Mq' = s - median + 1.
+__device__ __forceinline__ uint32_t
+extract_pair_biased_from(uint32_t lo_word, uint32_t hi_word, uint32_t sh)
+{
+  const uint32_t x = __funnelshift_r(lo_word, hi_word, sh);
+  const uint32_t u = x | 0xFFFFC000u;            // low half: field 0 | 0xC000; high half: all ones
+  return u & ((x << 2) | 0xC000FFFFu);           // high half: field 1 | 0xC000; low half kept
+}
+__device__ __forceinline__ uint32_t
+extract_pair_biased(const uint32_t* row, const PairPos& pp)
+{
+  return extract_pair_biased_from(row[pp.w0], row[pp.w1], pp.sh);
+}
+
 // ---- TP emission -----------------------------------------------------------------------------------------------------
 struct TpSink
 {

@@ -208,6 +208,11 @@ struct ScalarAlgo
   }
   __device__ __forceinline__ uint32_t phase_after(uint32_t ticks) const { return (kphase + ticks) & 7u; }
   __device__ __forceinline__ void configure(const KernelParams&) {}
+  static __device__ __forceinline__ uint32_t sample(const uint32_t* row, const PairPos& pp) { return extract_pair(row, pp); }
+  template<int ROW_WORDS = 28>
+  __device__ __forceinline__ void begin_chunk(const uint32_t*, const PairPos&) {}
+  template<bool WIB2_UNITS = false>
+  __device__ __forceinline__ void finish_link(const TickCtx&) {}
   template<bool WIB2_UNITS>
   static __device__ __forceinline__ void flush(const HitStage&, const TpSink&, const uint8_t*, uint32_t, uint32_t, bool = true) {} // emits directly
 
@@ -225,7 +230,7 @@ struct ScalarAlgo
 
   template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
   __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
-                                        uint32_t* wav_out)
+                                        uint32_t* wav_out, bool /*more*/)
   {
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -397,46 +402,64 @@ struct ScalarAlgo
 };
 
 // =====================================================================================================================
-// Packed fast path: WIBEth SimpleThreshold (wibeth/tpg/ProcessAVX2.hpp:23-229), two channels per 32-bit register.
+// Packed fast path: SimpleThreshold on either frame layout (wibeth/tpg/ProcessAVX2.hpp:23-229, wib2/tpg/ProcessAVX2.hpp:24-200),
+// two channels per 32-bit register.
 // Validity (checked by the host before selecting it): 1 <= L <= 1000 and 0 <= threshold <= 32767.
 //   * median m stays in [0, 16383] (it only ever steps towards samples, which are 14-bit), so adds_epi16 on it never
 //     saturates;
 //   * with a constant L >= 1 the accumulator is in [-L, L] between ticks, so "acc > L" <=> acc == L+1 and
-//     "-acc > L" <=> acc == -(L+1): both become add+clamp (VIADDMNMX) results in {0,1} / {0,-1};
+//     "-acc > L" <=> acc == -(L+1);
 //   * pedestal-subtracted samples s' are in [-16383, 16383] and threshold / peak_adc are non-negative, which is the
 //     operand range gt2_mask_nonneg requires.
-// Register forms (every update is an add: VIADD.16x2 has no subtract form):
-//   Mq  = 1 - median         so that  S + Mq = s' + 1  ("sp1": the pedestal-subtracted sample, biased by one) and
-//                            clamp(S + Mq, 0, 2) = sign(s - m) + 1 is a single VIADDMNMX.S16x2.RELU;
-//   PK1 = peak_adc + 1       compared against sp1;   thr1 = threshold + 1 likewise;
-//   Tn  = -tover, PTn = -peak_time.
+// Register forms:
+//   Sb  = S - 16384           the sample as extract_pair_biased delivers it (bits 14, 15 forced to one), and
+//   Mq  = 16385 - median      so that  Sb + Mq = s' + 1  ("sp1": the pedestal-subtracted sample, biased by one),
+//                             clamp(Sb + Mq, 0, 2) = sign(s - m) + 1 is a single VIADDMNMX.S16x2.RELU, and Mq stays in
+//                             [2, 16385]: it never passes through 0x0000 / 0xFFFF, so its +-1 steps are ONE 32-bit
+//                             three-input add (IADD3) — no carry or borrow can cross the halves;
+//   A   = accumulator - 1     as the bit pattern of an fp16x2 subnormal (value * 2^-24, sign-magnitude: exact integer
+//                             arithmetic for |v| <= 1023 on the FMA pipe);
+//   PK1 = peak_adc + 1        compared against sp1;   thr1 = threshold + 1 likewise;   Tn = -tover, PTn = -peak_time.
+// The recurrence median(t) -> median(t+1) is the critical path of a link (time is sequential per channel): VIADDMNMX ->
+// HADD2 -> HFMA2.SAT -> IADD3, four dependent instructions per tick (round 1: five). Everything else is taken off that
+// path by a two-stage software pipeline inside group(): the raw words of the NEXT group's rows are loaded before this
+// group's arithmetic starts (prefetch across the quiet-test branch), and the quiet test / hit bookkeeping of a group is
+// DEFERRED by one group, so that it is scheduled in the shadow of the next group's pedestal chain.
 // =====================================================================================================================
-struct PackedSimpleWibEth
+// PIPE = true: the two-stage software pipeline (for launches that cannot fill the GPU: a warp alone on its scheduler runs at
+// the speed of its dependent chain); PIPE = false: straight-line groups, fewer registers and instructions (for full launches,
+// where the other warps of the sub-partition hide the latencies anyway). The host picks per launch (swtpg_capi.cu).
+template<bool PIPE>
+struct PackedSimpleT
 {
   static constexpr int kGroupUnroll = SWTPG_GROUP_UNROLL;
-  static constexpr int kWarpsPerSm = 20; // measured best on B200 (profiles/r01_warps_sweep.txt): 5 warps per sub-partition
+  // persistent warps per SM, measured: 5 per sub-partition for the straight-line form (profiles/r01_warps_sweep.txt), 4 for the
+  // pipelined one (88 registers; profiles/r02_simple_pipeline_sweep.txt)
+  static constexpr int kWarpsPerSm = PIPE ? 16 : 20;
   static constexpr int kQuadCtasPerSm = SWTPG_QUAD_SIMPLE; // 0: one warp per CTA (measured faster for this policy)
   static constexpr int kWib2MinCtas = 5;
+  static constexpr bool kWib2Fields = false; // which process_swtpg_hits derives the TP fields (and whether the peak is tracked)
   uint32_t Mq, A, prev, C, Tn, PK1, PTn;
   uint32_t cUp, cDn, thr1;
+  uint32_t shift, shmask; // WIB2 flavour only
+  uint32_t raw[8];        // software pipeline: words of the next group's four rows ...
+  uint32_t dsp[4], dwhen; // ... and the deferred group: its four s' + 1 and (unit << 6 | first tick); dvalid below
+  bool dvalid;
+
+  static __device__ __forceinline__ uint32_t sample(const uint32_t* row, const PairPos& pp) { return extract_pair_biased(row, pp); }
 
   __device__ __forceinline__ void configure(const KernelParams& p)
   {
     const uint32_t L = uint32_t(p.acc_limit) & 0xFFFFu;
-#if SWTPG_FLOAT_ACC
     const uint32_t up = L + 1u;            // acc == L + 1       (as an fp16 subnormal: value * 2^-24 == bit pattern)
-    const uint32_t dn = 0x8000u | L;       // -L: addend of the "acc == -(L+1)" test (sign-magnitude)
-#else
-    const uint32_t up = (0x10000u - (L + 1u)) & 0xFFFFu; // -(L+1): T - (L+1) = acc - L
-    const uint32_t dn = L - 1u;
-#endif
+    const uint32_t dn = 0x8000u | L;       // -L: addend of the "acc - L" / "-acc - L" saturating tests (sign-magnitude)
     cUp = up | (up << 16);
     cDn = dn | (dn << 16);
     uint32_t th = p.threshold > 16383u ? 16383u : p.threshold; // s' <= 16383: any larger threshold is never exceeded
     th += 1u;
     thr1 = th | (th << 16);
+    shift = shmask = 0;
   }
-#if SWTPG_FLOAT_ACC
   // Register form of the accumulator: (acc - 1) as the bit pattern of an fp16x2 subnormal (value * 2^-24, sign-magnitude).
   static __device__ __forceinline__ uint32_t acc_to_reg(uint32_t v)
   {
@@ -451,21 +474,22 @@ struct PackedSimpleWibEth
     const uint32_t m = neg * 0xFFFFu;
     return add2(add2((v & 0x7FFF7FFFu) ^ m, neg), 0x00010001u);
   }
-#else
-  static __device__ __forceinline__ uint32_t acc_to_reg(uint32_t v) { return v; }
-  static __device__ __forceinline__ uint32_t acc_from_reg(uint32_t v) { return v; }
-#endif
   __device__ __forceinline__ void load(const uint32_t* st, uint32_t lane, uint32_t)
   {
-    Mq = add2(~st[SV_MEDIAN * 32 + lane], 0x00020002u); // ~m = -m - 1
+    Mq = add2(~st[SV_MEDIAN * 32 + lane], 0x40024002u); // ~m = -m - 1
     A = acc_to_reg(st[SV_ACCUM * 32 + lane]);
     prev = st[SV_PREV * 32 + lane];
     C = st[SV_CHARGE * 32 + lane];
     Tn = neg2(st[SV_TOVER * 32 + lane]);
     PK1 = add2(st[SV_PEAK_ADC * 32 + lane], 0x00010001u);
     PTn = neg2(st[SV_PEAK_TIME * 32 + lane]);
+    dvalid = false;
+    dwhen = 0u;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      dsp[g] = 0u; // s' = -1: below every threshold and every PK1, so an empty pipeline stage changes nothing
   }
-  __device__ __forceinline__ uint32_t median() const { return add2(~Mq, 0x00020002u); } // 1 - Mq
+  __device__ __forceinline__ uint32_t median() const { return add2(~Mq, 0x40024002u); } // 16385 - Mq
   __device__ __forceinline__ void store(uint32_t* st, uint32_t lane, uint32_t) const
   {
     st[SV_MEDIAN * 32 + lane] = median();
@@ -477,7 +501,7 @@ struct PackedSimpleWibEth
     st[SV_PEAK_TIME * 32 + lane] = neg2(PTn);
   }
   __device__ __forceinline__ uint32_t phase_after(uint32_t) const { return 0; }
-  __device__ __forceinline__ void seed(uint32_t S) { Mq = add2(~S, 0x00020002u); }
+  __device__ __forceinline__ void seed(uint32_t Sb) { Mq = add2(~Sb, 0x00020002u); } // 16385 - S = 1 - Sb
   template<bool WIB2_UNITS>
   static __device__ __forceinline__ void flush(const HitStage& h, const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane,
                                                bool everything = true)
@@ -485,36 +509,27 @@ struct PackedSimpleWibEth
     h.template flush<WIB2_UNITS, false>(k, link_base, link, lane, everything);
   }
 
-  // frugal streaming median (wibeth/tpg/UtilsAVX2.hpp:38-73) + pedestal subtraction (ProcessAVX2.hpp:85): S -> s' + 1
-  __device__ __forceinline__ uint32_t pedestal_step(uint32_t S)
+  // frugal streaming median (wibeth/tpg/UtilsAVX2.hpp:38-73) + pedestal subtraction (ProcessAVX2.hpp:85): Sb -> s' + 1.
+  // The accumulator lives as an fp16x2 subnormal stored minus one, so that adding sign+1 lands on the new value; both step
+  // flags come out of the FMA pipe as the integer bit patterns 0 / 1 (saturating fp16 FMAs of +-acc - L), and the median
+  // takes them in one 32-bit add. The ALU pipe does the sign, one compare and that add.
+  __device__ __forceinline__ uint32_t pedestal_step(uint32_t Sb)
   {
-    const uint32_t sg1 = addclamp2(S, Mq, 0x00020002u); // sign(s - m) + 1 in {0,1,2}
-#if SWTPG_FLOAT_ACC
-    // The accumulator lives as an fp16x2 subnormal (value * 2^-24: exact integer arithmetic for |v| <= 1023, executed by
-    // the FMA pipe), stored minus one so that adding sign+1 lands on the new accumulator value. The ALU pipe only does the
-    // two compares; the down-step flag, the reset and the re-bias are three fp16 FMAs.
-    const uint32_t T = hadd2_bits(A, sg1);              // acc after this sample, in [-(L+1), L+1]
-    const uint32_t upm = eq2_mask(T, cUp);              // 0xFFFF: acc == L+1
-    const uint32_t dn1 = hfma2_sat_bits(T, 0xBC00BC00u, cDn); // sat(-acc - L) -> bit pattern 1: acc == -(L+1)
-    const uint32_t keep = ne2_abs_one(T, cUp);          // 1.0 unless |acc| == L+1
-    A = hfma2_bits(keep, T, 0x80018001u);               // (stepped ? 0 : acc) - 1
-    Mq = add2(add2(Mq, upm), dn1);                      // m += up - down
-#else
-    const uint32_t T = add2(A, sg1);                    // acc + 1, acc in [-(L+1), L+1]
-    const uint32_t up = addmax2(T, cUp, 0u);            // {0,1}:      acc == L+1
-    const uint32_t dn = addmin2(T, cDn, 0u);            // {0,0xFFFF}: acc == -(L+1)
-    const uint32_t upm = up * 0xFFFFu;                  // {0,0xFFFF} (no cross-half carry: halves are 0 or 1)
-    A = add2(T, 0xFFFFFFFFu) & ~(upm | dn);             // reset where stepped
-    Mq = add2(Mq, upm | (dn & 0x00010001u));            // m += up - down
-#endif
-    return add2(S, Mq);                                 // s' + 1 with the UPDATED median
+    const uint32_t sg1 = addclamp2(Sb, Mq, 0x00020002u);        // sign(s - m) + 1 in {0,1,2}
+    const uint32_t T = hadd2_bits(A, sg1);                      // acc after this sample, in [-(L+1), L+1]
+    const uint32_t up1 = hfma2_sat_bits(T, 0x3C003C00u, cDn);   // sat(acc - L)  -> bit pattern 1: acc == L+1
+    const uint32_t dn1 = hfma2_sat_bits(T, 0xBC00BC00u, cDn);   // sat(-acc - L) -> bit pattern 1: acc == -(L+1)
+    const uint32_t keep = ne2_abs_one(T, cUp);                  // 1.0 unless |acc| == L+1
+    A = hfma2_bits(keep, T, 0x80018001u);                       // (stepped ? 0 : acc) - 1
+    Mq = Mq + dn1 - up1;                                        // m += up - down: one IADD3, halves cannot interact (see above)
+    return add2(Sb, Mq);                                        // s' + 1 with the UPDATED median
   }
   __device__ __forceinline__ uint32_t over_mask(uint32_t sp1) const { return gt2_mask_nonneg(sp1, thr1); } // (:97-98)
 
   // Hit bookkeeping of one tick (:102-207). A lane on which a channel ends a hit parks its packed registers in the warp's
   // staging buffer and resets (lane-divergent); accepted iff hit_charge != 0 (src/wibeth/WIBEthFrameProcessor.cpp:520),
   // which flush() decides on the masked charge.
-  __device__ __forceinline__ void hit_update(uint32_t sp1, const TickCtx& ctx, int t)
+  __device__ __forceinline__ void hit_update(uint32_t sp1, const TickCtx& ctx, uint32_t unit, uint32_t t)
   {
     const uint32_t over = over_mask(sp1);
     const uint32_t left = prev & ~over;                 //                                  (:102)
@@ -525,7 +540,7 @@ struct PackedSimpleWibEth
     Tn = addmax2(Tn, over, 0x80018001u);                // tover = adds(tover, 1): -tover >= -32767   (:139-140)
     prev = over;
     if (left != 0u) {                                   //                                  (:154-204)
-      ctx.stage->push(HitStage::meta(ctx.chan0, ctx.unit, uint32_t(t)), C & left, neg2(Tn), add2(PK1, 0xFFFFFFFFu), neg2(PTn));
+      ctx.stage->push(HitStage::meta(ctx.chan0, unit, t), C & left, neg2(Tn), add2(PK1, 0xFFFFFFFFu), neg2(PTn));
       C &= ~left;
       Tn &= ~left;
       PK1 = (PK1 & ~left) | (left & 0x00010001u);
@@ -533,53 +548,106 @@ struct PackedSimpleWibEth
     }
   }
 
-  // G consecutive ticks, two tiers (results identical in both):
-  //  1. The pedestal recurrence runs first for all G ticks. It never reads hit state, so it is one branch-free block
-  //     the scheduler can interleave with the 14-bit extraction of later ticks.
-  //  2. QUIET tier — no channel of the warp is inside a hit and none goes over threshold in the group (by far the most
-  //     common case on physical noise): per channel charge = tover = peak_time = 0 stay 0 and only the un-gated peak
-  //     tracker moves, peak_adc = max(peak_adc, max_g s'_g), because with tover == 0 every peak update writes
-  //     peak_time = 0 again (ProcessAVX2.hpp:134-136). Outside a hit peak_adc <= threshold (it restarts from 0 when a
-  //     hit ends and every sample since was not over), so "new peak > threshold" <=> "some sample of the group is over".
-  //  3. Otherwise per-tick bookkeeping for the whole warp.
-  template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
-  __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
-                                        uint32_t* wav_out)
+  // Quiet test and hit bookkeeping of four ticks, two tiers (results identical in both):
+  //  QUIET — no channel of the warp is inside a hit and none goes over threshold in the group (by far the most common case on
+  //     physical noise): per channel charge = tover = peak_time = 0 stay 0 and only the un-gated peak tracker moves,
+  //     peak_adc = max(peak_adc, max_g s'_g), because with tover == 0 every peak update writes peak_time = 0 again
+  //     (ProcessAVX2.hpp:134-136). Outside a hit peak_adc <= threshold (it restarts from 0 when a hit ends and every sample
+  //     since was not over), so "new peak > threshold" <=> "some sample of the group is over".
+  //  otherwise per-tick bookkeeping for the whole warp.
+  template<bool WIB2_UNITS>
+  __device__ __forceinline__ void hits_of_group(const uint32_t (&sp)[4], const TickCtx& ctx, uint32_t unit, uint32_t t0, bool valid)
   {
-    static_assert(G == 4, "max tree below is written for 4 ticks");
-    uint32_t sp[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const uint32_t S = extract_pair(rows + g * ROW_WORDS, pp);
-      sp[g] = pedestal_step(S);
-      if constexpr (DUMP) {
-        ped_out[g] = median();
-        wav_out[g] = add2(sp[g], 0xFFFFFFFFu);
-      }
-    }
     const uint32_t pk = __vimax3_s16x2(__vimax3_s16x2(sp[0], sp[1], sp[2]), sp[3], PK1);
     const uint32_t busy = over_mask(pk) | prev; // some tick of the group over threshold, or still inside a hit
     if (__builtin_expect(!__any_sync(0xFFFFFFFFu, busy != 0u), 1)) {
       PK1 = pk;
       return;
     }
+    if (!valid) // empty pipeline stage (first group of a link) while a hit carried over from the previous batch is still open
+      return;
 #pragma unroll
-    for (int g = 0; g < G; ++g)
-      hit_update(sp[g], ctx, t0 + g);
+    for (int g = 0; g < 4; ++g)
+      hit_update(sp[g], ctx, unit, t0 + uint32_t(g));
     if (ctx.stage->must_flush())
       flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u, false); // whole 32-pair rounds only
   }
+
+  // First group of a chunk: its rows' words come straight from shared memory (the copy has just landed).
+  template<int ROW_WORDS = 28>
+  __device__ __forceinline__ void begin_chunk(const uint32_t* rows, const PairPos& pp)
+  {
+    if constexpr (PIPE) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        raw[2 * g] = rows[g * ROW_WORDS + pp.w0];
+        raw[2 * g + 1] = rows[g * ROW_WORDS + pp.w1];
+      }
+    }
+  }
+
+  // G consecutive ticks. `more`: another group of the same chunk follows (its rows are prefetched before the branch).
+  template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
+  __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
+                                        uint32_t* wav_out, bool more)
+  {
+    static_assert(G == 4, "max tree and pipeline registers are written for 4 ticks");
+    uint32_t sp[G], Sb[G];
+    if constexpr (PIPE) {
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        Sb[g] = extract_pair_biased_from(raw[2 * g], raw[2 * g + 1], pp.sh);
+      if (more) // the loads of the next group are in flight while this group's recurrence runs
+        begin_chunk<ROW_WORDS>(rows + G * ROW_WORDS, pp);
+    } else {
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        Sb[g] = extract_pair_biased(rows + g * ROW_WORDS, pp);
+    }
+    // The pedestal recurrence never reads hit state: one branch-free dependent chain.
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      sp[g] = pedestal_step(Sb[g]);
+      if constexpr (DUMP) {
+        ped_out[g] = median();
+        wav_out[g] = add2(sp[g], 0xFFFFFFFFu);
+      }
+    }
+    if constexpr (PIPE) {
+      // ... and in its shadow the quiet test (max tree, compare, vote) of the PREVIOUS group, which is independent of it
+      hits_of_group<WIB2_UNITS>(dsp, ctx, dwhen >> 6, dwhen & 63u, dvalid);
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        dsp[g] = sp[g];
+      dwhen = (ctx.unit << 6) | uint32_t(t0);
+      dvalid = true;
+    } else {
+      hits_of_group<WIB2_UNITS>(sp, ctx, ctx.unit, uint32_t(t0), true);
+    }
+  }
+  // End of a link (before the staged hits are flushed and the state is stored): drain the pipeline.
+  template<bool WIB2_UNITS = false>
+  __device__ __forceinline__ void finish_link(const TickCtx& ctx)
+  {
+    if constexpr (PIPE) {
+      if (dvalid)
+        hits_of_group<WIB2_UNITS>(dsp, ctx, dwhen >> 6, dwhen & 63u, true);
+      dvalid = false;
+    }
+  }
 };
+using PackedSimpleWibEth = PackedSimpleT<false>;
+using PackedSimpleWibEthPipe = PackedSimpleT<true>;
 
 // =====================================================================================================================
-// Packed fast path: WIB2 SimpleThreshold (wib2/tpg/ProcessAVX2.hpp:24-200). Same pedestal recurrence with the limit fixed
-// at 10 (:79); charge accumulates (over ? s' : 0) >> tap_exponent with signed saturation (:110-112), no peak tracking,
-// hit block = {chan, t, charge, tover}. Validity: 0 <= threshold <= 32767.
+// WIB2 SimpleThreshold (wib2/tpg/ProcessAVX2.hpp:24-200). Same pedestal recurrence with the limit fixed at 10 (:79); charge
+// accumulates (over ? s' : 0) >> tap_exponent with signed saturation (:110-112), no peak tracking, hit block = {chan, t,
+// charge, tover}. Validity: 0 <= threshold <= 32767. Straight-line groups only: the CTA form caps the registers for five CTAs
+// per SM, and the pipelined form measured 7 % slower there (gpurun_out/r02_probe3.txt).
 // =====================================================================================================================
 struct PackedSimpleWib2 : PackedSimpleWibEth
 {
-  uint32_t shift, shmask;
-
+  static constexpr bool kWib2Fields = true;
   template<bool WIB2_UNITS>
   static __device__ __forceinline__ void flush(const HitStage& h, const TpSink& k, const uint8_t* link_base, uint32_t link, uint32_t lane,
                                                bool everything = true)
@@ -596,7 +664,7 @@ struct PackedSimpleWib2 : PackedSimpleWibEth
     const uint32_t m = 0xFFFFu >> shift;
     shmask = m | (m << 16);
   }
-  __device__ __forceinline__ void hit_update(uint32_t sp1, const TickCtx& ctx, int t)
+  __device__ __forceinline__ void hit_update(uint32_t sp1, const TickCtx& ctx, uint32_t unit, uint32_t t)
   {
     const uint32_t over = over_mask(sp1);
     const uint32_t left = prev & ~over;
@@ -607,35 +675,41 @@ struct PackedSimpleWib2 : PackedSimpleWibEth
     prev = over;
     if (left != 0u) {
       // accepted iff hit_charge != 0 (src/wib2/WIB2FrameProcessor.cpp:429): decided in flush on the masked charge
-      ctx.stage->push(HitStage::meta(ctx.chan0, ctx.unit, uint32_t(t)), C & left, neg2(Tn));
+      ctx.stage->push(HitStage::meta(ctx.chan0, unit, t), C & left, neg2(Tn));
       C &= ~left;
       Tn &= ~left;
     }
   }
+  template<bool WIB2_UNITS>
+  __device__ __forceinline__ void hits_of_group(const uint32_t (&sp)[4], const TickCtx& ctx, uint32_t unit, uint32_t t0, bool valid)
+  {
+    const uint32_t mx = __vimax3_s16x2(__vimax3_s16x2(sp[0], sp[1], sp[2]), sp[3], sp[3]);
+    const uint32_t busy = over_mask(mx) | prev;
+    if (__builtin_expect(!__any_sync(0xFFFFFFFFu, busy != 0u), 1))
+      return; // nothing but the pedestal moves outside hits
+    if (!valid)
+      return;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      hit_update(sp[g], ctx, unit, t0 + uint32_t(g));
+    if (ctx.stage->must_flush())
+      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u, false); // whole 32-pair rounds only
+  }
   template<int G, bool DUMP, int ROW_WORDS, bool WIB2_UNITS>
   __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
-                                        uint32_t* wav_out)
+                                        uint32_t* wav_out, bool /*more*/)
   {
-    static_assert(G == 4, "max tree below is written for 4 ticks");
+    static_assert(G == 4, "max tree is written for 4 ticks");
     uint32_t sp[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const uint32_t S = extract_pair(rows + g * ROW_WORDS, pp);
-      sp[g] = pedestal_step(S);
+      sp[g] = pedestal_step(extract_pair_biased(rows + g * ROW_WORDS, pp));
       if constexpr (DUMP) {
         ped_out[g] = median();
         wav_out[g] = add2(sp[g], 0xFFFFFFFFu);
       }
     }
-    const uint32_t mx = __vimax3_s16x2(__vimax3_s16x2(sp[0], sp[1], sp[2]), sp[3], sp[3]);
-    const uint32_t busy = over_mask(mx) | prev;
-    if (__builtin_expect(!__any_sync(0xFFFFFFFFu, busy != 0u), 1))
-      return; // nothing but the pedestal moves outside hits
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-      hit_update(sp[g], ctx, t0 + g);
-    if (ctx.stage->must_flush())
-      flush<WIB2_UNITS>(*ctx.stage, ctx.p->sink, ctx.link_base, ctx.link, (ctx.chan0 >> 1) & 31u, false); // whole 32-pair rounds only
+    hits_of_group<WIB2_UNITS>(sp, ctx, ctx.unit, uint32_t(t0), true);
   }
 };
 
@@ -659,6 +733,10 @@ struct PackedRsWibEth : PackedSimpleWibEth
   static constexpr int kWarpsPerSm = STANDARD ? 20 : 16; // AbsRS: 4 warps per sub-partition beat 5 by 3 % (same sweep)
   uint32_t RS1, MRq, AR;     // RS + 1 (carried value, after median subtraction); 1 - median_RS; (acc_RS - 1) as fp16 subnormal
   int f_lo, f_hi, nf_lo, nf_hi, scale;
+  template<int ROW_WORDS = 28>
+  __device__ __forceinline__ void begin_chunk(const uint32_t*, const PairPos&) {}
+  template<bool WIB2_UNITS = false>
+  __device__ __forceinline__ void finish_link(const TickCtx&) {}
 
   __device__ __forceinline__ void configure(const KernelParams& p)
   {
@@ -688,22 +766,17 @@ struct PackedRsWibEth : PackedSimpleWibEth
     st[SV_MED_RS * 32 + lane] = add2(~MRq, 0x00020002u);
     st[SV_ACC_RS * 32 + lane] = acc_from_reg(AR);
   }
-  // frugal update of (Mq_, A_) = (1 - median, accumulator) with sample S; returns S - median + 1 with the updated median
+  // frugal update of (Mq_, A_) = (1 - median, accumulator - 1) with sample S; returns S - median + 1 with the updated median.
+  // Used for the median of the RUNNING SUM, which lives in [-3277, 3277]: its register passes through zero, so the two step
+  // flags are added as packed halves (two VIADD.16x2) instead of the one 32-bit add the raw pedestal gets away with.
   __device__ __forceinline__ uint32_t frugal(uint32_t S, uint32_t& Mq_, uint32_t& A_) const
   {
     const uint32_t sg1 = addclamp2(S, Mq_, 0x00020002u);
-#if SWTPG_FLOAT_ACC
     const uint32_t T = hadd2_bits(A_, sg1);
     const uint32_t upm = eq2_mask(T, cUp);
     const uint32_t dn1 = hfma2_sat_bits(T, 0xBC00BC00u, cDn);
     A_ = hfma2_bits(ne2_abs_one(T, cUp), T, 0x80018001u);
     Mq_ = add2(add2(Mq_, upm), dn1);
-#else
-    const uint32_t T = add2(A_, sg1);
-    const uint32_t up = addmax2(T, cUp, 0u), dn = addmin2(T, cDn, 0u), upm = up * 0xFFFFu;
-    A_ = add2(T, 0xFFFFFFFFu) & ~(upm | dn);
-    Mq_ = add2(Mq_, upm | (dn & 0x00010001u));
-#endif
     return add2(S, Mq_);
   }
   // _mm256_mulhrs_epi16(v, 3276) for the 16-bit value in the LOW half of `w` (upper half ignored): ((v * 3276 >> 14) + 1) >> 1
@@ -760,13 +833,13 @@ struct PackedRsWibEth : PackedSimpleWibEth
 
   template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
   __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
-                                        uint32_t* wav_out)
+                                        uint32_t* wav_out, bool /*more*/)
   {
     static_assert(G == 4, "max trees below are written for 4 ticks");
     uint32_t sp[G], lv[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      sp[g] = frugal(extract_pair(rows + g * ROW_WORDS, pp), Mq, A);
+      sp[g] = pedestal_step(extract_pair_biased(rows + g * ROW_WORDS, pp));
       lv[g] = rs_step(sp[g]);
       if constexpr (DUMP) {
         ped_out[g] = median();
@@ -818,6 +891,11 @@ struct PackedFirIqr
   uint32_t prev, C, Tn;
   uint32_t xmax, sig3max, K, Kneg3, shift, shmask, thr_cfg, mult;
 
+  static __device__ __forceinline__ uint32_t sample(const uint32_t* row, const PairPos& pp) { return extract_pair(row, pp); }
+  template<int ROW_WORDS = 28>
+  __device__ __forceinline__ void begin_chunk(const uint32_t*, const PairPos&) {}
+  template<bool WIB2_UNITS = false>
+  __device__ __forceinline__ void finish_link(const TickCtx&) {}
   static constexpr uint32_t kTiny = 0x00010001u;    // 2^-24 per half
   static constexpr uint32_t kNegTiny = 0x80018001u;
   static constexpr uint32_t kUp = 0x000B000Bu;      // (L+1) * 2^-24, L = 10
@@ -1032,7 +1110,7 @@ struct PackedFirIqr
 
   template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
   __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
-                                        uint32_t* wav_out)
+                                        uint32_t* wav_out, bool /*more*/)
   {
     static_assert(G == 4, "trees below are written for 4 ticks");
     uint32_t filt[G], sig3[G];
@@ -1127,7 +1205,7 @@ struct PackedFirIqrAnyTaps : PackedFirIqr
 
   template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
   __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
-                                        uint32_t* wav_out)
+                                        uint32_t* wav_out, bool /*more*/)
   {
     static_assert(G == 4, "trees below are written for 4 ticks");
     uint32_t filt[G], sig3[G];
@@ -1256,7 +1334,7 @@ struct PackedRsIqrWib2 : PackedFirIqr
 
   template<int G, bool DUMP, int ROW_WORDS = 28, bool WIB2_UNITS = false>
   __device__ __forceinline__ void group(const uint32_t* rows, const PairPos& pp, const TickCtx& ctx, int t0, uint32_t* ped_out,
-                                        uint32_t* wav_out)
+                                        uint32_t* wav_out, bool /*more*/)
   {
     static_assert(G == 4, "trees below are written for 4 ticks");
     uint32_t lv[G], rs[G], sig3[G];
@@ -1441,7 +1519,7 @@ wibeth_kernel(const KernelParams p)
     for (uint32_t unit = 0; unit < n_units; ++unit) {
       ctx.tick_base = unit * 64u;
       ctx.unit = unit;
-      if constexpr (!std::is_same<Algo, PackedSimpleWibEth>::value) {
+      if constexpr (!std::is_same<Algo, PackedSimpleWibEth>::value && !std::is_same<Algo, PackedSimpleWibEthPipe>::value) {
         // DAQEthHeader word 1 = timestamp (docs/README.md:81); the packed path reads it when it flushes hits
         ctx.ts = *reinterpret_cast<const unsigned long long*>(link_base + size_t(unit) * SWTPG_WIBETH_FRAME_BYTES + 8);
       }
@@ -1450,16 +1528,17 @@ wibeth_kernel(const KernelParams p)
         mbar_wait(&bars[stg], phase);
         const uint32_t* rows = reinterpret_cast<const uint32_t*>(stages + stg * kChunkBytes);
         if (need_seed) {
-          algo.seed(extract_pair(rows, pp));
+          algo.seed(Algo::sample(rows, pp));
           need_seed = false;
         }
         constexpr int G = 4;
         static_assert(CHUNK_TICKS % G == 0, "group must divide the chunk");
         constexpr int kGroupUnroll = Algo::kGroupUnroll;
+        algo.begin_chunk(rows, pp);
 #pragma unroll kGroupUnroll
         for (int tt = 0; tt < CHUNK_TICKS; tt += G) {
           uint32_t ped[G], wav[G];
-          algo.template group<G, DUMP>(rows + tt * (kWibEthRowBytes / 4), pp, ctx, t0 + tt, ped, wav);
+          algo.template group<G, DUMP>(rows + tt * (kWibEthRowBytes / 4), pp, ctx, t0 + tt, ped, wav, tt + G < CHUNK_TICKS);
           if constexpr (DUMP) {
 #pragma unroll
             for (int g = 0; g < G; ++g) {
@@ -1482,6 +1561,7 @@ wibeth_kernel(const KernelParams p)
       }
     }
 
+    algo.template finish_link<false>(ctx); // drains the policy's software pipeline (deferred hit bookkeeping of the last group)
     Algo::template flush<false>(hits, p.sink, link_base, link, lane); // records carry unit indices of THIS link
     const uint32_t k_end = algo.phase_after(n_units * 64u);
     algo.store(st, lane, k_end);
@@ -1663,7 +1743,7 @@ wibeth_quad_kernel(const KernelParams p)
       const bool mine = unit < n_units;
       ctx.tick_base = unit * 64u;
       ctx.unit = unit;
-      if constexpr (!std::is_same<Algo, PackedSimpleWibEth>::value) {
+      if constexpr (!std::is_same<Algo, PackedSimpleWibEth>::value && !std::is_same<Algo, PackedSimpleWibEthPipe>::value) {
         if (mine) // DAQEthHeader word 1 = timestamp (docs/README.md:81); the packed path reads it when it flushes hits
           ctx.ts = *reinterpret_cast<const unsigned long long*>(link_base + size_t(unit) * SWTPG_WIBETH_FRAME_BYTES + 8);
       }
@@ -1674,16 +1754,17 @@ wibeth_quad_kernel(const KernelParams p)
         if (mine) {
           const uint32_t* rows = reinterpret_cast<const uint32_t*>(stages + (stg * kQuad + warp) * kChunkBytes);
           if (need_seed) {
-            algo.seed(extract_pair(rows, pp));
+            algo.seed(Algo::sample(rows, pp));
             need_seed = false;
           }
           constexpr int G = 4;
           static_assert(CHUNK_TICKS % G == 0, "group must divide the chunk");
           constexpr int kGroupUnroll = Algo::kGroupUnroll;
+          algo.begin_chunk(rows, pp);
 #pragma unroll kGroupUnroll
           for (int tt = 0; tt < CHUNK_TICKS; tt += G) {
             uint32_t ped[G], wav[G];
-            algo.template group<G, DUMP>(rows + tt * (kWibEthRowBytes / 4), pp, ctx, t0 + tt, ped, wav);
+            algo.template group<G, DUMP>(rows + tt * (kWibEthRowBytes / 4), pp, ctx, t0 + tt, ped, wav, tt + G < CHUNK_TICKS);
             if constexpr (DUMP) {
 #pragma unroll
               for (int g = 0; g < G; ++g) {
@@ -1709,6 +1790,7 @@ wibeth_quad_kernel(const KernelParams p)
     }
 
     if (n_units != 0) {
+      algo.template finish_link<false>(ctx);
       Algo::template flush<false>(hits, p.sink, link_base, link, lane); // records carry unit indices of THIS link
       const uint32_t k_end = algo.phase_after(n_units * 64u);
       algo.store(st, lane, k_end);
@@ -1865,14 +1947,15 @@ wib2_kernel(const KernelParams p)
         ctx.ts = uint64_t(sc[1]) | (uint64_t(sc[2]) << 32); // WIB2Frame::get_timestamp, first frame (:350-351)
       const uint32_t* rows = sc + row0;
       if (need_seed) {
-        algo.seed(extract_pair(rows, pp));
+        algo.seed(Algo::sample(rows, pp));
         need_seed = false;
       }
       constexpr int G = 4;
+      algo.template begin_chunk<kWib2FrameWords>(rows, pp);
 #pragma unroll
       for (int tt = 0; tt < 12; tt += G) {
         uint32_t ped[G], wav[G];
-        algo.template group<G, DUMP, kWib2FrameWords, true>(rows + tt * kWib2FrameWords, pp, ctx, tt, ped, wav);
+        algo.template group<G, DUMP, kWib2FrameWords, true>(rows + tt * kWib2FrameWords, pp, ctx, tt, ped, wav, tt + G < 12);
         if constexpr (DUMP) {
 #pragma unroll
           for (int g = 0; g < G; ++g) {
@@ -1893,6 +1976,7 @@ wib2_kernel(const KernelParams p)
       }
     }
 
+    algo.template finish_link<true>(ctx);
     Algo::template flush<true>(hits, p.sink, link_base, link, lane);
     const uint32_t k_end = algo.phase_after(n_units * 12u);
     algo.store(st, lane, k_end);

@@ -124,6 +124,8 @@ struct alignas(64) LinkQ
   uint64_t range_epoch = 0;        // cached registered range of this link's payloads (a link's payloads come from one latency buffer)
   uintptr_t range_lo = 0, range_hi = 0;
   intptr_t range_delta = 0;        // device-visible address = host address + delta
+  uintptr_t gap_lo = 0, gap_hi = 0; // cached MISS: the unregistered gap between ranges the link's last staged payload lay in
+  uint64_t n_zero_copy = 0, n_staged = 0; // units of this link submitted by address / by copy (summed by swtpg_get_counters)
   // written by the engine's threads
   alignas(64) std::atomic<uint64_t> tail{ 0 }; // units whose gather has completed: their ring slots are free again
   std::atomic<uint64_t> dispatched{ 0 };       // units handed to a batch
@@ -146,6 +148,7 @@ struct Batch
   cudaEvent_t ev_gather = nullptr, ev_kernel = nullptr, ev_count = nullptr, ev_tps = nullptr;
   uint32_t n_ready = 0, n_taken = 0;
   bool overflow = false;
+  bool released = false; // the release thread has handed the batch's ring slots back (guarded by StreamEngine::mu)
 };
 
 struct StreamEngine
@@ -170,15 +173,15 @@ struct StreamEngine
 
   std::vector<std::unique_ptr<Batch>> batches;
   std::mutex mu; // queues, requests, condition variables below
-  std::condition_variable cv_dispatch, cv_complete, cv_ready, cv_space, cv_flush;
-  std::deque<Batch*> free_q, inflight_q, ready_q;
+  std::condition_variable cv_dispatch, cv_complete, cv_release, cv_ready, cv_space, cv_flush;
+  std::deque<Batch*> free_q, inflight_q, release_q, ready_q;
   uint32_t building = 0; // batches taken from free_q that have not reached inflight_q yet
   std::atomic<bool> kicked{ false };
   std::atomic<uint32_t> space_waiters{ 0 };
   uint64_t flush_req = 0, flush_done = 0;
   bool reset_req = false, stalled_on_poll = false, quit = false;
   std::atomic<int> thread_status{ SWTPG_OK };
-  std::thread dispatcher, completer;
+  std::thread dispatcher, releaser, completer;
   std::mutex poll_mu; // one poller at a time
   std::chrono::microseconds timeout{ 5000 };
 
@@ -205,6 +208,7 @@ struct StreamEngine
   cudaError_t launch_gather(Batch& b);
   cudaError_t enqueue(Batch& b);
   void dispatcher_main();
+  void releaser_main();
   void completer_main();
 };
 
@@ -306,6 +310,7 @@ StreamEngine::dispatcher_main()
         q.tail.store(0);
         q.dispatched.store(0);
         q.slot = q.dslot = 0;
+        q.n_zero_copy = q.n_staged = 0;
       }
       have_pending_since = false;
       reset_req = false;
@@ -379,8 +384,11 @@ StreamEngine::dispatcher_main()
       have_pending_since = false;
       lk.lock();
       --building;
+      b->released = false;
       inflight_q.push_back(b);
+      release_q.push_back(b);
       cv_complete.notify_one();
+      cv_release.notify_one();
       lk.unlock();
       if (e != cudaSuccess)
         break;
@@ -390,6 +398,35 @@ StreamEngine::dispatcher_main()
       flush_done = std::max(flush_done, ticket);
       cv_flush.notify_all();
     }
+  }
+}
+
+// Ring space comes back the moment a batch's gather has finished — the frames are in HBM, so the units' ring slots (and the
+// borrow of zero-copy units) end there — independently of how long the TPG kernel and the TP read-back of earlier batches
+// take: its own thread, asleep in cudaEventSynchronize in between.
+void
+StreamEngine::releaser_main()
+{
+  cudaSetDevice(h->cfg.device);
+  std::unique_lock<std::mutex> lk(mu);
+  for (;;) {
+    cv_release.wait(lk, [&] { return quit || !release_q.empty(); });
+    if (release_q.empty())
+      return; // quit
+    Batch* b = release_q.front();
+    release_q.pop_front();
+    lk.unlock();
+    const cudaError_t e = cudaEventSynchronize(b->ev_gather);
+    for (uint32_t l = 0; l < n_links; ++l)
+      if (b->h_nunits[l])
+        links[l].tail.fetch_add(b->h_nunits[l], std::memory_order_release);
+    if (e != cudaSuccess)
+      thread_fail("gather", e);
+    lk.lock();
+    b->released = true;
+    cv_complete.notify_all();
+    if (space_waiters.load(std::memory_order_acquire) != 0)
+      cv_space.notify_all();
   }
 }
 
@@ -404,17 +441,7 @@ StreamEngine::completer_main()
       return; // quit
     Batch* b = inflight_q.front(); // stays at the front until it is complete (swtpg_sync waits for the queue to empty)
     lk.unlock();
-    cudaError_t e = cudaEventSynchronize(b->ev_gather);
-    // the frames are in HBM: the units' ring slots (and the borrow of zero-copy units) end here
-    for (uint32_t l = 0; l < n_links; ++l)
-      if (b->h_nunits[l])
-        links[l].tail.fetch_add(b->h_nunits[l], std::memory_order_release);
-    if (space_waiters.load(std::memory_order_acquire) != 0) {
-      std::lock_guard<std::mutex> g(mu);
-      cv_space.notify_all();
-    }
-    if (e == cudaSuccess)
-      e = cudaEventSynchronize(b->ev_count);
+    cudaError_t e = cudaEventSynchronize(b->ev_count);
     if (e == cudaSuccess) {
       const unsigned found = *b->h_count;
       const unsigned stored = std::min<unsigned>(found, h->tp_capacity);
@@ -434,6 +461,7 @@ StreamEngine::completer_main()
     if (e != cudaSuccess)
       thread_fail("batch completion", e);
     lk.lock();
+    cv_complete.wait(lk, [&] { return b->released || quit; }); // its ring slots are back (the release thread reads h_nunits)
     inflight_q.pop_front();
     ready_q.push_back(b);
     cv_ready.notify_all();
@@ -503,6 +531,7 @@ engine_create(swtpg_handle* h, StreamEngine** out)
   }
   StreamEngine* ep = e.release();
   ep->dispatcher = std::thread([ep] { ep->dispatcher_main(); });
+  ep->releaser = std::thread([ep] { ep->releaser_main(); });
   ep->completer = std::thread([ep] { ep->completer_main(); });
   h->engine.store(ep, std::memory_order_release);
   *out = ep;
@@ -537,22 +566,35 @@ registered_address(StreamEngine* e, LinkQ& q, const void* unit, size_t bytes)
   const uintptr_t a = reinterpret_cast<uintptr_t>(unit);
   if (a & 15u)
     return nullptr;
-  if (q.range_epoch != epoch || !(a >= q.range_lo && a + bytes <= q.range_hi)) {
-    if (q.range_epoch == epoch && q.range_hi == 0)
-      return nullptr; // cached miss: this link's payloads are not in registered memory
-    std::lock_guard<std::mutex> lk(e->ranges_mu); // first payload of the link, or the set of ranges changed, or another range
-    q.range_lo = q.range_hi = 0;
-    for (const auto& r : e->ranges)
-      if (a >= r.lo && a + bytes <= r.hi) {
-        q.range_lo = r.lo;
-        q.range_hi = r.hi;
-        q.range_delta = r.delta;
-      }
-    q.range_epoch = e->ranges_epoch.load(std::memory_order_relaxed);
-    if (q.range_hi == 0)
-      return nullptr;
+  if (q.range_epoch == epoch) {
+    if (a >= q.range_lo && a + bytes <= q.range_hi)
+      return reinterpret_cast<const uint8_t*>(a + uintptr_t(q.range_delta));
+    if (a >= q.gap_lo && a + bytes <= q.gap_hi)
+      return nullptr; // cached miss: inside the same unregistered gap as the link's last staged payload
   }
-  return reinterpret_cast<const uint8_t*>(a + uintptr_t(q.range_delta));
+  // first payload of the link, or the set of ranges changed, or the payload lies somewhere else than the last one
+  std::lock_guard<std::mutex> lk(e->ranges_mu);
+  q.range_epoch = e->ranges_epoch.load(std::memory_order_relaxed);
+  uintptr_t below = 0, above = ~uintptr_t(0);
+  for (const auto& r : e->ranges) {
+    if (a >= r.lo && a + bytes <= r.hi) {
+      q.range_lo = r.lo;
+      q.range_hi = r.hi;
+      q.range_delta = r.delta;
+      return reinterpret_cast<const uint8_t*>(a + uintptr_t(r.delta));
+    }
+    if (r.hi <= a)
+      below = std::max(below, r.hi);
+    else if (r.lo >= a + bytes)
+      above = std::min(above, r.lo);
+    else { // straddles a range boundary: staged, and not cached
+      below = a;
+      above = a;
+    }
+  }
+  q.gap_lo = below;
+  q.gap_hi = above;
+  return nullptr;
 }
 
 swtpg_status
@@ -603,6 +645,9 @@ submit_impl(swtpg_handle* h, uint32_t link, const void* unit, size_t bytes, uint
     }
     swtpg_stage_copy(st + idx * e->unit_bytes, unit, bytes);
     dev = e->stage_dev + idx * e->unit_bytes;
+    ++q.n_staged;
+  } else {
+    ++q.n_zero_copy;
   }
   e->ring_ptr[idx] = dev;
   q.slot = q.slot + 1 == e->R ? 0 : q.slot + 1;
@@ -668,12 +713,15 @@ engine_destroy(swtpg_handle* h)
     e->quit = true;
     e->cv_dispatch.notify_all();
     e->cv_complete.notify_all();
+    e->cv_release.notify_all();
     e->cv_ready.notify_all();
     e->cv_space.notify_all();
     e->cv_flush.notify_all();
   }
   if (e->dispatcher.joinable())
     e->dispatcher.join();
+  if (e->releaser.joinable())
+    e->releaser.join();
   if (e->completer.joinable())
     e->completer.join();
   cudaDeviceSynchronize();
@@ -743,11 +791,16 @@ swtpg_register_buffer(swtpg_handle* h, void* base, size_t bytes)
   SW_CUDA(h, cudaSetDevice(h->cfg.device));
   bool ours = true;
   cudaError_t ce = cudaHostRegister(base, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
-  if (ce == cudaErrorHostMemoryAlreadyRegistered) { // e.g. two handles (GPUs) sharing one latency buffer, or swtpg_alloc_pinned memory
+  if (ce != cudaSuccess) {
+    // already page-locked — by another handle (two GPUs sharing one latency buffer: "already registered") or by
+    // cudaHostAlloc / swtpg_alloc_pinned ("invalid value")? Then it only has to be looked up, not pinned again.
     cudaGetLastError();
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, base) != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+      cudaGetLastError();
+      SW_CUDA(h, ce);
+    }
     ours = false;
-  } else {
-    SW_CUDA(h, ce);
   }
   void* dev = nullptr;
   ce = cudaHostGetDevicePointer(&dev, base, 0);
@@ -832,6 +885,18 @@ swtpg_status
 swtpg_poll_wait(swtpg_handle* h, swtpg_tp* out, size_t cap, size_t* n_out, uint64_t timeout_us)
 {
   return poll_impl(h, out, cap, n_out, timeout_us);
+}
+
+// units submitted by address (zero-copy) and by staging copy since swtpg_start; used by swtpg_get_counters
+void
+swtpg_internal_ingest_counts(swtpg_handle* h, uint64_t* zero_copy, uint64_t* staged)
+{
+  *zero_copy = *staged = 0;
+  if (StreamEngine* e = h->engine.load(std::memory_order_acquire))
+    for (uint32_t l = 0; l < e->n_links; ++l) {
+      *zero_copy += e->links[l].n_zero_copy;
+      *staged += e->links[l].n_staged;
+    }
 }
 
 swtpg_status

@@ -812,7 +812,7 @@ struct swtpg_host_conf
   uint16_t crate_id, slot_id, first_link_id;
   uint8_t enable_tpg, emulator_mode, correct_channel_lookup, reversed_map, enable_simple_threshold_on_collection, block_on_backpressure;
   uint8_t count_only_sink; // 1: tp_out only counts what it accepts (throughput runs: no queue growth)
-  uint8_t pad;
+  uint8_t n_slots;         // staging depth of the engine in superchunks (0 = 3)
   uint32_t sink_capacity; // per link; try_send fails beyond it (0 = unbounded)
 };
 
@@ -854,7 +854,7 @@ swtpg_host_create(const swtpg_host_conf* c)
 {
   try {
     auto h = std::make_unique<swtpg_host>();
-    h->engine = std::make_shared<TpgEngine>(c->device, swtpg_format(c->format), c->n_links, c->superchunk_units);
+    h->engine = std::make_shared<TpgEngine>(c->device, swtpg_format(c->format), c->n_links, c->superchunk_units, c->n_slots ? c->n_slots : 3u);
     h->sink_capacity = c->sink_capacity;
     h->count_only = c->count_only_sink != 0;
     h->queues.resize(c->n_links);
@@ -1088,6 +1088,13 @@ swtpg_host_push_feeders(swtpg_host* h, void* payloads, uint32_t n_units, uint32_
     out->payloads = uint64_t(passes) * n_units * n_links;
   }
   return 0;
+}
+
+// the engine's swtpg_counters (units by address / by copy, batches, bytes)
+int
+swtpg_host_counters(swtpg_host* h, swtpg_counters* out)
+{
+  return h->engine->handle() && swtpg_get_counters(h->engine->handle(), out) == SWTPG_OK ? 0 : -1;
 }
 
 // TPs accepted by the count-only sinks so far

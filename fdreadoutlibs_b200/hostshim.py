@@ -18,7 +18,7 @@ class HostConf(C.Structure):
                 ("channel_mask", C.c_uint32 * 16), ("n_mask", C.c_uint32), ("crate_id", C.c_uint16), ("slot_id", C.c_uint16),
                 ("first_link_id", C.c_uint16), ("enable_tpg", C.c_uint8), ("emulator_mode", C.c_uint8),
                 ("correct_channel_lookup", C.c_uint8), ("reversed_map", C.c_uint8), ("enable_simple_threshold_on_collection", C.c_uint8),
-                ("block_on_backpressure", C.c_uint8), ("count_only_sink", C.c_uint8), ("pad", C.c_uint8), ("sink_capacity", C.c_uint32)]
+                ("block_on_backpressure", C.c_uint8), ("count_only_sink", C.c_uint8), ("n_slots", C.c_uint8), ("sink_capacity", C.c_uint32)]
 
 
 HOST_TP_DTYPE = np.dtype([("time_start", "<u8"), ("time_peak", "<u8"), ("time_over_threshold", "<u8"), ("channel", "<u4"),
@@ -49,7 +49,7 @@ class TpHandlerInfo(C.Structure):
 
 EXPORTS = ["swtpg_host_tpsets_create", "swtpg_host_tpsets_destroy", "swtpg_host_tpsets_receive", "swtpg_host_tpsets_cycle",
            "swtpg_host_tpsets_cutoff", "swtpg_host_tpsets_count", "swtpg_host_tpsets_get", "swtpg_host_tpsets_info",
-           "swtpg_host_push_parallel", "swtpg_host_push_feeders", "swtpg_host_tp_count", "swtpg_host_last_error", "swtpg_host_create", "swtpg_host_destroy", "swtpg_host_start", "swtpg_host_stop", "swtpg_host_push",
+           "swtpg_host_push_parallel", "swtpg_host_push_feeders", "swtpg_host_tp_count", "swtpg_host_counters", "swtpg_host_last_error", "swtpg_host_create", "swtpg_host_destroy", "swtpg_host_start", "swtpg_host_stop", "swtpg_host_push",
            "swtpg_host_take_tps", "swtpg_host_get_info", "swtpg_host_error_count", "swtpg_host_misconfigurations",
            "swtpg_host_last_daq_time", "swtpg_host_register_channel_map", "swtpg_host_register_buffer"]
 
@@ -70,6 +70,7 @@ def host_lib():
         lib.swtpg_host_push_parallel.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         lib.swtpg_host_push_feeders.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32,
                                                 C.POINTER(FeedStats)]
+        lib.swtpg_host_counters.argtypes = [C.c_void_p, C.c_void_p]
         lib.swtpg_host_tp_count.restype = C.c_uint64
         lib.swtpg_host_tp_count.argtypes = [C.c_void_p]
         lib.swtpg_host_take_tps.restype = C.c_size_t
@@ -110,7 +111,8 @@ class FrameProcessors:
                  rs_memory_factor: float = 0.8, rs_scale_factor: float = 2.0, acc_limit: int = 10, tp_timeout: int = 10 ** 9, channel_mask=(),
                  crate_id: int = 1, slot_id: int = 0, first_link_id: int = 0, enable_tpg: bool = True, emulator_mode: bool = False,
                  correct_channel_lookup: bool = False, reversed_map: bool = False, collection_simple_threshold: bool = False,
-                 sink_capacity: int = 0, block_on_backpressure: bool = True, device: int = 0, count_only_sink: bool = False):
+                 sink_capacity: int = 0, block_on_backpressure: bool = True, device: int = 0, count_only_sink: bool = False,
+                 n_slots: int = 3):
         c = HostConf()
         c.device, c.format, c.n_links, c.superchunk_units = device, 1 if fmt == "wib2" else 0, n_links, superchunk_units
         c.tpg_algorithm = algorithm.encode()
@@ -125,6 +127,7 @@ class FrameProcessors:
         c.sink_capacity = sink_capacity
         c.block_on_backpressure = block_on_backpressure
         c.count_only_sink = count_only_sink
+        c.n_slots = n_slots
         self.lib = host_lib()
         self.n_links = n_links
         self.h = self.lib.swtpg_host_create(C.byref(c))
@@ -158,6 +161,14 @@ class FrameProcessors:
         st = FeedStats()
         self._check(self.lib.swtpg_host_push_feeders(self.h, payloads.ctypes.data, payloads.shape[1], n_threads, burst, pace, passes, C.byref(st)))
         return {"wall_s": st.wall_s, "feeder_cpu_s": st.feeder_cpu_s, "payloads": int(st.payloads), "late_bursts": int(st.late_bursts)}
+
+    def counters(self) -> dict:
+        """swtpg_get_counters of the engine behind the processors."""
+        from ._lib import SwtpgCounters
+
+        c = SwtpgCounters()
+        self._check(self.lib.swtpg_host_counters(self.h, C.byref(c)))
+        return {n: int(getattr(c, n)) for n, _ in SwtpgCounters._fields_}
 
     def tp_count(self) -> int:
         """TPs accepted so far by count-only sinks (count_only_sink=True)."""

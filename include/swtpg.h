@@ -127,6 +127,8 @@ typedef struct swtpg_counters
   uint64_t batches;
   uint64_t submit_busy;      /* swtpg_submit calls refused with SWTPG_ERR_BUSY */
   uint64_t h2d_bytes, d2h_bytes;
+  uint64_t units_zero_copy;  /* streaming path: units read where they lay in a registered latency buffer ... */
+  uint64_t units_staged;     /* ... and units copied into the pinned staging ring by swtpg_submit */
 } swtpg_counters;
 
 typedef struct swtpg_handle swtpg_handle;

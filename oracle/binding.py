@@ -173,7 +173,7 @@ def ref_lib():
 
 # impl codes of oracle/ref_wrapper.cpp
 REF_ETH_SIMPLE_AVX2, REF_ETH_SIMPLE_NAIVE, REF_ETH_ABSRS_AVX2, REF_ETH_STDRS_AVX2 = range(4)
-REF_WIB2_SIMPLE_AVX2, REF_WIB2_FIR_AVX2, REF_WIB2_FIR_NAIVE, REF_WIB2_ABSRS_AVX2 = range(4)
+REF_WIB2_SIMPLE_AVX2, REF_WIB2_FIR_AVX2, REF_WIB2_FIR_NAIVE, REF_WIB2_ABSRS_AVX2, REF_WIB2_ABSRS_NAIVE = range(5)
 
 
 class ReferenceWibEth:

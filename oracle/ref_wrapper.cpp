@@ -27,6 +27,13 @@
 #include "fdreadoutlibs/wib2/tpg/ProcessAVX2FIR.hpp"
 #include "fdreadoutlibs/wib2/tpg/ProcessRSAVX2.hpp"
 #include "fdreadoutlibs/wib2/tpg/ProcessNaive.hpp" // ditto
+#include <cmath>   // ProcessNaiveRS.hpp uses std::round and std::stringstream without including their headers
+#include <sstream>
+// The reference's scalar AbsRS processor for WIB2. NOT a scalar twin of wib2/tpg/ProcessRSAVX2.hpp: it keeps the running sum
+// in float (R = 0.8, scale 2), tracks the inter-quartile range of the RUNNING SUM rather than of the raw samples, hard-wires the
+// threshold 5 * sigma and accumulates the pedestal-subtracted sample (not the running sum) as charge, so its hits differ from
+// the AVX2 processor's by construction (tests/test_oracle_vs_reference.py quantifies it). Nothing is pinned to it.
+#include "fdreadoutlibs/wib2/tpg/ProcessNaiveRS.hpp"
 #include "fdreadoutlibs/wib2/tpg/DesignFIR.hpp"
 
 #include "../include/swtpg.h"
@@ -92,7 +99,8 @@ enum Wib2Impl
   kWib2SimpleAVX2 = 0,
   kWib2FirAVX2 = 1,
   kWib2FirNaive = 2,
-  kWib2AbsRSAVX2 = 3
+  kWib2AbsRSAVX2 = 3,
+  kWib2AbsRSNaive = 4 // wib2/tpg/ProcessNaiveRS.hpp: float running sum, IQR of the running sum, threshold 5 * sigma
 };
 
 struct Wib2Ref
@@ -364,10 +372,12 @@ ref_wib2_process(void* h, const uint8_t* superchunks, size_t n_sc, uint32_t link
       case kWib2SimpleAVX2: process_window_avx2(*r->info, off); break;
       case kWib2FirAVX2: process_window_avx2(*r->info); break;
       case kWib2FirNaive: process_window_naive(*r->info, off); break;
+      case kWib2AbsRSNaive: process_window_naive_RS(*r->info, off); break; // prints one "Found N hits" line per call (:224)
       default: process_window_rs_avx2(*r->info, off); break;
     }
-    const bool fir = (r->impl == kWib2FirAVX2 || r->impl == kWib2FirNaive);
-    long k = decode_wib2(r->info->output, r->impl == kWib2FirNaive, fir ? 0 : 128 * r->sel, r->sel, ts, link, out, cap, n);
+    const bool scalar = (r->impl == kWib2FirNaive || r->impl == kWib2AbsRSNaive); // {position, itime, charge, tover} records
+    const bool positions = scalar || r->impl == kWib2FirAVX2;                       // channel ids relative to the handler's 128
+    long k = decode_wib2(r->info->output, scalar, positions ? 0 : 128 * r->sel, r->sel, ts, link, out, cap, n);
     if (k < 0)
       return -1;
     n += size_t(k);

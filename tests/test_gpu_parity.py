@@ -39,6 +39,80 @@ def test_golden_cases(name, golden):
     assert (ped == golden[name + "__pedestal"]).all()
 
 
+NAIVE_CASES = sorted(n for n, c in cases.GOLDEN_CASES.items() if c["flavour"] == 1)
+
+
+@pytest.mark.parametrize("name", NAIVE_CASES)
+def test_naive_golden_cases_where_defined(name, golden):
+    """north_star: bit-exact against the reference's naive AND AVX2 processors. The CUDA path follows the AVX2 code (the
+    production one); the scalar code agrees with it wherever SURVEY H3-H7 say the two are defined alike — accumulator limit 10,
+    charge below 32768, FIR threshold 5 with sigma below its clamp — after mapping the naive record's register position to
+    the frame channel. These are the reference's own NAIVE outputs (tests/golden/make_golden.py, ref_impl of the case).
+    The one documented divergence, charge overflow (H3: AVX2 wraps mod 2^16, the scalar code saturates), is asserted as such."""
+    case = cases.GOLDEN_CASES[name]
+    tps, ped = run_gpu(case, cases.make_input(case))
+    want = golden[name + "__tps"]
+    if case["kind"] == "overflow":
+        assert tps.size == want.size == 1
+        for f in ("time_start", "time_peak", "time_over_threshold", "adc_peak", "channel"):
+            assert tps[0][f] == want[0][f]
+        assert (tps[0]["adc_integral"], want[0]["adc_integral"]) == (59990, 32767)
+    else:
+        assert_same_tps(tps, want, name)
+    assert (ped == golden[name + "__pedestal"]).all()
+
+
+@pytest.mark.parametrize("fmt", ["wibeth", "wib2"])
+@pytest.mark.parametrize("thr", [5, 6, 7, 9, 11, 40])
+def test_fir_thresholds_beyond_the_packed_comparator_range(fmt, thr):
+    """sigma * multiplier * threshold is compared as a SIGNED int16 by the reference (_mm256_cmpgt_epi16 on the 16-bit lanes of a
+    64-bit-lane product, wib2/tpg/ProcessAVX2FIR.hpp:208): with multiplier 64 it goes negative once sigma * threshold > 511,
+    i.e. for threshold >= 6 on a channel whose IQR reaches 57..86 — is_over is then true for almost every sample and the
+    charge takes an arithmetic shift of a possibly negative filter output. Wide noise (sigma at its clamp of 102) puts every
+    channel there; 102 * 64 * 5 = 32640 is the last product the packed comparator handles, everything above runs the
+    exact-threshold tier. TPs, quartiles and the FIR ring must match the oracle (pinned to the reference for these inputs by
+    tests/test_oracle_vs_reference.py::test_fir_threshold_64bit_lane_product and the wib2_fir_thr*_noisy golden cases)."""
+    p = S.gen_params(61, 0.3, noise_q8=40 * 256)
+    n_links, n_units = 3, 40
+    units = (S.gen_wib2_host if fmt == "wib2" else S.gen_wibeth_host)(p, n_links, n_units)
+    cfg = B.make_config(fmt=fmt, algorithm=S.ALGORITHMS["FIR"], threshold=thr)
+    want, oracles = B.oracle_process_links(cfg, units)
+    with S.TPGenerator(n_links, 16, fmt=fmt, algorithm="FIR", threshold=thr, tp_capacity=1 << 20) as g:
+        g.start()
+        parts = [g.process_host(np.ascontiguousarray(units[:, u:u + 16]), units_stride=min(16, n_units - u)) for u in range(0, n_units, 16)]
+        got = np.concatenate(parts)
+        assert got.size > 100
+        assert_same_tps(got, want, f"{fmt} FIR thr {thr}")
+        st, so = g.dump_state(1), oracles[1].state()
+        for f in ("pedestal", "quantile25", "quantile75", "accum25", "accum75", "prev_was_over", "hit_charge", "hit_tover", "prev_samp"):
+            assert (st[f] == so[f]).all(), f
+
+
+def test_unpack_known_answer_through_the_abi():
+    """unittest/WIBEthFrameExpansion_test.cxx:92-156 and test/apps/wib2_test_bench.cxx:233-254 on the CUDA path: a frame whose
+    ADC value IS its channel number. The pedestal is seeded with the first sample and never moves on a constant input, so the
+    per-sample pedestal dump of swtpg_process_host_debug is the unpacked frame, by FRAME channel (the lane permutation of the
+    AVX2 registers, H1, does not exist on this path), and the pedestal-subtracted waveform is zero."""
+    with S.TPGenerator(1, 1, threshold=60) as g:
+        g.start()
+        tps, ped, wav = g.process_host(cases.unpack_kat_frame()[None, None], debug=True)
+        assert tps.size == 0
+        assert (ped[0, 0] == np.arange(64, dtype=np.int16)[None, :]).all() and not wav.any()
+        assert (g.dump_state(0)["pedestal"] == np.arange(64)).all()
+    with S.TPGenerator(1, 1, fmt="wib2", threshold=60) as g:
+        g.start()
+        tps, ped, wav = g.process_host(cases.unpack_kat_superchunk()[None, None], debug=True)
+        assert tps.size == 0
+        assert (ped[0, 0] == (0x3A0 + np.arange(256, dtype=np.int16))[None, :]).all() and not wav.any()
+    # every 14-bit value at every bit offset of the row: channel c carries (5 * 64 * t + 321 * c) mod 2^14 at tick t
+    adc = ((5 * 64 * np.arange(64)[:, None] + 321 * np.arange(64)[None, :]) % 16384).astype(np.uint16)
+    fr = F.pack_wibeth_frames(adc[None], 7)[0]
+    with S.TPGenerator(1, 1, threshold=16383) as g:
+        g.start()
+        _, ped, wav = g.process_host(fr[None, None], debug=True)
+        assert ((ped[0, 0].astype(np.int32) + wav[0, 0]) == adc).all()  # pedestal + (sample - pedestal) = the unpacked sample
+
+
 @pytest.mark.parametrize("name", ["noise_simple_thr60", "dense_simple_thr8", "noise_absrs_thr30", "wib2_simple_thr100", "wib2_fir_thr5", "wib2_absrs_thr60"])
 @pytest.mark.parametrize("max_units", [1, 7, 32])
 def test_batching_does_not_change_results(name, max_units, golden):
@@ -221,10 +295,7 @@ def test_wib2_many_links_ragged_and_streaming():
                 while not g.submit(l, units[l, u]):
                     got.append(g.poll())
             got.append(g.poll())
-        g.flush()
-        g.sync()
-        for _ in range(8):
-            got.append(g.poll())
+        got.append(g.drain())  # flush + sync + poll until the library reports nothing pending, in flight or ready
     assert_same_tps(np.concatenate(got), want2, "wib2 streaming")
 
 
@@ -328,10 +399,7 @@ def test_streaming_submit_poll_equals_batch():
                     busy += 1
                     got.append(g.poll())  # back-pressure: drain completed batches, then retry
             got.append(g.poll())
-        g.flush()
-        g.sync()
-        for _ in range(8):
-            got.append(g.poll())
+        got.append(g.drain())  # flush + sync + poll until the library reports nothing pending, in flight or ready
         c = g.counters()
         assert c["units_processed"] == n_links * n_units
         assert c["h2d_bytes"] == n_links * n_units * 7200
@@ -361,12 +429,12 @@ def test_streaming_zero_copy_from_a_registered_latency_buffer():
                 while not g.submit(l, src):
                     got.append(g.poll())
             got.append(g.poll())
-        g.flush()
-        g.sync()
-        for _ in range(8):
-            got.append(g.poll())
+        got.append(g.drain())  # flush + sync + poll until the library reports nothing pending, in flight or ready
         c = g.counters()
         assert c["units_processed"] == n_links * n_units and c["h2d_bytes"] == n_links * n_units * 7200
+        # links 0, 1, 2 entirely by address, link 3 entirely by copy, link 4 by address except every third payload
+        by_address = 3 * n_units + sum(1 for u in range(n_units) if u % 3)
+        assert (c["units_zero_copy"], c["units_staged"]) == (by_address, n_links * n_units - by_address)
         g.unregister_buffer(ring)
         g.unregister_buffer(latency_buffer)
         with pytest.raises(S.SwtpgError):
@@ -418,7 +486,7 @@ def test_streaming_back_pressure_is_busy_not_blocking():
         assert n_slots * sc <= accepted <= 2 * n_slots * sc, accepted  # n_slots batches + at most one ring of pending units
         assert accepted < units.shape[1]
         assert g.counters()["submit_busy"] > 0
-        assert not g.flush()  # every batch waits to be polled
+        assert not g.flush(busy_ok=True)  # every batch waits to be polled
         got.append(g.drain())
         for u in range(accepted, units.shape[1]):
             assert g.submit(0, units[0, u], wait_us=2_000_000)
@@ -465,7 +533,7 @@ def test_streaming_concurrent_feeders_and_flushes():
 
         def watchdog():
             while not stop.is_set():
-                g.flush()
+                g.flush(busy_ok=True)
                 time.sleep(0.0005)
 
         def poller():
@@ -569,6 +637,27 @@ def test_full_size_one_apa_properties():
         host = buf.view(n_links, n_units, 7200)[l].cpu().numpy()
         want = B.Oracle(cfg, link_id=l).process(host, cap=1 << 20)
         assert_same_tps(one[one["link"] == l], want, f"link {l} vs oracle")
+    # BASELINE config[1] names the FIR kernel: the same properties for the fused unpack -> pedestal -> FIR -> hit-find kernel
+    with S.TPGenerator(n_links, n_units, algorithm="FIR", threshold=5, tp_capacity=1 << 22) as g:
+        g.start()
+        g.process_device(buf.data_ptr(), n_units)
+        fir_one = g.fetch_tps(cap=1 << 22)
+    parts = []
+    with S.TPGenerator(n_links, n_units, algorithm="FIR", threshold=5, tp_capacity=1 << 22) as g:
+        g.start()
+        view = buf.view(n_links, n_units, 7200)
+        ts = torch.cuda.current_stream().cuda_stream
+        for b in range(16):
+            chunk = view[:, b * 512:(b + 1) * 512].contiguous()
+            g.process_device(chunk.data_ptr(), 512, stream=ts)
+            parts.append(g.fetch_tps(cap=1 << 22))
+    assert fir_one.size > 10000
+    assert_same_tps(np.concatenate(parts), fir_one, "FIR batch split")
+    fcfg = B.make_config(algorithm=S.ALGORITHMS["FIR"], threshold=5)
+    for l in (3, 38):
+        host = buf.view(n_links, n_units, 7200)[l].cpu().numpy()
+        want = B.Oracle(fcfg, link_id=l).process(host, cap=1 << 20)
+        assert_same_tps(fir_one[fir_one["link"] == l], want, f"FIR link {l} vs oracle")
 
 
 @pytest.mark.parametrize("thr", [60, 20])

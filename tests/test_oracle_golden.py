@@ -47,6 +47,29 @@ def test_edge_square_spans_frame_boundary():
     assert tp["adc_integral"] == 9 * 600 and tp["adc_peak"] == 600
 
 
+def test_documented_pulse_and_edge_patterns():
+    """docs/README.md:111-116, hand-derived answers (zero frames: pedestal 0, eight ticks over it never move the frugal median).
+    pulse: one tick of 650 on channel 33 at tick 17 of frame 1 -> ends at tick 18 with ToT 1.
+    edge left / right: the 8-tick triangle 501 520 540 560 540 520 505 501 across the frame boundary -> ONE TP, reported by the
+    second frame, time_start before that frame's timestamp; the peak time counts from the hit start."""
+    cfg = B.make_config(threshold=499)
+    for flav in (B.FLAVOUR_AVX2, B.FLAVOUR_NAIVE):
+        tp = B.Oracle(cfg, flav).process(cases.pulse_frames())
+        assert tp.size == 1
+        ts1 = (1 << 34) + 2048
+        assert (tp[0]["channel"], tp[0]["time_start"], tp[0]["time_over_threshold"], tp[0]["adc_integral"], tp[0]["adc_peak"]) == \
+            (33, ts1 + 32 * 17, 32, 650, 650)
+        assert tp[0]["time_peak"] == tp[0]["time_start"]
+        for frames, ch, ts0, n_first in ((cases.edge_left_frames(), 20, 1 << 35, 5), (cases.edge_right_frames(), 47, 1 << 36, 2)):
+            tp = B.Oracle(cfg, flav).process(frames)
+            assert tp.size == 1
+            t_end = 8 - n_first                              # first tick of frame 1 that is not over threshold any more
+            start = ts0 + 2048 + 32 * (t_end - 8)            # = 32 * n_first ticks before frame 1
+            assert (tp[0]["channel"], tp[0]["time_start"], tp[0]["time_over_threshold"]) == (ch, start, 8 * 32)
+            assert tp[0]["adc_integral"] == sum(cases.EDGE_TRIANGLE) and tp[0]["adc_peak"] == 560
+            assert tp[0]["time_peak"] == start + 32 * 3      # 560 is the 4th sample of the pulse
+
+
 def test_charge_overflow_avx2_wraps_naive_saturates():
     """20 ticks x 3000 ADC -> AVX2 add_epi16 wraps mod 2^16, the scalar code saturates at 32767."""
     frames = cases.overflow_frames()

@@ -91,3 +91,22 @@ def test_fir_threshold_64bit_lane_product():
         o = B.Oracle(B.make_config(fmt="wib2", algorithm=3, threshold=thr))
         r = B.ReferenceWib2(B.REF_WIB2_FIR_AVX2, thr)
         assert_same_tps(o.process(sc), r.process(sc), f"thr {thr}")
+
+
+def test_wib2_naive_rs_is_a_different_algorithm(capfd):
+    """wib2/tpg/ProcessNaiveRS.hpp:22-228 is wrapped like every other processor of the reference, but it is not a scalar twin of
+    wib2/tpg/ProcessRSAVX2.hpp: float running sum with R = 0.8 and scale 2 (:31-33,:122-130), quartiles of the RUNNING SUM
+    (:146-152), threshold hard-wired to 5 * sigma (:175), charge = sum of the pedestal-subtracted SAMPLE >> exponent (:179).
+    So there is nothing to pin to it; this test documents by how much the two disagree on ordinary input, so that nobody
+    mistakes it for a parity target (the CUDA path follows the AVX2 processor, like every production configuration)."""
+    sc = S.gen_wib2_host(S.gen_params(5, 0.05), 1, 100)[0]
+    avx = B.ReferenceWib2(B.REF_WIB2_ABSRS_AVX2, threshold=5).process(sc)
+    naive = B.ReferenceWib2(B.REF_WIB2_ABSRS_NAIVE, threshold=5).process(sc)
+    capfd.readouterr()  # the header prints "Found N hits" per call
+    assert avx.size == 228 and naive.size == 202
+    key = lambda t: set(zip(t["channel"].tolist(), t["time_start"].tolist()))
+    assert len(key(avx) & key(naive)) == 16  # 7 % of the hits share channel and start time; none of those shares its charge
+    both = {k: None for k in key(avx) & key(naive)}
+    ca = {(c, t): q for c, t, q in zip(avx["channel"].tolist(), avx["time_start"].tolist(), avx["adc_integral"].tolist())}
+    cn = {(c, t): q for c, t, q in zip(naive["channel"].tolist(), naive["time_start"].tolist(), naive["adc_integral"].tolist())}
+    assert all(ca[k] != cn[k] for k in both)
