@@ -42,7 +42,12 @@ host: $(HOST)
 $(HOST): fdreadoutlibs_b200/host/swtpg_host.cpp fdreadoutlibs_b200/host/swtpg_host.hpp include/swtpg.h $(LIB)
 	g++ -O2 -std=c++17 -Wall -Wextra -fPIC -shared -pthread -o $@ fdreadoutlibs_b200/host/swtpg_host.cpp -Lfdreadoutlibs_b200 -lswtpg_b200 -Wl,-rpath,'$$ORIGIN'
 
-apps:
+EMU = build/bin/wibeth_tpg_algorithms_emulator
+apps: $(EMU)
+$(EMU): apps/wibeth_tpg_algorithms_emulator.cpp fdreadoutlibs_b200/host/swtpg_host.hpp $(HOST)
+	@mkdir -p build/bin
+	g++ -O2 -std=c++17 -Wall -Wextra -pthread -o $@ apps/wibeth_tpg_algorithms_emulator.cpp -Lfdreadoutlibs_b200 -lswtpg_host -lswtpg_b200 \
+	  -Wl,-rpath,'$$ORIGIN/../../fdreadoutlibs_b200'
 
 oracle:
 	$(MAKE) -C oracle all

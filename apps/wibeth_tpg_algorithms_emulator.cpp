@@ -199,8 +199,11 @@ main(int argc, char** argv)
       c.tpg_threshold = uint16_t(o.threshold);
       c.crate_id = uint16_t(h0->crate_id);
       c.slot_id = uint16_t(h0->slot_id);
-      c.link_id = uint16_t(l == 0 ? h0->stream_id : (h0->stream_id + l) & 0xFF);
-      c.emulator_mode = looping || l != 0; // replicated links get their own geo id stamped, like emulated links
+      c.link_id = uint16_t((h0->stream_id + l) & 0xFF);
+      if (l != 0) // a replicated link is the same data arriving on another stream of the same crate and slot
+        for (auto& f : frames[l])
+          f.header()->stream_id = c.link_id;
+      c.emulator_mode = looping; // when the file is replayed over and over the timestamps keep running, as on emulated links
       c.block_on_backpressure = true;      // a replay stalls its source instead of dropping frames
       c.tp_timeout = ~uint64_t(0);
       procs[l]->conf(c);

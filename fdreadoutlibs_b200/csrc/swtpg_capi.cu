@@ -53,7 +53,10 @@ struct Geo
 #define SWTPG_GEO_STAGES 2
 #define SWTPG_GEO_CHUNK 32
 #endif
-using GeoDefault = Geo<1, SWTPG_GEO_STAGES, SWTPG_GEO_CHUNK>;
+#ifndef SWTPG_GEO_MINCTAS
+#define SWTPG_GEO_MINCTAS 1
+#endif
+using GeoDefault = Geo<1, SWTPG_GEO_STAGES, SWTPG_GEO_CHUNK, SWTPG_GEO_MINCTAS>;
 
 template<class Algo, bool DUMP, class G>
 cudaError_t

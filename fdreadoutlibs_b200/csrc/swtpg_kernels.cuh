@@ -873,8 +873,14 @@ struct PackedRsWibEth : PackedSimpleWibEth
 //     6 packed adds per tick instead of 7 multiply-adds on a rotating ring, and every add wraps mod 2^16 exactly like the
 //     reference's mullo/add chain (ring homomorphism). The carried state stays the reference's ring: it is converted to
 //     cascade registers when a link is loaded and back when it is stored, which also removes the ring phase from the loop;
-//   * accumulators are fp16x2 subnormals (see PackedSimpleWibEth); q25 is kept as 1 - q25 and q75 as q75 + 2, so that the
-//     sign tests are single VIADDMNMX.RELU ops against S and ~S and sigma + 3 is their clamped sum;
+//   * accumulators are fp16x2 subnormals and the median lives as 16385 - median against the biased sample Sb = S - 16384,
+//     with the four-instruction step of PackedSimpleT;
+//   * the two quartile trackers are ONE frugal step per tick: q25 moves only on the halves below the OLD median and q75 only on
+//     the halves above it (:119-121), so per half at most one of them does anything. The step runs on per-half SELECTED
+//     operands — (Sb, 16385 - q25, acc25) where the sample is below, (~S, q75 + 2, -acc75) elsewhere: with the sample and the
+//     accumulator negated the q75 tracker obeys the same "register += down - up" rule as the q25 one — and is written back
+//     through the two masks; where the sample equals the median the result is simply dropped. Both registers stay inside
+//     [2, 16405], so their +-1 steps are one 32-bit IADD3 like the median's. 15 instructions instead of 21;
 //   * while every sigma of the warp is >= 0 the 64-bit-lane product equals the per-channel product (no carries between
 //     positions) and is one packed IMAD; a warp that sees a negative sigma in a 4-tick group recomputes that
 //     group's thresholds with iqr_threshold_exact.
@@ -886,12 +892,13 @@ struct PackedFirIqr
   static constexpr int kWib2MinCtas = 5;
   static constexpr int kQuadCtasPerSm = 5; // CTA form, 20 consumer warps per SM: 14 % faster than one warp per CTA for this policy
                                            // (64 registers instead of 109; profiles/r01_quad_vs_warp.txt)
-  uint32_t Mq, A, Q25q, A25, Q75p, A75; // 1 - median, (acc - 1); 1 - q25, acc25; q75 + 2, acc75   (accumulators: fp16 subnormals)
+  // 16385 - median, acc - 1;  16385 - q25, acc25 - 1;  q75 + 2, -acc75 - 1   (accumulators: fp16x2 subnormal bit patterns)
+  uint32_t Mq, A, Q25n, A25, Q75p, A75n;
   uint32_t d1, d2, d3, d4, d5, d6, o1, o2; // cascade: d_j = previous input of stage j, o1/o2 = previous two outputs
   uint32_t prev, C, Tn;
   uint32_t xmax, sig3max, K, Kneg3, shift, shmask, thr_cfg, mult;
 
-  static __device__ __forceinline__ uint32_t sample(const uint32_t* row, const PairPos& pp) { return extract_pair(row, pp); }
+  static __device__ __forceinline__ uint32_t sample(const uint32_t* row, const PairPos& pp) { return extract_pair_biased(row, pp); }
   template<int ROW_WORDS = 28>
   __device__ __forceinline__ void begin_chunk(const uint32_t*, const PairPos&) {}
   template<bool WIB2_UNITS = false>
@@ -940,17 +947,34 @@ struct PackedFirIqr
     o2 = o1;
     o1 = y6;
   }
-  __device__ __forceinline__ void load(const uint32_t* st, uint32_t lane, uint32_t flags)
+  // the three trackers and the hit state, HBM form <-> register form (shared by the policies derived from this one)
+  __device__ __forceinline__ void load_trackers(const uint32_t* st, uint32_t lane)
   {
-    Mq = add2(~st[SV_MEDIAN * 32 + lane], 0x00020002u);
+    Mq = add2(~st[SV_MEDIAN * 32 + lane], 0x40024002u);       // ~m = -m - 1
     A = to_sm(add2(st[SV_ACCUM * 32 + lane], 0xFFFFFFFFu));
-    Q25q = add2(~st[SV_Q25 * 32 + lane], 0x00020002u);
-    A25 = to_sm(st[SV_A25 * 32 + lane]);
+    Q25n = add2(~st[SV_Q25 * 32 + lane], 0x40024002u);
+    A25 = to_sm(add2(st[SV_A25 * 32 + lane], 0xFFFFFFFFu));
     Q75p = add2(st[SV_Q75 * 32 + lane], 0x00020002u);
-    A75 = to_sm(st[SV_A75 * 32 + lane]);
+    A75n = to_sm(~st[SV_A75 * 32 + lane]);                     // ~a = -a - 1
     prev = st[SV_PREV * 32 + lane];
     C = st[SV_CHARGE * 32 + lane];
     Tn = neg2(st[SV_TOVER * 32 + lane]);
+  }
+  __device__ __forceinline__ void store_trackers(uint32_t* st, uint32_t lane) const
+  {
+    st[SV_MEDIAN * 32 + lane] = median();
+    st[SV_ACCUM * 32 + lane] = add2(from_sm(A), 0x00010001u);
+    st[SV_Q25 * 32 + lane] = add2(~Q25n, 0x40024002u);
+    st[SV_A25 * 32 + lane] = add2(from_sm(A25), 0x00010001u);
+    st[SV_Q75 * 32 + lane] = add2(Q75p, 0xFFFEFFFEu);
+    st[SV_A75 * 32 + lane] = ~from_sm(A75n);
+    st[SV_PREV * 32 + lane] = prev;
+    st[SV_CHARGE * 32 + lane] = C;
+    st[SV_TOVER * 32 + lane] = neg2(Tn);
+  }
+  __device__ __forceinline__ void load(const uint32_t* st, uint32_t lane, uint32_t flags)
+  {
+    load_trackers(st, lane);
     // ring -> cascade: replay the ring's 8 samples, oldest first, through an empty cascade (the state only depends on them)
     const uint32_t k = (flags >> 8) & 7u; // next slot to be written = oldest sample
     kphase0 = k;
@@ -958,18 +982,10 @@ struct PackedFirIqr
     for (uint32_t i = 0; i < 8; ++i)
       cascade(st[(SV_RING0 + ((k + i) & 7u)) * 32 + lane]);
   }
-  __device__ __forceinline__ uint32_t median() const { return add2(~Mq, 0x00020002u); }
+  __device__ __forceinline__ uint32_t median() const { return add2(~Mq, 0x40024002u); } // 16385 - Mq
   __device__ __forceinline__ void store(uint32_t* st, uint32_t lane, uint32_t k_end) const
   {
-    st[SV_MEDIAN * 32 + lane] = median();
-    st[SV_ACCUM * 32 + lane] = add2(from_sm(A), 0x00010001u);
-    st[SV_Q25 * 32 + lane] = add2(~Q25q, 0x00020002u);
-    st[SV_A25 * 32 + lane] = from_sm(A25);
-    st[SV_Q75 * 32 + lane] = add2(Q75p, 0xFFFEFFFEu);
-    st[SV_A75 * 32 + lane] = from_sm(A75);
-    st[SV_PREV * 32 + lane] = prev;
-    st[SV_CHARGE * 32 + lane] = C;
-    st[SV_TOVER * 32 + lane] = neg2(Tn);
+    store_trackers(st, lane);
     // cascade -> ring, by running the cascade backwards: with Y[j] = y_j one tick ago (y_0 = the sample itself),
     // y_{j-1}(two ticks ago) = Y[j] - Y[j-1]; every step back in time loses the top stage, and y_0 is the ring entry.
     uint32_t Y[7] = { d1, d2, d3, d4, d5, d6, o1 };
@@ -996,49 +1012,40 @@ struct PackedFirIqr
   uint32_t kphase0;
   __device__ __forceinline__ uint32_t phase_after(uint32_t ticks) const { return (kphase0 + ticks) & 7u; }
   // setState: pedestal = first sample, quartiles +-20 (wib2/tpg/ProcessingInfo.hpp:101-141)
-  __device__ __forceinline__ void seed(uint32_t S)
+  __device__ __forceinline__ void seed(uint32_t Sb) // Sb = ped - 16384
   {
-    Mq = add2(~S, 0x00020002u);                // 1 - ped
-    Q25q = add2(~S, 0x00160016u);              // 1 - (ped - 20)
-    Q75p = add2(S, 0x00160016u);               // (ped + 20) + 2
+    Mq = add2(~Sb, 0x00020002u);               // 16385 - ped = 1 - Sb
+    Q25n = add2(~Sb, 0x00160016u);             // 16385 - (ped - 20)
+    Q75p = add2(Sb, 0x40164016u);              // (ped + 20) + 2
   }
 
-  // One frugal quartile step on the lanes `en` (1.0 / 0.0 per half). sgn = sign(raw - q) * 2^-24.
-  //   NEG_REP: q is held as 1 - q (step up = add the 0xFFFF mask, step down = add the bit pattern 1), else as q + 2.
-  template<bool NEG_REP>
-  static __device__ __forceinline__ void quartile_step(uint32_t& Q, uint32_t& Aq, uint32_t sgn, uint32_t en)
+  // The three frugal trackers of one tick (Sb = raw - 16384); returns s' + 1 = raw - median + 1 (updated median);
+  // sig3 = min(sigma, sigmaMax) + 3.
+  __device__ __forceinline__ uint32_t track(uint32_t Sb, uint32_t& sig3)
   {
-    const uint32_t T = hfma2_bits(en, sgn, Aq);                       // acc (+= sign on enabled lanes)
-    const uint32_t keep = ne2_abs_one(T, kUp);                        // 1.0 unless |acc| == L+1
-    uint32_t a, b;
-    if constexpr (NEG_REP) {
-      a = eq2_mask(T, kUp);                                           // up:   -1
-      b = hfma2_sat_bits(T, kNegOne, kNegL);                          // down: +1
-    } else {
-      a = hfma2_sat_bits(T, kOne, kNegL);                             // up:   +1
-      b = eq2_mask(T, kDnEq);                                         // down: -1
-    }
-    Aq = hfma2_bits(keep, T, 0u);                                     // reset where stepped
-    Q = add2(add2(Q, a), b);
-  }
-
-  // The three frugal trackers of one tick; returns s' + 1 = raw - median + 1 (updated median); sig3 = min(sigma, sigmaMax) + 3.
-  __device__ __forceinline__ uint32_t track(uint32_t S, uint32_t& sig3)
-  {
-    const uint32_t sg1 = addclamp2(S, Mq, 0x00020002u);               // sign(raw - median) + 1, OLD median   (:108-117)
-    const uint32_t ltf = eq2_one(sg1, 0u), gtf = eq2_one(sg1, 0x00020002u);
-    // q25 on the lanes below the median (:119)
-    quartile_step<true>(Q25q, A25, hadd2_bits(addclamp2(S, Q25q, 0x00020002u), kNegTiny), ltf);
-    // q75 on the lanes above (:121): 1 - sign(raw - q75) from ~S = -S - 1
-    quartile_step<false>(Q75p, A75, hfma2_bits(addclamp2(~S, Q75p, 0x00020002u), kNegOne, kTiny), gtf);
-    // median (:125), as PackedSimpleWibEth::pedestal_step with L = 10
+    const uint32_t sg1 = addclamp2(Sb, Mq, 0x00020002u);              // sign(raw - median) + 1, OLD median   (:108-117)
+    // the quartiles: q25 on the halves below the median (:119), q75 on the halves above (:121) — one step on selected operands
+    const uint32_t lt = eq2_mask(sg1, 0u), gt = eq2_mask(sg1, 0x00020002u);
+    const uint32_t a = (lt & Sb) | (~lt & (~Sb | 0xC000C000u));       // raw - 16384 below; ~raw = -raw - 1 elsewhere (one LOP3)
+    const uint32_t Qs = (lt & Q25n) | (~lt & Q75p), As = (lt & A25) | (~lt & A75n);
+    const uint32_t sgq = addclamp2(a, Qs, 0x00020002u);               // sign(raw - q25) + 1  |  sign(q75 - raw) + 1
+    const uint32_t Tq = hadd2_bits(As, sgq);                          // acc25  |  -acc75, after this sample
+    const uint32_t uq = hfma2_sat_bits(Tq, kOne, kNegL);              // bit pattern 1 where it reached  L+1 ...
+    const uint32_t dq = hfma2_sat_bits(Tq, kNegOne, kNegL);           // ...                            -(L+1)
+    const uint32_t An = hfma2_bits(ne2_abs_one(Tq, kUp), Tq, kNegTiny); // (stepped ? 0 : acc) - 1
+    const uint32_t Qn = Qs + dq - uq;                                 // 16385 - q25 steps down when q25 steps up; q75 + 2 steps up when
+                                                                      // -acc75 reached -(L+1): the same rule for both, one IADD3
+    Q25n = (lt & Qn) | (~lt & Q25n);
+    A25 = (lt & An) | (~lt & A25);
+    Q75p = (gt & Qn) | (~gt & Q75p);                                  // raw == median: neither moves, the step is dropped
+    A75n = (gt & An) | (~gt & A75n);
+    // median (:125), as PackedSimpleT::pedestal_step with L = 10
     const uint32_t T = hadd2_bits(A, sg1);
-    const uint32_t upm = eq2_mask(T, kUp);
-    const uint32_t dn1 = hfma2_sat_bits(T, kNegOne, kNegL);
+    const uint32_t up1 = hfma2_sat_bits(T, kOne, kNegL), dn1 = hfma2_sat_bits(T, kNegOne, kNegL);
     A = hfma2_bits(ne2_abs_one(T, kUp), T, kNegTiny);
-    Mq = add2(add2(Mq, upm), dn1);
-    sig3 = addmin2(Q75p, Q25q, sig3max);                              // min(q75 - q25, sigmaMax) + 3        (:131-134)
-    return add2(S, Mq);
+    Mq = Mq + dn1 - up1;
+    sig3 = addmin2(add2(Q75p, 0xC000C000u), Q25n, sig3max);           // min(q75 - q25, sigmaMax) + 3        (:131-134)
+    return add2(Sb, Mq);
   }
   // One tick: returns the filter output of this tick.
   __device__ __forceinline__ uint32_t tick(uint32_t S, uint32_t& sig3)
@@ -1116,7 +1123,7 @@ struct PackedFirIqr
     uint32_t filt[G], sig3[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      filt[g] = tick(extract_pair(rows + g * ROW_WORDS, pp), sig3[g]);
+      filt[g] = tick(extract_pair_biased(rows + g * ROW_WORDS, pp), sig3[g]);
       if constexpr (DUMP) {
         ped_out[g] = median();
         wav_out[g] = filt[g];
@@ -1151,15 +1158,7 @@ struct PackedFirIqrAnyTaps : PackedFirIqr
   static __device__ __forceinline__ uint32_t swap_halves(uint32_t v) { return __byte_perm(v, v, 0x1032); }
   __device__ __forceinline__ void load(const uint32_t* st, uint32_t lane, uint32_t flags)
   {
-    Mq = add2(~st[SV_MEDIAN * 32 + lane], 0x00020002u);
-    A = to_sm(add2(st[SV_ACCUM * 32 + lane], 0xFFFFFFFFu));
-    Q25q = add2(~st[SV_Q25 * 32 + lane], 0x00020002u);
-    A25 = to_sm(st[SV_A25 * 32 + lane]);
-    Q75p = add2(st[SV_Q75 * 32 + lane], 0x00020002u);
-    A75 = to_sm(st[SV_A75 * 32 + lane]);
-    prev = st[SV_PREV * 32 + lane];
-    C = st[SV_CHARGE * 32 + lane];
-    Tn = neg2(st[SV_TOVER * 32 + lane]);
+    load_trackers(st, lane);
     const uint32_t k = (flags >> 8) & 7u; // next slot to be written = oldest sample
     kphase0 = k;
 #pragma unroll
@@ -1170,15 +1169,7 @@ struct PackedFirIqrAnyTaps : PackedFirIqr
   }
   __device__ __forceinline__ void store(uint32_t* st, uint32_t lane, uint32_t k_end) const
   {
-    st[SV_MEDIAN * 32 + lane] = median();
-    st[SV_ACCUM * 32 + lane] = add2(from_sm(A), 0x00010001u);
-    st[SV_Q25 * 32 + lane] = add2(~Q25q, 0x00020002u);
-    st[SV_A25 * 32 + lane] = from_sm(A25);
-    st[SV_Q75 * 32 + lane] = add2(Q75p, 0xFFFEFFFEu);
-    st[SV_A75 * 32 + lane] = from_sm(A75);
-    st[SV_PREV * 32 + lane] = prev;
-    st[SV_CHARGE * 32 + lane] = C;
-    st[SV_TOVER * 32 + lane] = neg2(Tn);
+    store_trackers(st, lane);
 #pragma unroll
     for (uint32_t i = 0; i < 8; ++i)
       st[(SV_RING0 + ((k_end + i) & 7u)) * 32 + lane] = w[i]; // w[0] is the oldest = the slot written next
@@ -1211,7 +1202,7 @@ struct PackedFirIqrAnyTaps : PackedFirIqr
     uint32_t filt[G], sig3[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      filt[g] = tick(extract_pair(rows + g * ROW_WORDS, pp), sig3[g]);
+      filt[g] = tick(extract_pair_biased(rows + g * ROW_WORDS, pp), sig3[g]);
       if constexpr (DUMP) {
         ped_out[g] = median();
         wav_out[g] = filt[g];
@@ -1250,15 +1241,7 @@ struct PackedRsIqrWib2 : PackedFirIqr
   }
   __device__ __forceinline__ void load(const uint32_t* st, uint32_t lane, uint32_t)
   {
-    Mq = add2(~st[SV_MEDIAN * 32 + lane], 0x00020002u);
-    A = to_sm(add2(st[SV_ACCUM * 32 + lane], 0xFFFFFFFFu));
-    Q25q = add2(~st[SV_Q25 * 32 + lane], 0x00020002u);
-    A25 = to_sm(st[SV_A25 * 32 + lane]);
-    Q75p = add2(st[SV_Q75 * 32 + lane], 0x00020002u);
-    A75 = to_sm(st[SV_A75 * 32 + lane]);
-    prev = st[SV_PREV * 32 + lane];
-    C = st[SV_CHARGE * 32 + lane];
-    Tn = neg2(st[SV_TOVER * 32 + lane]);
+    load_trackers(st, lane);
     RS1 = add2(st[SV_RS * 32 + lane], 0x00010001u);
     MRq = add2(~st[SV_MED_RS * 32 + lane], 0x00020002u);
     AR = to_sm(add2(st[SV_ACC_RS * 32 + lane], 0xFFFFFFFFu));
@@ -1266,15 +1249,7 @@ struct PackedRsIqrWib2 : PackedFirIqr
   }
   __device__ __forceinline__ void store(uint32_t* st, uint32_t lane, uint32_t) const
   {
-    st[SV_MEDIAN * 32 + lane] = median();
-    st[SV_ACCUM * 32 + lane] = add2(from_sm(A), 0x00010001u);
-    st[SV_Q25 * 32 + lane] = add2(~Q25q, 0x00020002u);
-    st[SV_A25 * 32 + lane] = from_sm(A25);
-    st[SV_Q75 * 32 + lane] = add2(Q75p, 0xFFFEFFFEu);
-    st[SV_A75 * 32 + lane] = from_sm(A75);
-    st[SV_PREV * 32 + lane] = prev;
-    st[SV_CHARGE * 32 + lane] = C;
-    st[SV_TOVER * 32 + lane] = neg2(Tn);
+    store_trackers(st, lane);
     st[SV_RS * 32 + lane] = add2(RS1, 0xFFFFFFFFu);
     st[SV_MED_RS * 32 + lane] = add2(~MRq, 0x00020002u);
     st[SV_ACC_RS * 32 + lane] = add2(from_sm(AR), 0x00010001u);
@@ -1340,7 +1315,7 @@ struct PackedRsIqrWib2 : PackedFirIqr
     uint32_t lv[G], rs[G], sig3[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      lv[g] = rs_step(track(extract_pair(rows + g * ROW_WORDS, pp), sig3[g]), rs[g]);
+      lv[g] = rs_step(track(extract_pair_biased(rows + g * ROW_WORDS, pp), sig3[g]), rs[g]);
       if constexpr (DUMP) {
         ped_out[g] = median();
         wav_out[g] = add2(lv[g], 0xFFFFFFFFu);
