@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--pulse-rate", type=float, default=0.02, help="pulses per channel per 64 ticks")
     ap.add_argument("--stream-links", type=int, default=240, help="links of the streaming (plug-in) run per GPU: 240 = 6 APAs")
     ap.add_argument("--stream-units", type=int, default=512, help="frames per link in the streaming run's latency buffer")
-    ap.add_argument("--stream-passes", type=int, default=8)
+    ap.add_argument("--stream-passes", type=int, default=16)
     ap.add_argument("--feeders", type=int, default=4, help="feeder threads of the streaming run per GPU")
     ap.add_argument("--module-links", type=int, default=6000, help="config[2] as written: links of the whole module, split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -386,6 +386,7 @@ def main():
             cpu_s = (r1.ru_utime - r0.ru_utime) + (r1.ru_stime - r0.ru_stime)
             dropped = sum(fp.get_info(l)["num_frames_dropped_busy"] for l in range(links))
             cnt = fp.counters()
+            tim = fp.stream_timing()
             n_tp = fp.tp_count()
             checked = 0
             if verify_links:  # untimed: the TriggerPrimitives of sampled links against the oracle (offline channel through the LUT, H2)
@@ -411,7 +412,10 @@ def main():
                 "host_cores_busy": cpu_s / dt, "feeder_cores_busy": st["feeder_cpu_s"] / dt, "feeder_us_per_frame": st["feeder_cpu_s"] / n * 1e6,
                 "core_seconds_per_apa_second": (cpu_s / dt) / max(1e-9, (n - dropped) * SAMPLES_PER_FRAME / dt / APA_SAMPLES_PER_S),
                 "units_by_address": cnt["units_zero_copy"], "units_by_copy": cnt["units_staged"], "batches": cnt["batches"], "tps": n_tp,
-                "late_bursts": st["late_bursts"], "verified_links": checked}
+                "late_bursts": st["late_bursts"], "verified_links": checked,
+                # device time of the engine's batches (CUDA events): the gather kernel IS the host-link transfer
+                "gather_ms_per_batch": tim["gather_ms"] / max(1, tim["batches"]), "kernel_ms_per_batch": tim["kernel_ms"] / max(1, tim["batches"]),
+                "gather_gbs_while_active": cnt["h2d_bytes"] / max(1e-9, tim["gather_ms"]) / 1e6}
 
     stream_main = run_stream(True, feeders, args.stream_passes)
     e2e_dt = max_over_ranks(stream_main["wall_seconds"])

@@ -243,6 +243,12 @@ class TPGenerator:
         self._check(lib.swtpg_stream_status(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def stream_timing(self):
+        """(device ms in the gather kernel, device ms in the TPG kernel, batches) of the streaming path since start()."""
+        g, k, n = C.c_double(0), C.c_double(0), C.c_uint64(0)
+        self._check(lib.swtpg_stream_timing(self._h, C.byref(g), C.byref(k), C.byref(n)))
+        return g.value, k.value, n.value
+
     # -- parity / monitoring -------------------------------------------------------------------------------------------------
     def dump_state(self, link: int) -> np.ndarray:
         out = np.zeros(self.channels, dtype=F.STATE_DTYPE)

@@ -58,7 +58,7 @@ struct Geo
 #endif
 using GeoDefault = Geo<1, SWTPG_GEO_STAGES, SWTPG_GEO_CHUNK, SWTPG_GEO_MINCTAS>;
 
-template<class Algo, bool DUMP, class G>
+template<class Algo, bool DUMP, class G, int WARPS_PER_SM = 0> // WARPS_PER_SM: 0 = the policy's own measured optimum (Algo::kWarpsPerSm)
 cudaError_t
 launch_wibeth_geo(const KernelParams& kp, cudaStream_t s)
 {
@@ -93,8 +93,9 @@ launch_wibeth_geo(const KernelParams& kp, cudaStream_t s)
   // sub-partition of every SM 20 % slower than its neighbours — profiles/README.md).
   const unsigned per_sm = unsigned(resident[dev]) / unsigned(sm_count[dev]);
   unsigned even = G::warps == 1 && per_sm >= 4 ? per_sm / 4 * 4 : per_sm;
-  if (G::warps == 1 && Algo::kWarpsPerSm > 0) // the policy's measured optimum, if the device holds that many
-    even = std::min<unsigned>(even, unsigned(Algo::kWarpsPerSm));
+  constexpr int kWarpsPerSm = WARPS_PER_SM > 0 ? WARPS_PER_SM : Algo::kWarpsPerSm;
+  if (G::warps == 1 && kWarpsPerSm > 0) // the measured optimum, if the device holds that many
+    even = std::min<unsigned>(even, unsigned(kWarpsPerSm));
   unsigned warps = std::min<unsigned>(kp.n_links, even * unsigned(sm_count[dev]) * G::warps);
   static const int warps_override = [] { const char* e = getenv("SWTPG_WARPS"); return e ? atoi(e) : 0; }(); // tuning aid
   if (warps_override > 0)
@@ -150,19 +151,35 @@ launch_wibeth_quad(const KernelParams& kp, cudaStream_t s)
 // for FIR + IQR (ptxas needs 64 registers instead of 109 for it, so 20 consumer warps fit an SM), the one-warp-per-CTA form
 // 2-5 % faster for SimpleThreshold and the running sums (the quad's lock-step costs more than the producer bookkeeping it
 // saves). SWTPG_WIBETH_KERNEL=warp forces the latter.
-// WIBEth SimpleThreshold, the production algorithm, runs the software-pipelined form of its policy (prefetch + deferred quiet
-// test, PackedSimpleT<true>) on the one-warp-per-CTA kernel with 16 persistent warps per SM. Measured against the straight-line
-// form (profiles/r02_simple_pipeline_sweep.txt): faster at every link count below a full GPU — a warp that has its scheduler
-// (almost) to itself runs at the speed of its dependent chain: 40 links +18 %, 750 links +12 %, 3000 links +7 % — and equal
-// at 5920 links, where its 88 registers (against 70) want 4 warps per sub-partition instead of 5: 66.3 % of the HBM peak
-// against 64.6 %. A deeper ring (4 stages) never helps: not even a lone warp is bound by the copy engine's latency.
-// SWTPG_SIMPLE_PIPE=0 selects the straight-line form (tuning aid).
+// WIBEth SimpleThreshold, the production algorithm: which form of its policy runs, on which ring and with how many persistent
+// warps, is decided per launch from the number of links — from whether the launch can fill the GPU (measured:
+// profiles/r02_simple_pipeline_sweep.txt, profiles/r02_simple_geometry_sweep.txt).
+//   * A launch below 36 links per SM (a 750-link shard of an 8-GPU module, the streaming path's 240 links, one APA) is bound
+//     by what ONE warp does per tick: it runs the software-pipelined form (prefetch + deferred quiet test,
+//     PackedSimpleT<true>, 88 registers) on the 2 x 32-tick ring with at most 16 warps per SM: 40 links +18 %, 750 links
+//     +12 %, 3000 links +7 % over the straight-line form.
+//   * A launch that can runs the straight-line form (70 registers) on a ring of 2 x 16 ticks — half the shared memory per
+//     warp — with 28 warps per SM, 7 per sub-partition: what limits a full GPU is how many warps the scheduler can pick from,
+//     and the smaller footprint buys two more per sub-partition. 5920 links: 67.6 % of the HBM peak (pipelined form, 16 warps
+//     per SM: 66.3 %; round 1: 64.5 %); the dense-hit stress batch 2.11 ms against 2.60 ms.
+// A deeper ring (4 stages) never helps: not even a lone warp is bound by the copy engine's latency.
+// SWTPG_SIMPLE_PIPE = 0 | 1 forces one form on the default ring (tuning aid).
 template<bool DUMP>
 cudaError_t
 launch_wibeth_simple(const KernelParams& kp, cudaStream_t s)
 {
-  static const bool straight = [] { const char* e = getenv("SWTPG_SIMPLE_PIPE"); return e && atoi(e) == 0; }();
-  return straight ? launch_wibeth_geo<PackedSimpleWibEth, DUMP, GeoDefault>(kp, s) : launch_wibeth_geo<PackedSimpleWibEthPipe, DUMP, GeoDefault>(kp, s);
+  static const int forced = [] { const char* e = getenv("SWTPG_SIMPLE_PIPE"); return e ? atoi(e) : -1; }();
+  if (forced == 0)
+    return launch_wibeth_geo<PackedSimpleWibEth, DUMP, GeoDefault>(kp, s);
+  if (forced == 1)
+    return launch_wibeth_geo<PackedSimpleWibEthPipe, DUMP, GeoDefault>(kp, s);
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess)
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  constexpr int kFullWarpsPerSm = 28, kFullFromLinksPerSm = 36; // measured cross-over: 4440 links (30 per SM) still favour the pipelined form
+  if (kp.n_links >= unsigned(kFullFromLinksPerSm * sms))
+    return launch_wibeth_geo<PackedSimpleWibEth, DUMP, Geo<1, 2, 16>, kFullWarpsPerSm>(kp, s);
+  return launch_wibeth_geo<PackedSimpleWibEthPipe, DUMP, GeoDefault>(kp, s);
 }
 
 template<class Algo, bool DUMP>

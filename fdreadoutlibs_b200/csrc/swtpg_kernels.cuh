@@ -875,12 +875,17 @@ struct PackedRsWibEth : PackedSimpleWibEth
 //     cascade registers when a link is loaded and back when it is stored, which also removes the ring phase from the loop;
 //   * accumulators are fp16x2 subnormals and the median lives as 16385 - median against the biased sample Sb = S - 16384,
 //     with the four-instruction step of PackedSimpleT;
-//   * the two quartile trackers are ONE frugal step per tick: q25 moves only on the halves below the OLD median and q75 only on
-//     the halves above it (:119-121), so per half at most one of them does anything. The step runs on per-half SELECTED
-//     operands — (Sb, 16385 - q25, acc25) where the sample is below, (~S, q75 + 2, -acc75) elsewhere: with the sample and the
-//     accumulator negated the q75 tracker obeys the same "register += down - up" rule as the q25 one — and is written back
-//     through the two masks; where the sample equals the median the result is simply dropped. Both registers stay inside
-//     [2, 16405], so their +-1 steps are one 32-bit IADD3 like the median's. 15 instructions instead of 21;
+//   * the kernel is bound by the ALU pipe (LOP3 / SHF / VIADD.16x2 / VIADDMNMX / IADD3: 16 lanes per sub-partition, half the
+//     issue rate), while the fp16 pipe (HFMA2 / HADD2 / HSET2) idles at 40 % — measured, profiles/r02_wibeth_fir_*. So every
+//     tracker keeps its ALU work to the sign test and one three-input add: the step flags come out of the fp16 pipe as the
+//     integer bit patterns 0 / 1 (saturating FMAs of +-acc - L), the quartile enables (sample below / above the OLD median,
+//     :119-121) multiply into the accumulator's FMA, and q25 lives as 16385 - q25, q75 as q75 + 2 — both inside [2, 16405] for
+//     every input, so their +-1 steps cannot carry between the halves. (Merging the two quartile trackers into one step on
+//     per-half selected operands — they never move in the same tick — saves 6 instructions per tick but ADDS three to the
+//     ALU pipe, the selects and write-backs being LOP3s: measured, no gain, not kept.)
+//   * sigma is only needed where the threshold is: the quiet test works with a lower bound of the group's sigmas taken from the
+//     quartiles after its last tick (sigma moves by at most one per tick, because at most one quartile moves), and the per-tick
+//     values are formed from the saved quartile registers only in a group that turns out busy;
 //   * while every sigma of the warp is >= 0 the 64-bit-lane product equals the per-channel product (no carries between
 //     positions) and is one packed IMAD; a warp that sees a negative sigma in a 4-tick group recomputes that
 //     group's thresholds with iqr_threshold_exact.
@@ -890,10 +895,14 @@ struct PackedFirIqr
   static constexpr int kGroupUnroll = SWTPG_FIR_GROUP_UNROLL;
   static constexpr int kWarpsPerSm = 12; // 3 warps per sub-partition: 3 % faster than the 16 its 128 registers allow (same sweep)
   static constexpr int kWib2MinCtas = 5;
-  static constexpr int kQuadCtasPerSm = 5; // CTA form, 20 consumer warps per SM: 14 % faster than one warp per CTA for this policy
+  static constexpr int kQuadCtasPerSm = 4; // CTA form, 16 consumer warps per SM (measured: 4 CTAs 29.8 %, 5 CTAs 27.8 %, profiles/r02_fir_forms.txt)
                                            // (64 registers instead of 109; profiles/r01_quad_vs_warp.txt)
-  // 16385 - median, acc - 1;  16385 - q25, acc25 - 1;  q75 + 2, -acc75 - 1   (accumulators: fp16x2 subnormal bit patterns)
-  uint32_t Mq, A, Q25n, A25, Q75p, A75n;
+#ifndef SWTPG_FIR_MERGED
+#define SWTPG_FIR_MERGED 1 // 1: the two quartile trackers share one step on per-half selected operands; 0: two separate steps
+#endif
+  // 16385 - median, acc - 1;  16385 - q25, q75 + 2;  quartile accumulators (fp16x2 subnormal bit patterns):
+  // merged form acc25 - 1 and -acc75 - 1, separate form acc25 and acc75
+  uint32_t Mq, A, Q25n, A25, Q75p, A75;
   uint32_t d1, d2, d3, d4, d5, d6, o1, o2; // cascade: d_j = previous input of stage j, o1/o2 = previous two outputs
   uint32_t prev, C, Tn;
   uint32_t xmax, sig3max, K, Kneg3, shift, shmask, thr_cfg, mult;
@@ -953,9 +962,14 @@ struct PackedFirIqr
     Mq = add2(~st[SV_MEDIAN * 32 + lane], 0x40024002u);       // ~m = -m - 1
     A = to_sm(add2(st[SV_ACCUM * 32 + lane], 0xFFFFFFFFu));
     Q25n = add2(~st[SV_Q25 * 32 + lane], 0x40024002u);
-    A25 = to_sm(add2(st[SV_A25 * 32 + lane], 0xFFFFFFFFu));
     Q75p = add2(st[SV_Q75 * 32 + lane], 0x00020002u);
-    A75n = to_sm(~st[SV_A75 * 32 + lane]);                     // ~a = -a - 1
+#if SWTPG_FIR_MERGED
+    A25 = to_sm(add2(st[SV_A25 * 32 + lane], 0xFFFFFFFFu));
+    A75 = to_sm(~st[SV_A75 * 32 + lane]);                      // ~a = -a - 1
+#else
+    A25 = to_sm(st[SV_A25 * 32 + lane]);
+    A75 = to_sm(st[SV_A75 * 32 + lane]);
+#endif
     prev = st[SV_PREV * 32 + lane];
     C = st[SV_CHARGE * 32 + lane];
     Tn = neg2(st[SV_TOVER * 32 + lane]);
@@ -965,9 +979,14 @@ struct PackedFirIqr
     st[SV_MEDIAN * 32 + lane] = median();
     st[SV_ACCUM * 32 + lane] = add2(from_sm(A), 0x00010001u);
     st[SV_Q25 * 32 + lane] = add2(~Q25n, 0x40024002u);
-    st[SV_A25 * 32 + lane] = add2(from_sm(A25), 0x00010001u);
     st[SV_Q75 * 32 + lane] = add2(Q75p, 0xFFFEFFFEu);
-    st[SV_A75 * 32 + lane] = ~from_sm(A75n);
+#if SWTPG_FIR_MERGED
+    st[SV_A25 * 32 + lane] = add2(from_sm(A25), 0x00010001u);
+    st[SV_A75 * 32 + lane] = ~from_sm(A75);
+#else
+    st[SV_A25 * 32 + lane] = from_sm(A25);
+    st[SV_A75 * 32 + lane] = from_sm(A75);
+#endif
     st[SV_PREV * 32 + lane] = prev;
     st[SV_CHARGE * 32 + lane] = C;
     st[SV_TOVER * 32 + lane] = neg2(Tn);
@@ -1019,38 +1038,61 @@ struct PackedFirIqr
     Q75p = add2(Sb, 0x40164016u);              // (ped + 20) + 2
   }
 
-  // The three frugal trackers of one tick (Sb = raw - 16384); returns s' + 1 = raw - median + 1 (updated median);
-  // sig3 = min(sigma, sigmaMax) + 3.
-  __device__ __forceinline__ uint32_t track(uint32_t Sb, uint32_t& sig3)
+  // One frugal quartile step on the halves `en` (1.0 / 0.0 per half); c = sign(...) + 1 in {0,1,2} as the sign test delivers it.
+  // Returns the step as two bit patterns 0 / 1 (up, down); the caller adds them to its register with the sign its form needs.
+  static __device__ __forceinline__ void quartile_acc(uint32_t& Aq, uint32_t sgn, uint32_t en, uint32_t& up, uint32_t& dn)
+  {
+    const uint32_t T = hfma2_bits(en, sgn, Aq);                       // acc (+= sign on the enabled halves)
+    up = hfma2_sat_bits(T, kOne, kNegL);                              // bit pattern 1 where acc reached  L+1
+    dn = hfma2_sat_bits(T, kNegOne, kNegL);                           // ...                             -(L+1)
+    Aq = hfma2_bits(ne2_abs_one(T, kUp), T, 0u);                      // reset where stepped
+  }
+  // The three frugal trackers of one tick (Sb = raw - 16384); returns s' + 1 = raw - median + 1 (updated median).
+  // ALU pipe: three sign tests, one complement, three IADD3, the final add. Everything else runs on the fp16 pipe.
+  __device__ __forceinline__ uint32_t track(uint32_t Sb)
   {
     const uint32_t sg1 = addclamp2(Sb, Mq, 0x00020002u);              // sign(raw - median) + 1, OLD median   (:108-117)
-    // the quartiles: q25 on the halves below the median (:119), q75 on the halves above (:121) — one step on selected operands
+    const uint32_t ltf = eq2_one(sg1, 0u), gtf = eq2_one(sg1, 0x00020002u);
+#if SWTPG_FIR_MERGED
+    // q25 moves only on the halves below the OLD median and q75 only on the halves above it (:119-121): per half at most one of
+    // them does anything, so ONE frugal step runs on per-half SELECTED operands — (Sb, 16385 - q25, acc25) below, (~raw, q75 + 2,
+    // -acc75) elsewhere: with the sample and the accumulator negated the q75 tracker obeys the same "register += down - up"
+    // rule as the q25 one — and is written back through the two masks; where the sample equals the median it is dropped.
+    (void)ltf;
+    (void)gtf;
     const uint32_t lt = eq2_mask(sg1, 0u), gt = eq2_mask(sg1, 0x00020002u);
     const uint32_t a = (lt & Sb) | (~lt & (~Sb | 0xC000C000u));       // raw - 16384 below; ~raw = -raw - 1 elsewhere (one LOP3)
-    const uint32_t Qs = (lt & Q25n) | (~lt & Q75p), As = (lt & A25) | (~lt & A75n);
-    const uint32_t sgq = addclamp2(a, Qs, 0x00020002u);               // sign(raw - q25) + 1  |  sign(q75 - raw) + 1
-    const uint32_t Tq = hadd2_bits(As, sgq);                          // acc25  |  -acc75, after this sample
-    const uint32_t uq = hfma2_sat_bits(Tq, kOne, kNegL);              // bit pattern 1 where it reached  L+1 ...
-    const uint32_t dq = hfma2_sat_bits(Tq, kNegOne, kNegL);           // ...                            -(L+1)
+    const uint32_t Qs = (lt & Q25n) | (~lt & Q75p), As = (lt & A25) | (~lt & A75);
+    const uint32_t Tq = hadd2_bits(As, addclamp2(a, Qs, 0x00020002u)); // acc25 | -acc75 after this sample
+    const uint32_t uq = hfma2_sat_bits(Tq, kOne, kNegL), dq = hfma2_sat_bits(Tq, kNegOne, kNegL);
     const uint32_t An = hfma2_bits(ne2_abs_one(Tq, kUp), Tq, kNegTiny); // (stepped ? 0 : acc) - 1
-    const uint32_t Qn = Qs + dq - uq;                                 // 16385 - q25 steps down when q25 steps up; q75 + 2 steps up when
-                                                                      // -acc75 reached -(L+1): the same rule for both, one IADD3
+    const uint32_t Qn = Qs + dq - uq;
     Q25n = (lt & Qn) | (~lt & Q25n);
     A25 = (lt & An) | (~lt & A25);
-    Q75p = (gt & Qn) | (~gt & Q75p);                                  // raw == median: neither moves, the step is dropped
-    A75n = (gt & An) | (~gt & A75n);
+    Q75p = (gt & Qn) | (~gt & Q75p);
+    A75 = (gt & An) | (~gt & A75);
+#else
+    uint32_t up, dn;
+    // q25 on the halves below the median (:119): sign(raw - q25) from Sb + (16385 - q25)
+    quartile_acc(A25, hadd2_bits(addclamp2(Sb, Q25n, 0x00020002u), kNegTiny), ltf, up, dn);
+    Q25n = Q25n + dn - up;                                            // 16385 - q25 steps down when q25 steps up
+    // q75 on the halves above (:121): 1 - (sign(q75 - raw) + 1) from ~raw + (q75 + 2), ~raw = -raw - 1 = ~Sb | 0xC000 per half
+    quartile_acc(A75, hfma2_bits(addclamp2(~Sb | 0xC000C000u, Q75p, 0x00020002u), kNegOne, kTiny), gtf, up, dn);
+    Q75p = Q75p + up - dn;
+#endif
     // median (:125), as PackedSimpleT::pedestal_step with L = 10
     const uint32_t T = hadd2_bits(A, sg1);
     const uint32_t up1 = hfma2_sat_bits(T, kOne, kNegL), dn1 = hfma2_sat_bits(T, kNegOne, kNegL);
     A = hfma2_bits(ne2_abs_one(T, kUp), T, kNegTiny);
     Mq = Mq + dn1 - up1;
-    sig3 = addmin2(add2(Q75p, 0xC000C000u), Q25n, sig3max);           // min(q75 - q25, sigmaMax) + 3        (:131-134)
     return add2(Sb, Mq);
   }
+  // min(q75 - q25, sigmaMax) + 3 (:131-134) from a pair of quartile registers (q75 + 2, 16385 - q25)
+  __device__ __forceinline__ uint32_t sig3_of(uint32_t q75p, uint32_t q25n) const { return addmin2(add2(q75p, 0xC000C000u), q25n, sig3max); }
   // One tick: returns the filter output of this tick.
-  __device__ __forceinline__ uint32_t tick(uint32_t S, uint32_t& sig3)
+  __device__ __forceinline__ uint32_t tick(uint32_t Sb)
   {
-    const uint32_t x = addmin2(track(S, sig3), 0xFFFFFFFFu, xmax);    // min(raw - median, adcMax)           (:128,142)
+    const uint32_t x = addmin2(track(Sb), 0xFFFFFFFFu, xmax);         // min(raw - median, adcMax)           (:128,142)
     const uint32_t filt = o2;                                         // window = samples t-8 .. t-2          (:160-201)
     cascade(x);
     return filt;
@@ -1087,20 +1129,30 @@ struct PackedFirIqr
     }
   }
 
-  // Quiet test and hit bookkeeping of one 4-tick group, given its filter outputs and sigmas.
+  // Quiet test and hit bookkeeping of one 4-tick group, given its filter outputs and the quartile registers after each tick.
   template<int G, bool WIB2_UNITS>
-  __device__ __forceinline__ void finish_group(const uint32_t (&filt)[G], const uint32_t (&sig3)[G], const TickCtx& ctx, int t0)
+  __device__ __forceinline__ void finish_group(const uint32_t (&filt)[G], const uint32_t (&q75v)[G], const uint32_t (&q25v)[G], const TickCtx& ctx,
+                                               int t0)
   {
-    // conservative quiet test: max filter output of the group vs the threshold of the group's smallest sigma
+    // Conservative quiet test: the largest filter output of the group against the threshold of a LOWER BOUND of its sigmas.
+    // At most one quartile moves per tick, by one, so every sigma of the group is >= sigma(last tick) - 3.
     const uint32_t mx = __vimax3_s16x2(__vimax3_s16x2(filt[0], filt[1], filt[2]), filt[3], 0u);
-    const uint32_t smin = __vimin3_s16x2(__vimin3_s16x2(sig3[0], sig3[1], sig3[2]), sig3[3], sig3[3]);
-    uint32_t neg = addmin2(smin, 0xFFFDFFFDu, 0u); // min(sigma, 0) of the group: non-zero <=> some sigma < 0
+    const uint32_t lo3 = add2(sig3_of(q75v[G - 1], q25v[G - 1]), 0xFFFDFFFDu); // (bound of min(sigma, sigmaMax)) + 3
+    uint32_t neg = addmin2(lo3, 0xFFFDFFFDu, 0u);        // non-zero <=> the bound is negative: some sigma MAY be below zero
     if (ctx.p->debug_flags & 1u)
       neg = 0xFFFFFFFFu;
-    const uint32_t busy = gt2_mask_bf16(mx, threshold(smin)) | prev | neg;
+    const uint32_t busy = gt2_mask_bf16(mx, threshold(lo3)) | prev | neg;
     if (__builtin_expect(!__any_sync(0xFFFFFFFFu, busy != 0u), 1))
       return; // nothing but the trackers and the filter moves outside hits
-    if (__any_sync(0xFFFFFFFFu, neg != 0u)) { // rare: carries between the positions of a 64-bit lane (H7)
+    uint32_t sig3[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      sig3[g] = sig3_of(q75v[g], q25v[g]);
+    const uint32_t smin = __vimin3_s16x2(__vimin3_s16x2(sig3[0], sig3[1], sig3[2]), sig3[3], sig3[3]);
+    uint32_t really_neg = addmin2(smin, 0xFFFDFFFDu, 0u); // min(sigma, 0) of the group: non-zero <=> some sigma < 0
+    if (ctx.p->debug_flags & 1u)
+      really_neg = 0xFFFFFFFFu;
+    if (__any_sync(0xFFFFFFFFu, really_neg != 0u)) { // rare: carries between the positions of a 64-bit lane (H7)
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         const uint32_t th = iqr_threshold_exact(add2(sig3[g], 0xFFFDFFFDu), (ctx.chan0 >> 1) & 31u, int(mult), thr_cfg);
@@ -1120,16 +1172,18 @@ struct PackedFirIqr
                                         uint32_t* wav_out, bool /*more*/)
   {
     static_assert(G == 4, "trees below are written for 4 ticks");
-    uint32_t filt[G], sig3[G];
+    uint32_t filt[G], q75v[G], q25v[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      filt[g] = tick(extract_pair_biased(rows + g * ROW_WORDS, pp), sig3[g]);
+      filt[g] = tick(extract_pair_biased(rows + g * ROW_WORDS, pp));
+      q75v[g] = Q75p;
+      q25v[g] = Q25n;
       if constexpr (DUMP) {
         ped_out[g] = median();
         wav_out[g] = filt[g];
       }
     }
-    finish_group<G, WIB2_UNITS>(filt, sig3, ctx, t0);
+    finish_group<G, WIB2_UNITS>(filt, q75v, q25v, ctx, t0);
   }
 };
 
@@ -1174,9 +1228,9 @@ struct PackedFirIqrAnyTaps : PackedFirIqr
     for (uint32_t i = 0; i < 8; ++i)
       st[(SV_RING0 + ((k_end + i) & 7u)) * 32 + lane] = w[i]; // w[0] is the oldest = the slot written next
   }
-  __device__ __forceinline__ uint32_t tick(uint32_t S, uint32_t& sig3)
+  __device__ __forceinline__ uint32_t tick(uint32_t Sb)
   {
-    const uint32_t x = addmin2(track(S, sig3), 0xFFFFFFFFu, xmax);    // min(raw - median, adcMax)
+    const uint32_t x = addmin2(track(Sb), 0xFFFFFFFFu, xmax);         // min(raw - median, adcMax)
     int lo = 0, hi = 0;
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
@@ -1199,16 +1253,18 @@ struct PackedFirIqrAnyTaps : PackedFirIqr
                                         uint32_t* wav_out, bool /*more*/)
   {
     static_assert(G == 4, "trees below are written for 4 ticks");
-    uint32_t filt[G], sig3[G];
+    uint32_t filt[G], q75v[G], q25v[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      filt[g] = tick(extract_pair_biased(rows + g * ROW_WORDS, pp), sig3[g]);
+      filt[g] = tick(extract_pair_biased(rows + g * ROW_WORDS, pp));
+      q75v[g] = Q75p;
+      q25v[g] = Q25n;
       if constexpr (DUMP) {
         ped_out[g] = median();
         wav_out[g] = filt[g];
       }
     }
-    finish_group<G, WIB2_UNITS>(filt, sig3, ctx, t0);
+    finish_group<G, WIB2_UNITS>(filt, q75v, q25v, ctx, t0);
   }
 };
 
@@ -1315,7 +1371,8 @@ struct PackedRsIqrWib2 : PackedFirIqr
     uint32_t lv[G], rs[G], sig3[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      lv[g] = rs_step(track(extract_pair_biased(rows + g * ROW_WORDS, pp), sig3[g]), rs[g]);
+      lv[g] = rs_step(track(extract_pair_biased(rows + g * ROW_WORDS, pp)), rs[g]);
+      sig3[g] = sig3_of(Q75p, Q25n);
       if constexpr (DUMP) {
         ped_out[g] = median();
         wav_out[g] = add2(lv[g], 0xFFFFFFFFu);

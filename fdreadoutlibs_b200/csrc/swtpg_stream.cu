@@ -146,6 +146,7 @@ struct Batch
   uint32_t n_items = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_gather = nullptr, ev_kernel = nullptr, ev_count = nullptr, ev_tps = nullptr;
+  cudaEvent_t ev_g0 = nullptr, ev_k0 = nullptr; // timing: start of the gather / of the TPG kernel (device clocks, swtpg_stream_timing)
   uint32_t n_ready = 0, n_taken = 0;
   bool overflow = false;
   bool released = false; // the release thread has handed the batch's ring slots back (guarded by StreamEngine::mu)
@@ -181,6 +182,7 @@ struct StreamEngine
   uint64_t flush_req = 0, flush_done = 0;
   bool reset_req = false, stalled_on_poll = false, quit = false;
   std::atomic<int> thread_status{ SWTPG_OK };
+  std::atomic<uint64_t> gather_us{ 0 }, kernel_us{ 0 }, timed_batches{ 0 };
   std::thread dispatcher, releaser, completer;
   std::mutex poll_mu; // one poller at a time
   std::chrono::microseconds timeout{ 5000 };
@@ -230,6 +232,8 @@ free_batch(Batch& b)
   if (b.d_items) cudaFree(b.d_items);
   if (b.ev_gather) cudaEventDestroy(b.ev_gather);
   if (b.ev_kernel) cudaEventDestroy(b.ev_kernel);
+  if (b.ev_g0) cudaEventDestroy(b.ev_g0);
+  if (b.ev_k0) cudaEventDestroy(b.ev_k0);
   if (b.ev_count) cudaEventDestroy(b.ev_count);
   if (b.ev_tps) cudaEventDestroy(b.ev_tps);
   if (b.stream) cudaStreamDestroy(b.stream);
@@ -271,10 +275,12 @@ StreamEngine::enqueue(Batch& b)
   return e
   TRY(cudaMemcpyAsync(b.d_items, b.h_items, size_t(b.n_items) * sizeof(GatherItem), cudaMemcpyHostToDevice, b.stream));
   TRY(cudaMemcpyAsync(b.d_nunits, b.h_nunits, size_t(n_links) * 4, cudaMemcpyHostToDevice, b.stream));
+  TRY(cudaEventRecord(b.ev_g0, b.stream));
   TRY(launch_gather(b));
-  TRY(cudaMemsetAsync(b.d_count, 0, sizeof(unsigned), b.stream));
   TRY(cudaEventRecord(b.ev_gather, b.stream));
+  TRY(cudaMemsetAsync(b.d_count, 0, sizeof(unsigned), b.stream));
   TRY(cudaStreamWaitEvent(h->stream, b.ev_gather, 0));
+  TRY(cudaEventRecord(b.ev_k0, h->stream));
   TRY(launch_batch_kernel(h, b.d_frames, b.d_nunits, M, b.d_tps, b.d_count, h->stream));
   TRY(cudaEventRecord(b.ev_kernel, h->stream));
   TRY(cudaStreamWaitEvent(b.stream, b.ev_kernel, 0));
@@ -313,6 +319,7 @@ StreamEngine::dispatcher_main()
         q.n_zero_copy = q.n_staged = 0;
       }
       have_pending_since = false;
+      gather_us = kernel_us = timed_batches = 0;
       reset_req = false;
       cv_flush.notify_all();
       continue;
@@ -453,6 +460,14 @@ StreamEngine::completer_main()
         e = cudaEventSynchronize(b->ev_tps);
       b->n_ready = stored;
       b->overflow = found > stored;
+      float g_ms = 0.f, k_ms = 0.f; // device time the gather and the TPG kernel of this batch took (both have completed)
+      if (cudaEventElapsedTime(&g_ms, b->ev_g0, b->ev_gather) == cudaSuccess && cudaEventElapsedTime(&k_ms, b->ev_k0, b->ev_kernel) == cudaSuccess) {
+        gather_us.fetch_add(uint64_t(g_ms * 1000.f), std::memory_order_relaxed);
+        kernel_us.fetch_add(uint64_t(k_ms * 1000.f), std::memory_order_relaxed);
+        timed_batches.fetch_add(1, std::memory_order_relaxed);
+      } else {
+        cudaGetLastError();
+      }
       h->counters.tps_emitted += found;
       h->counters.d2h_bytes += uint64_t(stored) * sizeof(swtpg_tp) + sizeof(unsigned);
       if (found > stored)
@@ -519,8 +534,10 @@ engine_create(swtpg_handle* h, StreamEngine** out)
     ok(cudaMalloc(&b.d_items, n_items * sizeof(GatherItem)));
     ok(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
     // blocking-sync events: the completion thread sleeps in cudaEventSynchronize instead of spinning on a core
-    ok(cudaEventCreateWithFlags(&b.ev_gather, cudaEventDisableTiming | cudaEventBlockingSync));
-    ok(cudaEventCreateWithFlags(&b.ev_kernel, cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&b.ev_gather, cudaEventBlockingSync));
+    ok(cudaEventCreateWithFlags(&b.ev_kernel, cudaEventDefault));
+    ok(cudaEventCreate(&b.ev_g0));
+    ok(cudaEventCreate(&b.ev_k0));
     ok(cudaEventCreateWithFlags(&b.ev_count, cudaEventDisableTiming | cudaEventBlockingSync));
     ok(cudaEventCreateWithFlags(&b.ev_tps, cudaEventDisableTiming | cudaEventBlockingSync));
     if (ce != cudaSuccess) {
@@ -885,6 +902,27 @@ swtpg_status
 swtpg_poll_wait(swtpg_handle* h, swtpg_tp* out, size_t cap, size_t* n_out, uint64_t timeout_us)
 {
   return poll_impl(h, out, cap, n_out, timeout_us);
+}
+
+swtpg_status
+swtpg_stream_timing(swtpg_handle* h, double* gather_ms, double* kernel_ms, uint64_t* batches)
+{
+  if (!h)
+    return SWTPG_ERR_INVALID_ARG;
+  double g = 0, k = 0;
+  uint64_t n = 0;
+  if (StreamEngine* e = h->engine.load(std::memory_order_acquire)) {
+    g = double(e->gather_us.load()) * 1e-3;
+    k = double(e->kernel_us.load()) * 1e-3;
+    n = e->timed_batches.load();
+  }
+  if (gather_ms)
+    *gather_ms = g;
+  if (kernel_ms)
+    *kernel_ms = k;
+  if (batches)
+    *batches = n;
+  return SWTPG_OK;
 }
 
 // units submitted by address (zero-copy) and by staging copy since swtpg_start; used by swtpg_get_counters

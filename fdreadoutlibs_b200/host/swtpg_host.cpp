@@ -1097,6 +1097,13 @@ swtpg_host_counters(swtpg_host* h, swtpg_counters* out)
   return h->engine->handle() && swtpg_get_counters(h->engine->handle(), out) == SWTPG_OK ? 0 : -1;
 }
 
+// device time of the streaming path's gather and TPG kernels (swtpg_stream_timing)
+int
+swtpg_host_stream_timing(swtpg_host* h, double* gather_ms, double* kernel_ms, uint64_t* batches)
+{
+  return h->engine->handle() && swtpg_stream_timing(h->engine->handle(), gather_ms, kernel_ms, batches) == SWTPG_OK ? 0 : -1;
+}
+
 // TPs accepted by the count-only sinks so far
 uint64_t
 swtpg_host_tp_count(swtpg_host* h)

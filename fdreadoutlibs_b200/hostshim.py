@@ -49,7 +49,7 @@ class TpHandlerInfo(C.Structure):
 
 EXPORTS = ["swtpg_host_tpsets_create", "swtpg_host_tpsets_destroy", "swtpg_host_tpsets_receive", "swtpg_host_tpsets_cycle",
            "swtpg_host_tpsets_cutoff", "swtpg_host_tpsets_count", "swtpg_host_tpsets_get", "swtpg_host_tpsets_info",
-           "swtpg_host_push_parallel", "swtpg_host_push_feeders", "swtpg_host_tp_count", "swtpg_host_counters", "swtpg_host_last_error", "swtpg_host_create", "swtpg_host_destroy", "swtpg_host_start", "swtpg_host_stop", "swtpg_host_push",
+           "swtpg_host_push_parallel", "swtpg_host_push_feeders", "swtpg_host_tp_count", "swtpg_host_counters", "swtpg_host_stream_timing", "swtpg_host_last_error", "swtpg_host_create", "swtpg_host_destroy", "swtpg_host_start", "swtpg_host_stop", "swtpg_host_push",
            "swtpg_host_take_tps", "swtpg_host_get_info", "swtpg_host_error_count", "swtpg_host_misconfigurations",
            "swtpg_host_last_daq_time", "swtpg_host_register_channel_map", "swtpg_host_register_buffer"]
 
@@ -71,6 +71,7 @@ def host_lib():
         lib.swtpg_host_push_feeders.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32,
                                                 C.POINTER(FeedStats)]
         lib.swtpg_host_counters.argtypes = [C.c_void_p, C.c_void_p]
+        lib.swtpg_host_stream_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         lib.swtpg_host_tp_count.restype = C.c_uint64
         lib.swtpg_host_tp_count.argtypes = [C.c_void_p]
         lib.swtpg_host_take_tps.restype = C.c_size_t
@@ -169,6 +170,12 @@ class FrameProcessors:
         c = SwtpgCounters()
         self._check(self.lib.swtpg_host_counters(self.h, C.byref(c)))
         return {n: int(getattr(c, n)) for n, _ in SwtpgCounters._fields_}
+
+    def stream_timing(self) -> dict:
+        """Device time the engine's batches spent in the gather kernel (host-link transfer) and in the TPG kernel."""
+        g, k, n = C.c_double(0), C.c_double(0), C.c_uint64(0)
+        self._check(self.lib.swtpg_host_stream_timing(self.h, C.byref(g), C.byref(k), C.byref(n)))
+        return {"gather_ms": g.value, "kernel_ms": k.value, "batches": int(n.value)}
 
     def tp_count(self) -> int:
         """TPs accepted so far by count-only sinks (count_only_sink=True)."""

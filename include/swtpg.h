@@ -238,6 +238,9 @@ swtpg_status swtpg_sync(swtpg_handle* h);
 /* Streaming path bookkeeping: units submitted but not yet dispatched, batches dispatched but not yet completed, completed
  * batches waiting for swtpg_poll. Any pointer may be NULL. */
 swtpg_status swtpg_stream_status(swtpg_handle* h, uint64_t* units_pending, uint32_t* batches_in_flight, uint32_t* batches_ready);
+/* Device time (CUDA events) the completed batches of the streaming path spent in the gather kernel — the host-link transfer —
+ * and in the fused TPG kernel since swtpg_start, and how many batches that covers. Monitoring / bench aid. */
+swtpg_status swtpg_stream_timing(swtpg_handle* h, double* gather_ms, double* kernel_ms, uint64_t* batches);
 
 /* Carried state of one link, by frame channel (ChanState parity). out has SWTPG_*_CHANNELS entries. */
 swtpg_status swtpg_dump_state(swtpg_handle* h, uint32_t link, swtpg_channel_state* out);

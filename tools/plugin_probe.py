@@ -49,6 +49,7 @@ with H.FrameProcessors(links, sc, threshold=60, n_slots=SLOTS, emulator_mode=EMU
     dropped = sum(per_pass) + sum(fp.get_info(l)["num_frames_dropped_busy"] for l in range(links))
     tps = fp.tp_count()
     cnt = fp.counters()
+    tim = fp.stream_timing()
     if zc:
         fp.register_buffer(h, on=False)
 n = passes * links * units
@@ -57,4 +58,5 @@ print(f"links={links} sc={sc} zero_copy={zc} threads={threads} burst={burst} pac
       f"{n*4096/dt/5e9:.2f} real-time APAs)  wall {dt*1e3:.0f} ms (feed {t_feed*1e3:.0f})  process cpu {cpu*1e3:.0f} ms = {cpu/dt:.2f} cores busy, "
       f"feeders {st['feeder_cpu_s']/dt:.2f} cores = {st['feeder_cpu_s']/n*1e6:.3f} us/frame  host core-s per APA-s {cpu/dt/ (n*4096/dt/5e9):.3f}  "
       f"tps={tps} dropped={dropped} late_bursts={st['late_bursts']} by_address={cnt['units_zero_copy']} by_copy={cnt['units_staged']} "
-      f"batches={cnt['batches']}" + (f" dropped_per_pass={per_pass}" if per_pass else ""), flush=True)
+      f"batches={cnt['batches']} gather {tim['gather_ms']:.1f} ms = {cnt['h2d_bytes']/max(tim['gather_ms'],1e-9)/1e6:.1f} GB/s while active, "
+      f"kernel {tim['kernel_ms']:.1f} ms" + (f" dropped_per_pass={per_pass}" if per_pass else ""), flush=True)
