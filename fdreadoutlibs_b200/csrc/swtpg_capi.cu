@@ -298,6 +298,8 @@ make_params(const swtpg_handle* h, const void* d_frames, const uint32_t* d_nunit
   kp.wib2_adc_offset = h->cfg.wib2_adc_offset;
   static const bool force_exact = [] { const char* e = getenv("SWTPG_FIR_FORCE_EXACT"); return e && atoi(e) != 0; }();
   kp.debug_flags = (force_exact || h->fir_force_exact) ? 1u : 0u;
+  kp.all_ones = 0xFFFFFFFFu;
+  kp.one = 1u;
   return kp;
 }
 

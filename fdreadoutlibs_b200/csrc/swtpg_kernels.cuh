@@ -34,6 +34,11 @@
 #ifndef SWTPG_FLOAT_ACC
 #define SWTPG_FLOAT_ACC 1
 #endif
+// Frugal accumulator of the SimpleThreshold / running-sum pedestal: 0 = fp16x2 subnormal (round 1), 1 = biased integer, seven
+// instructions per tick, 2 = biased integer with the step taken off the median's dependent chain (eight instructions, shorter chain)
+#ifndef SWTPG_SIMPLE_INT
+#define SWTPG_SIMPLE_INT 1
+#endif
 
 namespace swtpg {
 
@@ -81,7 +86,27 @@ struct KernelParams
   int32_t taps[8];
   uint32_t wib2_adc_offset;
   uint32_t debug_flags;    // bit 0: PackedFirIqr always takes its exact-threshold tier (test aid, SWTPG_FIR_FORCE_EXACT=1)
+  uint32_t all_ones;       // 0xFFFFFFFF: a constant the compiler cannot fold, so that it stays in ONE register (VIADDMNMX takes a
+                           // single immediate; ptxas otherwise re-materialises the -1 operand with a move in front of every use)
+  uint32_t one;            // 1: multiplier of the adds that are to run on the FMA pipe as IMAD (see fma_add below)
 };
+
+// Pipe steering. Measured with ncu on every kernel of this file: the ALU pipe (LOP3, SHF, PRMT, IADD3, VIMNMX, VIADDMNMX, HSET2,
+// ISETP, SEL: half issue rate) is 70-75 % busy while the FMA pipe (IMAD, VIADD.16x2, HFMA2, HADD2: half rate as well) idles at
+// 25-30 %, and ptxas turns `a + b` into IADD3 (ALU) or IMAD.IADD (FMA) by its own alternation. An add written as a * ONE + b with
+// ONE = 1 read from the kernel parameters cannot be strength-reduced and is an IMAD: the add runs on the idle pipe.
+// Used by the FIR + IQR trackers (WIB2 layout 30.5 -> 31.8 % of the HBM peak); the SimpleThreshold step keeps plain adds (steered:
+// 1 % slower, profiles/r02_integer_accumulators.txt).
+__device__ __forceinline__ uint32_t
+fma_add(uint32_t a, uint32_t b, uint32_t one)
+{
+  return a * one + b;
+}
+__device__ __forceinline__ uint32_t
+fma_sub(uint32_t a, uint32_t b, uint32_t minus_one)
+{ // a - b
+  return b * minus_one + a;
+}
 
 struct TickCtx
 {
@@ -441,6 +466,7 @@ struct PackedSimpleT
   static constexpr bool kWib2Fields = false; // which process_swtpg_hits derives the TP fields (and whether the peak is tracked)
   uint32_t Mq, A, prev, C, Tn, PK1, PTn;
   uint32_t cUp, cDn, thr1;
+  uint32_t cL, c2L, cL1, cLL, kM1; // integer accumulator form: L, (2L, 2L), L + 1, (L, L); 0xFFFFFFFF in a register
   uint32_t shift, shmask; // WIB2 flavour only
   uint32_t raw[8];        // software pipeline: words of the next group's four rows ...
   uint32_t dsp[4], dwhen; // ... and the deferred group: its four s' + 1 and (unit << 6 | first tick); dvalid below
@@ -455,6 +481,11 @@ struct PackedSimpleT
     const uint32_t dn = 0x8000u | L;       // -L: addend of the "acc - L" / "-acc - L" saturating tests (sign-magnitude)
     cUp = up | (up << 16);
     cDn = dn | (dn << 16);
+    cL = L;
+    cL1 = L + 1u;
+    cLL = L * 0x00010001u;
+    c2L = 2u * L * 0x00010001u;
+    kM1 = p.all_ones;
     uint32_t th = p.threshold > 16383u ? 16383u : p.threshold; // s' <= 16383: any larger threshold is never exceeded
     th += 1u;
     thr1 = th | (th << 16);
@@ -477,7 +508,11 @@ struct PackedSimpleT
   __device__ __forceinline__ void load(const uint32_t* st, uint32_t lane, uint32_t)
   {
     Mq = add2(~st[SV_MEDIAN * 32 + lane], 0x40024002u); // ~m = -m - 1
+#if SWTPG_SIMPLE_INT
+    A = add2(st[SV_ACCUM * 32 + lane], cLL);            // acc + L in [0, 2L]
+#else
     A = acc_to_reg(st[SV_ACCUM * 32 + lane]);
+#endif
     prev = st[SV_PREV * 32 + lane];
     C = st[SV_CHARGE * 32 + lane];
     Tn = neg2(st[SV_TOVER * 32 + lane]);
@@ -493,7 +528,11 @@ struct PackedSimpleT
   __device__ __forceinline__ void store(uint32_t* st, uint32_t lane, uint32_t) const
   {
     st[SV_MEDIAN * 32 + lane] = median();
+#if SWTPG_SIMPLE_INT
+    st[SV_ACCUM * 32 + lane] = add2(A, neg2(cLL));
+#else
     st[SV_ACCUM * 32 + lane] = acc_from_reg(A);
+#endif
     st[SV_PREV * 32 + lane] = prev;
     st[SV_CHARGE * 32 + lane] = C;
     st[SV_TOVER * 32 + lane] = neg2(Tn);
@@ -513,9 +552,31 @@ struct PackedSimpleT
   // The accumulator lives as an fp16x2 subnormal stored minus one, so that adding sign+1 lands on the new value; both step
   // flags come out of the FMA pipe as the integer bit patterns 0 / 1 (saturating fp16 FMAs of +-acc - L), and the median
   // takes them in one 32-bit add. The ALU pipe does the sign, one compare and that add.
+  //
+  // Integer form (SWTPG_SIMPLE_INT, round 2): the accumulator biased by +L is a small non-negative number per half, like the
+  // sign code, so their sum is a plain 32-bit add (either pipe); one clamp takes out the two step values, the difference is
+  // the step D in {-1, 0, +1} per half held as ONE 32-bit integer (the low half may borrow from the high one — harmless, only
+  // linear 32-bit operations consume it and their results have non-negative halves again), and the accumulator returns to L
+  // where it stepped through one IMAD. Two instructions on the ALU pipe, two (one without the final add) on the FMA pipe, three
+  // that issue on either; the fp16 form has 2 / 5 / 1.
   __device__ __forceinline__ uint32_t pedestal_step(uint32_t Sb)
   {
     const uint32_t sg1 = addclamp2(Sb, Mq, 0x00020002u);        // sign(s - m) + 1 in {0,1,2}
+#if SWTPG_SIMPLE_INT
+    const uint32_t U = A + sg1;                                 // acc' + L + 1 in [0, 2L + 2]
+    const uint32_t c = addclamp2(U, kM1, c2L);                  // clamp(acc' + L, 0, 2L)
+#if SWTPG_SIMPLE_INT == 2
+    const uint32_t W = Mq - U + 0x00010001u;                    // in the shadow of the clamp
+    const uint32_t V = cLL - cL * U;                            // L - L U
+    Mq = W + c;                                                 // m += U - 1 - c
+    A = cL1 * c + V;                                            // c - L (U - 1 - c)
+#else
+    const uint32_t D = U - c - 0x00010001u;                     // the step
+    A = c - cL * D;                                             // back to L where it stepped
+    Mq -= D;                                                    // (steering these adds to the FMA pipe measured 1 % slower here)
+#endif
+    return add2(Sb, Mq);                                        // s' + 1 with the UPDATED median
+#else
     const uint32_t T = hadd2_bits(A, sg1);                      // acc after this sample, in [-(L+1), L+1]
     const uint32_t up1 = hfma2_sat_bits(T, 0x3C003C00u, cDn);   // sat(acc - L)  -> bit pattern 1: acc == L+1
     const uint32_t dn1 = hfma2_sat_bits(T, 0xBC00BC00u, cDn);   // sat(-acc - L) -> bit pattern 1: acc == -(L+1)
@@ -523,6 +584,7 @@ struct PackedSimpleT
     A = hfma2_bits(keep, T, 0x80018001u);                       // (stepped ? 0 : acc) - 1
     Mq = Mq + dn1 - up1;                                        // m += up - down: one IADD3, halves cannot interact (see above)
     return add2(Sb, Mq);                                        // s' + 1 with the UPDATED median
+#endif
   }
   __device__ __forceinline__ uint32_t over_mask(uint32_t sp1) const { return gt2_mask_nonneg(sp1, thr1); } // (:97-98)
 
@@ -897,12 +959,20 @@ struct PackedFirIqr
   static constexpr int kWib2MinCtas = 5;
   static constexpr int kQuadCtasPerSm = 4; // CTA form, 16 consumer warps per SM (measured: 4 CTAs 29.8 %, 5 CTAs 27.8 %, profiles/r02_fir_forms.txt)
                                            // (64 registers instead of 109; profiles/r01_quad_vs_warp.txt)
-#ifndef SWTPG_FIR_MERGED
-#define SWTPG_FIR_MERGED 1 // 1: the two quartile trackers share one step on per-half selected operands; 0: two separate steps
+#ifndef SWTPG_FIR_INT
+#define SWTPG_FIR_INT 1 // 1: integer accumulators (round 2, see track()); 0: the fp16-subnormal forms of round 1 below
 #endif
-  // 16385 - median, acc - 1;  16385 - q25, q75 + 2;  quartile accumulators (fp16x2 subnormal bit patterns):
-  // merged form acc25 - 1 and -acc75 - 1, separate form acc25 and acc75
+#ifndef SWTPG_FIR_U3
+#define SWTPG_FIR_U3 0 // integer form: the two three-input adds as one IADD3 each (ALU pipe, 0) or as two IMADs each (FMA pipe, 1)
+#endif
+#ifndef SWTPG_FIR_MERGED
+#define SWTPG_FIR_MERGED 1 // fp16 forms only. 1: the two quartile trackers share one step on per-half selected operands; 0: two separate steps
+#endif
+  // 16385 - median, 16385 - q25 in every form. Integer form: Q75p = 16385 - q75, A = acc + 10, A25 = acc25 + 10, A75 = acc75 + 11.
+  // fp16 forms: Q75p = q75 + 2, A = acc - 1 and the quartile accumulators as fp16x2 subnormal bit patterns
+  // (merged form acc25 - 1 and -acc75 - 1, separate form acc25 and acc75)
   uint32_t Mq, A, Q25n, A25, Q75p, A75;
+  uint32_t kM1, kP1; // 0xFFFFFFFF and 1 in registers the compiler cannot see through (KernelParams::all_ones, one)
   uint32_t d1, d2, d3, d4, d5, d6, o1, o2; // cascade: d_j = previous input of stage j, o1/o2 = previous two outputs
   uint32_t prev, C, Tn;
   uint32_t xmax, sig3max, K, Kneg3, shift, shmask, thr_cfg, mult;
@@ -938,6 +1008,8 @@ struct PackedFirIqr
     shift = uint32_t(p.tap_exponent);
     const uint32_t m = 0xFFFFu >> shift;
     shmask = m | (m << 16);
+    kM1 = p.all_ones;
+    kP1 = p.one;
   }
   static __device__ __forceinline__ uint32_t to_sm(uint32_t v)
   { // two's complement s16x2 -> sign-magnitude (= bit pattern of value * 2^-24 as fp16), |v| <= 1023
@@ -960,8 +1032,14 @@ struct PackedFirIqr
   __device__ __forceinline__ void load_trackers(const uint32_t* st, uint32_t lane)
   {
     Mq = add2(~st[SV_MEDIAN * 32 + lane], 0x40024002u);       // ~m = -m - 1
-    A = to_sm(add2(st[SV_ACCUM * 32 + lane], 0xFFFFFFFFu));
     Q25n = add2(~st[SV_Q25 * 32 + lane], 0x40024002u);
+#if SWTPG_FIR_INT
+    A = add2(st[SV_ACCUM * 32 + lane], 0x000A000Au);
+    Q75p = add2(~st[SV_Q75 * 32 + lane], 0x40024002u);
+    A25 = add2(st[SV_A25 * 32 + lane], 0x000A000Au);
+    A75 = add2(st[SV_A75 * 32 + lane], 0x000B000Bu);
+#else
+    A = to_sm(add2(st[SV_ACCUM * 32 + lane], 0xFFFFFFFFu));
     Q75p = add2(st[SV_Q75 * 32 + lane], 0x00020002u);
 #if SWTPG_FIR_MERGED
     A25 = to_sm(add2(st[SV_A25 * 32 + lane], 0xFFFFFFFFu));
@@ -970,6 +1048,7 @@ struct PackedFirIqr
     A25 = to_sm(st[SV_A25 * 32 + lane]);
     A75 = to_sm(st[SV_A75 * 32 + lane]);
 #endif
+#endif
     prev = st[SV_PREV * 32 + lane];
     C = st[SV_CHARGE * 32 + lane];
     Tn = neg2(st[SV_TOVER * 32 + lane]);
@@ -977,8 +1056,14 @@ struct PackedFirIqr
   __device__ __forceinline__ void store_trackers(uint32_t* st, uint32_t lane) const
   {
     st[SV_MEDIAN * 32 + lane] = median();
-    st[SV_ACCUM * 32 + lane] = add2(from_sm(A), 0x00010001u);
     st[SV_Q25 * 32 + lane] = add2(~Q25n, 0x40024002u);
+#if SWTPG_FIR_INT
+    st[SV_ACCUM * 32 + lane] = add2(A, 0xFFF6FFF6u);
+    st[SV_Q75 * 32 + lane] = add2(~Q75p, 0x40024002u);
+    st[SV_A25 * 32 + lane] = add2(A25, 0xFFF6FFF6u);
+    st[SV_A75 * 32 + lane] = add2(A75, 0xFFF5FFF5u);
+#else
+    st[SV_ACCUM * 32 + lane] = add2(from_sm(A), 0x00010001u);
     st[SV_Q75 * 32 + lane] = add2(Q75p, 0xFFFEFFFEu);
 #if SWTPG_FIR_MERGED
     st[SV_A25 * 32 + lane] = add2(from_sm(A25), 0x00010001u);
@@ -986,6 +1071,7 @@ struct PackedFirIqr
 #else
     st[SV_A25 * 32 + lane] = from_sm(A25);
     st[SV_A75 * 32 + lane] = from_sm(A75);
+#endif
 #endif
     st[SV_PREV * 32 + lane] = prev;
     st[SV_CHARGE * 32 + lane] = C;
@@ -1035,7 +1121,11 @@ struct PackedFirIqr
   {
     Mq = add2(~Sb, 0x00020002u);               // 16385 - ped = 1 - Sb
     Q25n = add2(~Sb, 0x00160016u);             // 16385 - (ped - 20)
+#if SWTPG_FIR_INT
+    Q75p = add2(~Sb, 0xFFEEFFEEu);             // 16385 - (ped + 20)
+#else
     Q75p = add2(Sb, 0x40164016u);              // (ped + 20) + 2
+#endif
   }
 
   // One frugal quartile step on the halves `en` (1.0 / 0.0 per half); c = sign(...) + 1 in {0,1,2} as the sign test delivers it.
@@ -1047,11 +1137,54 @@ struct PackedFirIqr
     dn = hfma2_sat_bits(T, kNegOne, kNegL);                           // ...                             -(L+1)
     Aq = hfma2_bits(ne2_abs_one(T, kUp), T, 0u);                      // reset where stepped
   }
-  // The three frugal trackers of one tick (Sb = raw - 16384); returns s' + 1 = raw - median + 1 (updated median).
-  // ALU pipe: three sign tests, one complement, three IADD3, the final add. Everything else runs on the fp16 pipe.
+  // The three frugal trackers of one tick (Sb = raw - 16384). Returns 16385 - median (integer form) or s' + 1 = raw - median + 1
+  // (fp16 forms), updated median: see sp1_of / clamped_sample.
+  // fp16 forms — ALU pipe: three sign tests, one complement, three IADD3, the final add. Everything else runs on the fp16 pipe.
+  //
+  // Integer form (SWTPG_FIR_INT, round 2). A frugal accumulator stays in [-10, 10] between ticks, so biased by +10 it is a small
+  // NON-NEGATIVE number in each half, and so are the sign codes {0,1,2}: sums of such values are plain 32-bit adds (IADD3 issues on
+  // either pipe at twice the rate of the packed-16x2 and fp16x2 instructions) because nothing carries between the halves. One
+  // tracker step is
+  //     U = B + sign + 1                      acc' + 11 in [0, 22]                                         IADD3
+  //     c = clamp(U - 1, 0, 20)               acc' + 10 without the two step values                        VIADDMNMX.RELU
+  //     D = U - 1 - c                         the step, -1 / 0 / +1 per half, as ONE 32-bit integer        IADD3
+  //     B = c - 10 D  (or U - 11 D)           back to 10 (11) where it stepped                             IMAD
+  //     Q = Q - D                             16385 - quantile follows                                     IADD3
+  // D is a "true integer" d_hi * 65536 + d_lo whose low half may be negative (its bit pattern then borrows from the high half);
+  // that is harmless because only LINEAR 32-bit operations consume it and every result they produce has non-negative halves
+  // again, for which the 32-bit value and the packed value coincide. The quartile enables (:119-121: sample below / above the OLD
+  // median) cost no select: the clamp's upper bound is 2 on the enabled halves and 0 elsewhere, which turns the sign code into 0
+  // there, and the missing +1 comes from n1 (q25, "+10" form) or is taken back out by g1 (q75, "+11" form).
+  // Per tick: 8 ALU-pipe instructions (sign tests, clamps, enables), 3-4 on the FMA pipe, 10 adds that go to whichever is free
+  // — against 13 / 8 / 2 for the merged fp16 form and 9 / 14 / 3 for the separate one.
   __device__ __forceinline__ uint32_t track(uint32_t Sb)
   {
     const uint32_t sg1 = addclamp2(Sb, Mq, 0x00020002u);              // sign(raw - median) + 1, OLD median   (:108-117)
+#if SWTPG_FIR_INT
+    // q25 on the halves below the OLD median (:119)
+    const uint32_t n1 = min2(sg1, 0x00010001u);                       // 0 where below, 1 elsewhere
+    const uint32_t s25 = addclamp2(Sb, Q25n, n1 * (kM1 + kM1) + 0x00020002u); // bound 2 - 2 n1 (IMAD): sign(raw - q25) + 1 where enabled, else 0
+    const uint32_t U25 = SWTPG_FIR_U3 ? fma_add(n1, fma_add(s25, A25, kP1), kP1) : A25 + s25 + n1; // acc25' + 11
+    const uint32_t c25 = addclamp2(U25, kM1, 0x00140014u);
+    const uint32_t D25 = U25 - c25 - 0x00010001u;
+    A25 = c25 - 10u * D25;
+    Q25n = fma_sub(Q25n, D25, kM1);
+    // q75 on the halves above it (:121)
+    const uint32_t g1 = __viaddmax_s16x2_relu(sg1, kM1, 0u);          // 1 where above, 0 elsewhere
+    const uint32_t s75 = addclamp2(Sb, Q75p, fma_add(g1, g1, kP1));  // bound 2 g1: sign(raw - q75) + 1 where enabled, else 0
+    const uint32_t U75 = SWTPG_FIR_U3 ? fma_sub(fma_add(s75, A75, kP1), g1, kM1) : A75 + s75 - g1; // acc75' + 11
+    const uint32_t c75 = addclamp2(U75, kM1, 0x00140014u);
+    const uint32_t D75 = U75 - c75 - 0x00010001u;
+    A75 = U75 - 11u * D75;
+    Q75p = fma_sub(Q75p, D75, kM1);
+    // median (:125)
+    const uint32_t U = fma_add(sg1, A, kP1);
+    const uint32_t cm = addclamp2(U, kM1, 0x00140014u);
+    const uint32_t D = U - cm - 0x00010001u;
+    A = cm - 10u * D;
+    Mq = fma_sub(Mq, D, kM1);
+    return Mq;
+#else
     const uint32_t ltf = eq2_one(sg1, 0u), gtf = eq2_one(sg1, 0x00020002u);
 #if SWTPG_FIR_MERGED
     // q25 moves only on the halves below the OLD median and q75 only on the halves above it (:119-121): per half at most one of
@@ -1086,13 +1219,39 @@ struct PackedFirIqr
     A = hfma2_bits(ne2_abs_one(T, kUp), T, kNegTiny);
     Mq = Mq + dn1 - up1;
     return add2(Sb, Mq);
+#endif
   }
-  // min(q75 - q25, sigmaMax) + 3 (:131-134) from a pair of quartile registers (q75 + 2, 16385 - q25)
-  __device__ __forceinline__ uint32_t sig3_of(uint32_t q75p, uint32_t q25n) const { return addmin2(add2(q75p, 0xC000C000u), q25n, sig3max); }
+  // min(q75 - q25, sigmaMax) + 3 (:131-134) from a pair of quartile registers (Q75p, Q25n)
+  __device__ __forceinline__ uint32_t sig3_of(uint32_t q75p, uint32_t q25n) const
+  {
+#if SWTPG_FIR_INT
+    return addmin2(add2(~q75p, 0x00040004u), q25n, sig3max);          // -(16385 - q75) + 3 = ~Q75p + 4 per half
+#else
+    return addmin2(add2(q75p, 0xC000C000u), q25n, sig3max);
+#endif
+  }
   // One tick: returns the filter output of this tick.
+  // s' + 1 = raw - median + 1 from what track() returns
+  static __device__ __forceinline__ uint32_t sp1_of(uint32_t Sb, uint32_t tr)
+  {
+#if SWTPG_FIR_INT
+    return add2(Sb, tr);
+#else
+    return tr;
+#endif
+  }
+  // min(raw - median, adcMax) (:128,142) from what track() returns
+  __device__ __forceinline__ uint32_t clamped_sample(uint32_t Sb, uint32_t tr) const
+  {
+#if SWTPG_FIR_INT
+    return addmin2(Sb, fma_add(tr, 0xFFFEFFFFu, kP1), xmax);         // tr = 16385 - median >= 2: the -1 is a plain 32-bit add
+#else
+    return addmin2(tr, 0xFFFFFFFFu, xmax);                            // tr = raw - median + 1
+#endif
+  }
   __device__ __forceinline__ uint32_t tick(uint32_t Sb)
   {
-    const uint32_t x = addmin2(track(Sb), 0xFFFFFFFFu, xmax);         // min(raw - median, adcMax)           (:128,142)
+    const uint32_t x = clamped_sample(Sb, track(Sb));
     const uint32_t filt = o2;                                         // window = samples t-8 .. t-2          (:160-201)
     cascade(x);
     return filt;
@@ -1230,7 +1389,7 @@ struct PackedFirIqrAnyTaps : PackedFirIqr
   }
   __device__ __forceinline__ uint32_t tick(uint32_t Sb)
   {
-    const uint32_t x = addmin2(track(Sb), 0xFFFFFFFFu, xmax);         // min(raw - median, adcMax)
+    const uint32_t x = clamped_sample(Sb, track(Sb));
     int lo = 0, hi = 0;
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
@@ -1371,7 +1530,8 @@ struct PackedRsIqrWib2 : PackedFirIqr
     uint32_t lv[G], rs[G], sig3[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      lv[g] = rs_step(track(extract_pair_biased(rows + g * ROW_WORDS, pp)), rs[g]);
+      const uint32_t Sb = extract_pair_biased(rows + g * ROW_WORDS, pp);
+      lv[g] = rs_step(sp1_of(Sb, track(Sb)), rs[g]);
       sig3[g] = sig3_of(Q75p, Q25n);
       if constexpr (DUMP) {
         ped_out[g] = median();
