@@ -368,7 +368,7 @@ def main():
     lat_buf = S.gen_wibeth_host(gp, s_links, s_units, link0=link0, n_threads=max(1, min(8, binding["cores"])))  # the "latency buffer"
     warm = lat_buf[:, :128].copy()
 
-    def run_stream(zero_copy, threads, passes, pace=0.0, n_slots=3, links=s_links, verify_links=0):
+    def run_stream(zero_copy, threads, passes, pace=0.0, n_slots=4, links=s_links, verify_links=0):
         buf = lat_buf[:links]
         with H.FrameProcessors(links, s_sc, threshold=args.threshold, device=local_rank, emulator_mode=False, block_on_backpressure=pace == 0,
                                count_only_sink=verify_links == 0, n_slots=n_slots, first_link_id=0) as fp:

@@ -101,7 +101,24 @@ launch_wibeth_geo(const KernelParams& kp, cudaStream_t s)
   if (warps_override > 0)
     warps = std::min<unsigned>(unsigned(warps_override), kp.n_links);
   const unsigned grid = std::min<unsigned>((warps + G::warps - 1) / G::warps, unsigned(resident[dev]));
-  k<<<grid, G::warps * 32, G::smem, s>>>(kp);
+  // More links than persistent warps = several rounds of links per warp, and whatever the last round leaves idle is lost: 6000
+  // links on 4144 warps run at 64.9 % of the HBM peak, 8288 (two full rounds) at 73.0 %. Handing the links out in 4 slices of >= 16
+  // units makes the rounds short — 6000 links 68.7 %, 4440 links 61.7 -> 64.8 %, the dense-hit batch +6 %, AbsRS +3 % — at a cost of
+  // about 3 % per launch for the extra state round trips, which is why a link count that is a whole number of rounds keeps
+  // whole links (8288: 73.0 % against 70.8 % sliced; profiles/r02_sliced_handout_probe.txt). A launch that cannot fill the GPU
+  // keeps whole links too: time is sequential per link, slices could only wait for each other.
+  KernelParams kq = kp;
+  unsigned parts = 1;
+  const unsigned persistent = grid * unsigned(G::warps);
+  if (kp.n_links > persistent && kp.n_links % persistent != 0)
+    parts = std::max(1u, std::min(4u, kp.units_stride / 16u));
+  static const int parts_override = [] { const char* e = getenv("SWTPG_PARTS"); return e ? atoi(e) : 0; }(); // tuning aid
+  if (parts_override > 0)
+    parts = std::min(unsigned(parts_override), 8u);
+  kq.parts_log2 = 0;
+  while ((2u << kq.parts_log2) <= parts) // the largest power of two not above it
+    ++kq.parts_log2;
+  k<<<grid, G::warps * 32, G::smem, s>>>(kq);
   return cudaGetLastError();
 }
 
@@ -284,6 +301,8 @@ make_params(const swtpg_handle* h, const void* d_frames, const uint32_t* d_nunit
   kp.state = h->d_state;
   kp.group_flags = h->d_flags;
   kp.link_cursor = h->d_link_cursor;
+  kp.link_done = h->d_link_cursor + 2;
+  kp.parts_log2 = 0;
   kp.sink.buf = d_tps;
   kp.sink.count = d_count;
   kp.sink.cap = h->tp_capacity;
@@ -322,7 +341,7 @@ reset_state(swtpg_handle* h)
   }
   SW_CUDA(h, cudaMemcpyAsync(h->d_state, st.data(), st.size() * 4, cudaMemcpyHostToDevice, h->stream));
   SW_CUDA(h, cudaMemsetAsync(h->d_flags, 0, size_t(h->n_groups) * 4, h->stream));
-  SW_CUDA(h, cudaMemsetAsync(h->d_link_cursor, 0, 2 * sizeof(uint32_t), h->stream));
+  SW_CUDA(h, cudaMemsetAsync(h->d_link_cursor, 0, (2 + size_t(h->cfg.n_links)) * sizeof(uint32_t), h->stream));
   SW_CUDA(h, cudaStreamSynchronize(h->stream));
   return SWTPG_OK;
 }
@@ -537,7 +556,7 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
   h->groups_per_link = h->channels / 64;
   h->n_groups = cfg->n_links * h->groups_per_link;
   if (h->cfg.n_slots == 0)
-    h->cfg.n_slots = 3;
+    h->cfg.n_slots = 4; // measured: 2 slots 38.0, 3 slots 45.4, 4 slots 47.1, 6 slots 47.2 GB/s (profiles/r02_streaming_slots_probe.txt)
   if (h->cfg.n_slots < 2)
     return fail(nullptr, SWTPG_ERR_INVALID_ARG, "n_slots must be >= 2");
   if (h->cfg.tap_exponent == 0)
@@ -603,8 +622,8 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
   SW_CUDA(hp, cudaEventCreate(&h->ev1));
   SW_CUDA(hp, cudaMalloc(&h->d_state, size_t(h->n_groups) * kStateWordsPerGroup * 4));
   SW_CUDA(hp, cudaMalloc(&h->d_flags, size_t(h->n_groups) * 4));
-  SW_CUDA(hp, cudaMalloc(&h->d_link_cursor, 2 * sizeof(uint32_t)));
-  SW_CUDA(hp, cudaMemset(h->d_link_cursor, 0, 2 * sizeof(uint32_t)));
+  SW_CUDA(hp, cudaMalloc(&h->d_link_cursor, (2 + size_t(h->cfg.n_links)) * sizeof(uint32_t)));
+  SW_CUDA(hp, cudaMemset(h->d_link_cursor, 0, (2 + size_t(h->cfg.n_links)) * sizeof(uint32_t)));
   SW_CUDA(hp, cudaMalloc(&h->d_tps, size_t(h->tp_capacity) * sizeof(swtpg_tp)));
   SW_CUDA(hp, cudaMalloc(&h->d_count, sizeof(unsigned)));
   SW_CUDA(hp, cudaMallocHost(&h->h_count, sizeof(unsigned)));

@@ -36,7 +36,8 @@ struct swtpg_handle
 
   uint32_t* d_state = nullptr;
   uint32_t* d_flags = nullptr;
-  uint32_t* d_link_cursor = nullptr; // {claimed, finished}: dynamic link hand-out of the kernels, self-resetting
+  uint32_t* d_link_cursor = nullptr; // {claimed, finished}: dynamic link hand-out of the kernels, self-resetting; followed by
+                                     // [n_links] slices done per link (wibeth_kernel's sliced hand-out, self-resetting too)
   swtpg_tp* d_tps = nullptr;
   unsigned* d_count = nullptr;
   unsigned* h_count = nullptr;

@@ -75,6 +75,8 @@ struct KernelParams
   uint32_t* state;         // [n_groups][SV_COUNT][32]
   uint32_t* group_flags;   // [n_groups]: bit 0 initialized, bits 8..10 FIR ring phase (absTimeModNTAPS)
   uint32_t* link_cursor;   // [2] {links claimed beyond each warp's first, warps finished}; zero between launches (WIBEth kernel)
+  uint32_t* link_done;     // [n_links] slices of the link finished in THIS launch; zero between launches (wibeth_kernel, sliced)
+  uint32_t parts_log2;     // wibeth_kernel: a link's units are handed out in 2^parts_log2 consecutive slices (0 = whole links)
   TpSink sink;
   int16_t* pedestal_out;   // debug dumps [link][unit][tick][channel] or nullptr
   int16_t* waveform_out;
@@ -1586,6 +1588,19 @@ struct WibEthSmem
   static constexpr size_t total = fifo + size_t(WARPS) * 32; // 8-entry link FIFO per warp
 };
 
+// Whole warp: wait until *counter == want (acquire: what the publishing warp stored before its release is visible afterwards).
+__device__ __noinline__ void
+wait_for_slices(const uint32_t* counter, uint32_t want)
+{
+  uint32_t seen;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    if (__all_sync(0xFFFFFFFFu, seen == want))
+      break;
+    __nanosleep(200);
+  }
+}
+
 template<class Algo, int WARPS, int NSTAGE, int CHUNK_TICKS, bool DUMP, int MIN_CTAS = 1>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 wibeth_kernel(const KernelParams p)
@@ -1598,8 +1613,9 @@ wibeth_kernel(const KernelParams p)
   // warp index through a shuffle: tells the compiler it is warp-uniform, so the ring bookkeeping runs on the uniform datapath
   const uint32_t warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31u;
   const uint32_t warps_total = gridDim.x * WARPS;
-  const uint32_t first_link = blockIdx.x * WARPS + warp;
-  if (first_link >= p.n_links)
+  const uint32_t first_link = blockIdx.x * WARPS + warp; // this warp's first work item
+  const uint32_t n_items = p.n_links << p.parts_log2;
+  if (first_link >= n_items)
     return; // warps are fully independent: no block-level barrier anywhere below
 
   using L = WibEthSmem<WARPS, NSTAGE, CHUNK_TICKS>;
@@ -1634,34 +1650,55 @@ wibeth_kernel(const KernelParams p)
     --fifo_n;
     return link;
   };
-  bool pr_done = false; // the cursor has run past the last link
-  uint32_t pr_link = first_link, pr_left = units_of(first_link) * kChunksPerUnit, pr_in_unit = 0, pr_slot = 0;
-  const uint8_t* pr_src = base_of(first_link) + 32;
-  auto claim = [&]() -> uint32_t { // next unclaimed link (links 0 .. warps_total-1 are the warps' first links)
+  // Work items: item i = slice (i / n_links) of link (i % n_links); slice k of a link with n units is its units
+  // [k n >> parts_log2, (k + 1) n >> parts_log2). Items are claimed in increasing order, so every first slice is handed out
+  // before any second one.
+  auto slice_of = [&](uint32_t item, uint32_t& link, uint32_t& u0, uint32_t& u1) -> uint32_t { // returns the slice number
+    uint32_t part = 0;
+    link = item;
+    while (link >= p.n_links) { // at most 7 rounds; warp-uniform
+      link -= p.n_links;
+      ++part;
+    }
+    const uint32_t n = units_of(link);
+    u0 = (part * n) >> p.parts_log2;
+    u1 = ((part + 1u) * n) >> p.parts_log2;
+    return part;
+  };
+  // same value in every lane -> uniform register, so that the producer's per-chunk bookkeeping stays on the uniform datapath
+  auto uniform = [](uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); };
+  bool pr_done = false; // the cursor has run past the last item
+  uint32_t pr_left = 0, pr_in_unit = 0, pr_slot = 0;
+  const uint8_t* pr_src = nullptr;
+  auto pr_start = [&](uint32_t item) { // point the producer at an item (pr_left stays 0 if it is empty)
+    uint32_t link, u0, u1;
+    slice_of(item, link, u0, u1);
+    pr_left = uniform((u1 - u0) * kChunksPerUnit);
+    if (pr_left != 0) {
+      fifo_push(item);
+      pr_src = base_of(uniform(link)) + size_t(uniform(u0)) * SWTPG_WIBETH_FRAME_BYTES + 32;
+      pr_in_unit = 0;
+    }
+  };
+  auto claim = [&]() -> uint32_t { // next unclaimed item (items 0 .. warps_total-1 are the warps' first ones)
     uint32_t k = 0;
     if (lane == 0)
       k = atomicAdd(p.link_cursor, 1u);
     return warps_total + __reduce_add_sync(0xFFFFFFFFu, k); // REDUX: the result lands in a uniform register
   };
-  // same value in every lane -> uniform register, so that the producer's per-chunk bookkeeping stays on the uniform datapath
-  auto uniform = [](uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); };
-  if (pr_left != 0)
-    fifo_push(first_link);
-  auto produce = [&]() { // request one more chunk, if any link is left for this warp (whole warp calls, converged)
-    if (__builtin_expect(pr_left == 0, 0)) { // link exhausted (or empty): claim the next link that has data
+  pr_start(first_link);
+  auto produce = [&]() { // request one more chunk, if any item is left for this warp (whole warp calls, converged)
+    if (__builtin_expect(pr_left == 0, 0)) { // item exhausted (or empty): claim the next one that has data
       if (pr_done)
         return;
       do {
-        pr_link = claim();
-        if (pr_link >= p.n_links) {
+        const uint32_t item = claim();
+        if (item >= n_items) {
           pr_done = true;
           return;
         }
-        pr_left = uniform(units_of(pr_link) * kChunksPerUnit);
+        pr_start(item);
       } while (pr_left == 0);
-      fifo_push(pr_link);
-      pr_src = base_of(pr_link) + 32;
-      pr_in_unit = 0;
     }
     if (SWTPG_ELECT ? elect_one() : lane == 0) {
       mbar_arrive_expect_tx(&bars[pr_slot], kChunkBytes);
@@ -1698,18 +1735,26 @@ wibeth_kernel(const KernelParams p)
 
   uint32_t stg = 0, phase = 0; // consumer position in the ring and its mbarrier phase
   while (fifo_n != 0) { // the producer started this link NSTAGE chunks ago (or at start-up)
-    const uint32_t link = fifo_pop();
-    const uint32_t n_units = units_of(link);
+    uint32_t link, u0, n_units; // n_units: end of the slice
+    const uint32_t part = slice_of(fifo_pop(), link, u0, n_units);
     const uint8_t* link_base = base_of(link);
     uint32_t* st = p.state + size_t(link) * kStateWordsPerGroup;
-    const uint32_t flags = p.group_flags[link];
+    // A later slice of a link continues from the state its predecessor stored: wait until the NON-EMPTY slices before it are
+    // done (with fewer units than slices some are empty and never run: exactly min(part, u0) of the earlier ones are not). By
+    // the time a second slice is claimed every first one was handed out a whole round ago, so this hardly ever spins; it cannot
+    // dead-lock because every warp of the persistent grid is resident and items are taken in dependency order.
+    if (part != 0u && u0 != 0u) {
+      const uint32_t before = min(part, u0);
+      wait_for_slices(p.link_done + link, before); // out of line: the spin must not cost the tick loop registers
+    }
+    const uint32_t flags = *reinterpret_cast<volatile uint32_t*>(p.group_flags + link);
     algo.load(st, lane, flags);
     bool need_seed = !(flags & kFlagInitialized);
     ctx.link = link;
     ctx.link_base = link_base;
 
-    for (uint32_t unit = 0; unit < n_units; ++unit) {
-      ctx.tick_base = unit * 64u;
+    for (uint32_t unit = u0; unit < n_units; ++unit) {
+      ctx.tick_base = 0u; // 64 ticks per unit = 0 mod 8: the FIR ring phase at a unit's first tick is the slice's initial one
       ctx.unit = unit;
       if constexpr (!std::is_same<Algo, PackedSimpleWibEth>::value && !std::is_same<Algo, PackedSimpleWibEthPipe>::value) {
         // DAQEthHeader word 1 = timestamp (docs/README.md:81); the packed path reads it when it flushes hits
@@ -1755,14 +1800,22 @@ wibeth_kernel(const KernelParams p)
 
     algo.template finish_link<false>(ctx); // drains the policy's software pipeline (deferred hit bookkeeping of the last group)
     Algo::template flush<false>(hits, p.sink, link_base, link, lane); // records carry unit indices of THIS link
-    const uint32_t k_end = algo.phase_after(n_units * 64u);
+    const uint32_t k_end = algo.phase_after((n_units - u0) * 64u);
     algo.store(st, lane, k_end);
     if (lane == 0)
       p.group_flags[link] = kFlagInitialized | (k_end << 8);
+    if (p.parts_log2 != 0u) { // publish the state to the warp that runs the link's next slice; the last slice re-arms the counter
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t done = part + 1u == (1u << p.parts_log2) ? 0u : min(part, u0) + 1u;
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.link_done + link), "r"(done) : "memory");
+      }
+    }
   }
   // Last warp out re-arms the cursor for the next launch (launches of one handle are stream-ordered: state is carried).
   if (lane == 0) {
-    const uint32_t active = min(warps_total, p.n_links);
+    const uint32_t active = min(warps_total, n_items);
     __threadfence();
     if (atomicAdd(p.link_cursor + 1, 1u) == active - 1u) {
       p.link_cursor[0] = 0u;

@@ -812,7 +812,7 @@ struct swtpg_host_conf
   uint16_t crate_id, slot_id, first_link_id;
   uint8_t enable_tpg, emulator_mode, correct_channel_lookup, reversed_map, enable_simple_threshold_on_collection, block_on_backpressure;
   uint8_t count_only_sink; // 1: tp_out only counts what it accepts (throughput runs: no queue growth)
-  uint8_t n_slots;         // staging depth of the engine in superchunks (0 = 3)
+  uint8_t n_slots;         // staging depth of the engine in superchunks (0 = 4)
   uint32_t sink_capacity; // per link; try_send fails beyond it (0 = unbounded)
 };
 
@@ -854,7 +854,7 @@ swtpg_host_create(const swtpg_host_conf* c)
 {
   try {
     auto h = std::make_unique<swtpg_host>();
-    h->engine = std::make_shared<TpgEngine>(c->device, swtpg_format(c->format), c->n_links, c->superchunk_units, c->n_slots ? c->n_slots : 3u);
+    h->engine = std::make_shared<TpgEngine>(c->device, swtpg_format(c->format), c->n_links, c->superchunk_units, c->n_slots ? c->n_slots : 4u);
     h->sink_capacity = c->sink_capacity;
     h->count_only = c->count_only_sink != 0;
     h->queues.resize(c->n_links);

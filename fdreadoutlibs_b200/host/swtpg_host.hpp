@@ -222,7 +222,7 @@ class FrameProcessorBase;
 class TpgEngine
 {
 public:
-  TpgEngine(int device, swtpg_format format, uint32_t n_links, uint32_t superchunk_units, uint32_t n_slots = 3, uint32_t tp_capacity = 0);
+  TpgEngine(int device, swtpg_format format, uint32_t n_links, uint32_t superchunk_units, uint32_t n_slots = 4, uint32_t tp_capacity = 0);
   ~TpgEngine();
   TpgEngine(const TpgEngine&) = delete;
   uint32_t attach(FrameProcessorBase* p);      // conf(): returns the link index

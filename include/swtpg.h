@@ -88,7 +88,7 @@ typedef struct swtpg_config
   uint32_t n_links;          /* independent links owned by this handle (one reference FrameProcessor each) */
   uint32_t max_units;        /* superchunk length: units (frames / WIB2 superchunks) per link per batch, < 2^18 */
   uint32_t tp_capacity;      /* device TP buffer, records per batch; 0 = sized for the worst case */
-  uint32_t n_slots;          /* staging-ring depth of the streaming path (>= 2); 0 = 3 */
+  uint32_t n_slots;          /* staging-ring depth of the streaming path (>= 2); 0 = 4 */
   uint16_t threshold;        /* tpg_threshold (ADC; sigma units for FIR_IQR) */
   int16_t frugal_acc_limit;  /* tpg_frugal_streaming_accumulator_limit (WIB2 and FIR paths hard-wire 10) */
   uint16_t rs_memory_factor; /* already x10, as conf() scales it (WIBEthFrameProcessor.cpp:202) */

@@ -1,5 +1,8 @@
 """GPU (B200): parity of the CUDA path — always called through the C ABI (include/swtpg.h) — against the CPU oracle and the
 reference-generated golden vectors. Bit-exact: TP field tuples, carried state, pedestal and waveform dumps."""
+import os
+import subprocess
+import sys
 import time
 
 import numpy as np
@@ -406,6 +409,22 @@ def test_more_links_than_persistent_warps_ragged():
             a2 = g.process_host(np.ascontiguousarray(units[:, :stride]), n_units=nus[0])
             b2 = g.process_host(np.ascontiguousarray(units[:, stride:]), n_units=nus[1])
         assert_same_tps(np.concatenate([a2, b2]), got, f"{algorithm} run-to-run")
+
+
+@pytest.mark.skipif(os.environ.get("SWTPG_PARTS") is not None, reason="already running with forced slicing")
+@pytest.mark.parametrize("parts", [2, 8])
+def test_links_handed_out_in_slices(parts):
+    """A launch with more links than persistent warps hands every link out in slices (wibeth_kernel: a later slice continues from
+    the state its predecessor stored, and may run on another warp). SWTPG_PARTS forces that for EVERY launch of a process, so
+    the ragged / empty / carried-state / dump / hand-out cases above are repeated under it: units fewer than slices (empty
+    slices), hits open across a slice boundary, FIR ring phase, running sums, the scalar policies."""
+    env = dict(os.environ, SWTPG_PARTS=str(parts))
+    sel = ("test_more_links_than_persistent_warps_ragged or test_ragged_and_empty_batches or test_against_oracle_with_state_and_dumps or "
+           "test_batching_does_not_change_results or test_extreme_amplitudes_wrap_and_saturate_like_the_reference")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k", sel, "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
 
 
 def test_restart_resets_state():
