@@ -368,7 +368,7 @@ def main():
     lat_buf = S.gen_wibeth_host(gp, s_links, s_units, link0=link0, n_threads=max(1, min(8, binding["cores"])))  # the "latency buffer"
     warm = lat_buf[:, :128].copy()
 
-    def run_stream(zero_copy, threads, passes, pace=0.0, n_slots=4, links=s_links, verify_links=0):
+    def run_stream(zero_copy, threads, passes, pace=0.0, n_slots=4, links=s_links, verify_links=0, all_ranks=False):
         buf = lat_buf[:links]
         with H.FrameProcessors(links, s_sc, threshold=args.threshold, device=local_rank, emulator_mode=False, block_on_backpressure=pace == 0,
                                count_only_sink=verify_links == 0, n_slots=n_slots, first_link_id=0) as fp:
@@ -377,7 +377,10 @@ def main():
             fp.start()
             fp.push_feeders(np.ascontiguousarray(warm[:links]), n_threads=threads, burst=16)  # staging ring allocation, first launches
             time.sleep(0.02)
-            barrier()
+            if all_ranks:  # every rank drives its own GPU at the same time (a collective: only where every rank makes this call)
+                barrier()
+            else:
+                torch.cuda.synchronize()
             r0, t0 = resource.getrusage(resource.RUSAGE_SELF), time.perf_counter()
             st = fp.push_feeders(buf, n_threads=threads, burst=16, pace=pace, passes=passes)
             fp.stop()  # flush of the ragged tail, every remaining TriggerPrimitive delivered
@@ -417,7 +420,7 @@ def main():
                 "gather_ms_per_batch": tim["gather_ms"] / max(1, tim["batches"]), "kernel_ms_per_batch": tim["kernel_ms"] / max(1, tim["batches"]),
                 "gather_gbs_while_active": cnt["h2d_bytes"] / max(1e-9, tim["gather_ms"]) / 1e6}
 
-    stream_main = run_stream(True, feeders, args.stream_passes)
+    stream_main = run_stream(True, feeders, args.stream_passes, all_ranks=True)
     e2e_dt = max_over_ranks(stream_main["wall_seconds"])
     e2e_frames = sum_over_ranks(stream_main["frames"] - stream_main["frames_dropped"])
     e2e_value = e2e_frames * SAMPLES_PER_FRAME / e2e_dt
@@ -499,12 +502,12 @@ def main():
         t0 = time.perf_counter()
         mine = S.sort_tps(sharding.globalise(mine, m_link0))
         sort_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-        merged_n, merge_ms = mine.size, 0.0
+        merged_n, merge_ms, transport_ms = mine.size, 0.0, 0.0
         if dist is not None:
             barrier()
-            t0 = time.perf_counter()
-            merged = sharding.gather_and_merge(mine)  # host side: rank 0 receives the sorted lists and merges them
-            merge_ms = (time.perf_counter() - t0) * 1e3
+            tm = {}
+            merged = sharding.gather_and_merge(mine, timings=tm)  # host side: rank 0 receives the sorted lists and merges them
+            merge_ms, transport_ms = tm.get("merge_s", 0.0) * 1e3, tm.get("gather_s", 0.0) * 1e3
             if rank == 0:
                 merged_n = merged.size
                 ok = bool((merged["time_start"][1:] >= merged["time_start"][:-1]).all())
@@ -518,9 +521,10 @@ def main():
               "real_time_apas": args.module_links * frames * SAMPLES_PER_FRAME / (shard_ms * 1e-3) / APA_SAMPLES_PER_S,
               "real_time_multiple_of_the_module": args.module_links * frames * SAMPLES_PER_FRAME / (shard_ms * 1e-3) / (args.module_links / 40 * APA_SAMPLES_PER_S),
               "roofline_frac_per_gpu": by / (shard_ms * 1e-3) / 1e9 / hbm_peak, "tps_per_step_per_gpu": int(mine.size),
-              "host_sort_ms_per_gpu": sort_ms, "merge_ms": merge_ms, "merged_tps": int(merged_n), "verified_links": v_strong,
-              "merge": "each rank orders its list by (time_start, link, channel) (swtpg_sort_tps); rank 0 gathers the lists over the host and "
-                       "merges them (swtpg_merge_sorted): no device collective"}
+              "host_sort_ms_per_gpu": sort_ms, "merge_ms": merge_ms, "gather_to_rank0_ms": transport_ms, "merged_tps": int(merged_n), "verified_links": v_strong,
+              "merge": "each rank orders its list by (time_start, link, channel) (swtpg_sort_tps); rank 0 gathers the lists (torch.distributed "
+                       "object gather: pickling + transport = gather_to_rank0_ms, a test-harness transport, not part of the path) and merges them "
+                       "(swtpg_merge_sorted = merge_ms): no device collective in the data path"}
     del d_m
 
     # --- BASELINE config[1]: ONE APA (40 links) on one GPU, and the shards of config[2] at 8 / 4 / 2 GPUs: launches that cannot fill a GPU ---

@@ -42,16 +42,26 @@ def globalise(tps: np.ndarray, link0: int) -> np.ndarray:
     return out
 
 
-def gather_and_merge(local_sorted: np.ndarray, group=None, dst: int = 0) -> Optional[np.ndarray]:
-    """Rank `dst` receives every rank's sorted TP list and returns the merged list; other ranks return None."""
+def gather_and_merge(local_sorted: np.ndarray, group=None, dst: int = 0, timings: Optional[dict] = None) -> Optional[np.ndarray]:
+    """Rank `dst` receives every rank's sorted TP list and returns the merged list; other ranks return None. `timings`, if
+    given, receives the seconds spent in the transport (`gather_s`) and in the merge itself (`merge_s`, rank `dst` only)."""
+    import time
+
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
+    t0 = time.perf_counter()
     payload = np.ascontiguousarray(local_sorted, dtype=F.TP_DTYPE).tobytes()
     gathered: Optional[List[bytes]] = [None] * world if rank == dst else None  # type: ignore[list-item]
     dist.gather_object(payload, gathered, dst=dst, group=group)
+    t1 = time.perf_counter()
+    if timings is not None:
+        timings["gather_s"] = t1 - t0
     if rank != dst:
         return None
     lists = [np.frombuffer(b, dtype=F.TP_DTYPE) for b in gathered]  # type: ignore[union-attr]
-    return merge_sorted(lists)
+    merged = merge_sorted(lists)
+    if timings is not None:
+        timings["merge_s"] = time.perf_counter() - t1
+    return merged
