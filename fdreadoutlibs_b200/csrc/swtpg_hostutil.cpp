@@ -169,15 +169,51 @@ swtpg_sort_tps(swtpg_tp* tps, size_t n)
 extern "C" void
 swtpg_merge_sorted(const swtpg_tp* const* lists, const size_t* n, size_t k, swtpg_tp* out)
 {
-  // The lists are sorted like swtpg_sort_tps; ties are resolved by list index (stable across GPUs). Concatenating them in list
-  // order and running the stable radix sort gives exactly that order, in O(total) instead of O(total log k) comparisons.
+  // The lists are sorted like swtpg_sort_tps; ties are resolved by list index (stable across GPUs). A tree of two-way merges
+  // of neighbouring runs: every level streams the records once (sequential reads and writes, one mostly-predictable comparison
+  // on time_start per record), ceil(log2 k) levels, ping-pong between `out` and one scratch buffer arranged so that the last
+  // level lands in `out`. std::merge takes equal elements from its first range first, and runs stay in list order, so the
+  // result is what a stable sort of the concatenation gives (which is what this function did before, 10x slower).
+  struct Run
+  {
+    const swtpg_tp* p;
+    size_t n;
+  };
+  std::vector<Run> runs;
   size_t total = 0;
-  for (size_t i = 0; i < k; ++i) {
-    if (n[i])
-      memcpy(out + total, lists[i], n[i] * sizeof(swtpg_tp));
-    total += n[i];
+  for (size_t i = 0; i < k; ++i)
+    if (n[i]) {
+      runs.push_back({ lists[i], n[i] });
+      total += n[i];
+    }
+  if (runs.empty())
+    return;
+  if (runs.size() == 1) {
+    memcpy(out, runs[0].p, total * sizeof(swtpg_tp));
+    return;
   }
-  sort_tps_impl(out, total);
+  unsigned levels = 0;
+  for (size_t r = runs.size(); r > 1; r = (r + 1) / 2)
+    ++levels;
+  thread_local std::vector<swtpg_tp> scratch; // grow-only, like the sort's
+  if (levels > 1 && scratch.size() < total)
+    scratch.resize(total + total / 4);
+  for (unsigned level = 1; level <= levels; ++level) {
+    swtpg_tp* w = ((levels - level) & 1u) ? scratch.data() : out;
+    std::vector<Run> next;
+    size_t pos = 0;
+    for (size_t i = 0; i < runs.size(); i += 2) {
+      if (i + 1 < runs.size()) {
+        std::merge(runs[i].p, runs[i].p + runs[i].n, runs[i + 1].p, runs[i + 1].p + runs[i + 1].n, w + pos, tp_less);
+        next.push_back({ w + pos, runs[i].n + runs[i + 1].n });
+      } else { // odd run out: carried to this level's buffer so that the next level's inputs never alias its output
+        memcpy(w + pos, runs[i].p, runs[i].n * sizeof(swtpg_tp));
+        next.push_back({ w + pos, runs[i].n });
+      }
+      pos += next.back().n;
+    }
+    runs.swap(next);
+  }
 }
 
 extern "C" int
