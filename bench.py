@@ -485,7 +485,7 @@ def main():
     d_m = torch.empty(m_n * frames * FRAME_BYTES, dtype=torch.uint8, device="cuda")
     S.gen_wibeth_device(gp, d_m.data_ptr(), m_n, frames, link0=m_link0)
     torch.cuda.synchronize()
-    with S.TPGenerator(m_n, frames, threshold=args.threshold, device=local_rank, tp_capacity=1 << 22) as g:
+    with S.TPGenerator(m_n, frames, threshold=args.threshold, device=local_rank, tp_capacity=1 << 22, sorted_tps=True) as g:
         g.start()
         for _ in range(3):
             g.process_device(d_m.data_ptr(), frames)
@@ -497,11 +497,22 @@ def main():
             g.fetch_count()
             ms.append(g.last_kernel_ms())
         shard_ms = max_over_ranks(sum(ms) / len(ms))
-        g.process_device(d_m.data_ptr(), frames)
-        mine = g.fetch_tps(cap=1 << 22)
+        # the rank's TP list, ordered by (time_start, link, channel) ON THE DEVICE before it crosses the host link (SWTPG_FLAG_SORTED_TPS)
+        dev_sort = []
+        for _ in range(3):
+            g.process_device(d_m.data_ptr(), frames)
+            mine = g.fetch_tps(cap=1 << 22)
+            dev_sort.append(g.sort_stats()["last_ms"])
+        dev_sort_ms = max_over_ranks(min(dev_sort))
+        mine = sharding.globalise(mine, m_link0)
+        # what the same ordering costs on one host core (round 1's path), on a shuffled copy; also the check of the device's order
+        shuffled = mine[np.random.default_rng(5).permutation(mine.size)]
         t0 = time.perf_counter()
-        mine = S.sort_tps(sharding.globalise(mine, m_link0))
+        by_host = S.sort_tps(shuffled)
         sort_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        if not (by_host == mine).all() or g.sort_stats()["finished_on_host"] != 0:
+            raise AssertionError("device-ordered TP list differs from the host's ordering")
+        del shuffled, by_host
         merged_n, merge_ms, transport_ms = mine.size, 0.0, 0.0
         if dist is not None:
             barrier()
@@ -521,10 +532,12 @@ def main():
               "real_time_apas": args.module_links * frames * SAMPLES_PER_FRAME / (shard_ms * 1e-3) / APA_SAMPLES_PER_S,
               "real_time_multiple_of_the_module": args.module_links * frames * SAMPLES_PER_FRAME / (shard_ms * 1e-3) / (args.module_links / 40 * APA_SAMPLES_PER_S),
               "roofline_frac_per_gpu": by / (shard_ms * 1e-3) / 1e9 / hbm_peak, "tps_per_step_per_gpu": int(mine.size),
-              "host_sort_ms_per_gpu": sort_ms, "merge_ms": merge_ms, "gather_to_rank0_ms": transport_ms, "merged_tps": int(merged_n), "verified_links": v_strong,
-              "merge": "each rank orders its list by (time_start, link, channel) (swtpg_sort_tps); rank 0 gathers the lists (torch.distributed "
-                       "object gather: pickling + transport = gather_to_rank0_ms, a test-harness transport, not part of the path) and merges them "
-                       "(swtpg_merge_sorted = merge_ms): no device collective in the data path"}
+              "device_sort_ms": dev_sort_ms, "host_sort_ms_per_gpu": sort_ms, "merge_ms": merge_ms, "gather_to_rank0_ms": transport_ms, "merged_tps": int(merged_n), "verified_links": v_strong,
+              "merge": "each rank's list comes back ordered by (time_start, link, channel), ordered on the device (SWTPG_FLAG_SORTED_TPS: an LSD radix "
+                       "sort of packed keys in HBM = device_sort_ms; host_sort_ms_per_gpu = the same ordering by swtpg_sort_tps on one host core, "
+                       "for comparison, and the two lists are asserted identical); rank 0 gathers the lists (torch.distributed object gather: "
+                       "pickling + transport = gather_to_rank0_ms, a test-harness transport, not part of the path) and merges them with a k-way "
+                       "merge (swtpg_merge_sorted = merge_ms): no device collective in the data path"}
     del d_m
 
     # --- BASELINE config[1]: ONE APA (40 links) on one GPU, and the shards of config[2] at 8 / 4 / 2 GPUs: launches that cannot fill a GPU ---

@@ -77,6 +77,7 @@ EXPORTS = {
     "swtpg_sync": (C.c_int, [C.c_void_p]),
     "swtpg_dump_state": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "swtpg_get_counters": (C.c_int, [C.c_void_p, C.POINTER(SwtpgCounters)]),
+    "swtpg_sort_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "swtpg_alloc_pinned": (C.c_void_p, [C.c_size_t, C.c_int]),
     "swtpg_free_pinned": (None, [C.c_void_p]),
     "swtpg_sort_tps": (None, [C.c_void_p, C.c_size_t]),

@@ -22,6 +22,7 @@ ALGORITHMS = {
     "FIR": ALGO_FIR_IQR,
 }
 FORMATS = {"wibeth": FORMAT_WIBETH, "wib2": FORMAT_WIB2}
+FLAG_SORTED_TPS = 1  # SWTPG_FLAG_SORTED_TPS
 
 
 class SwtpgError(RuntimeError):
@@ -52,7 +53,9 @@ class TPGenerator:
     def __init__(self, n_links: int, max_units: int, *, fmt: str = "wibeth", algorithm: str = "SimpleThreshold", threshold: int = 60,
                  acc_limit: int = 10, rs_memory_factor: int = 8, rs_scale_factor: int = 5, fir_taps: Optional[Sequence[int]] = None,
                  tap_exponent: int = 6, tp_capacity: int = 0, n_slots: int = 0, device: int = 0, wib2_adc_offset: int = 0,
-                 dispatch_timeout_us: int = 0):
+                 dispatch_timeout_us: int = 0, sorted_tps: bool = False):
+        """sorted_tps: SWTPG_FLAG_SORTED_TPS — every batch's TP list comes back ordered by (time_start, link, channel), ordered on
+        the device (include/swtpg.h)."""
         if algorithm not in ALGORITHMS:
             raise TPGAlgorithmInexistent(algorithm)
         cfg = SwtpgConfig()
@@ -74,6 +77,7 @@ class TPGenerator:
         cfg.tap_exponent = tap_exponent
         cfg.wib2_adc_offset = wib2_adc_offset
         cfg.dispatch_timeout_us = dispatch_timeout_us
+        cfg.flags = FLAG_SORTED_TPS if sorted_tps else 0
         self.cfg = cfg
         self.fmt = fmt
         self.n_links = n_links
@@ -254,6 +258,12 @@ class TPGenerator:
         out = np.zeros(self.channels, dtype=F.STATE_DTYPE)
         self._check(lib.swtpg_dump_state(self._h, link, out.ctypes.data))
         return out
+
+    def sort_stats(self) -> dict:
+        """Device-side ordering (sorted_tps=True): ms of the last list, ms of all lists, lists ordered, lists the host finished."""
+        a, b, n, f = C.c_double(0), C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+        self._check(lib.swtpg_sort_stats(self._h, C.byref(a), C.byref(b), C.byref(n), C.byref(f)))
+        return {"last_ms": a.value, "total_ms": b.value, "lists": n.value, "finished_on_host": f.value}
 
     def counters(self) -> dict:
         c = SwtpgCounters()

@@ -431,9 +431,21 @@ fetch(swtpg_handle* h, cudaStream_t s, swtpg_tp* out, size_t cap, size_t* n_out)
   const size_t found = *h->h_count;
   const size_t stored = std::min<size_t>(found, h->tp_capacity);
   const size_t n = std::min(stored, cap);
+  const swtpg_tp* src = h->d_tps;
+  bool finish_on_host = false;
+  std::unique_lock<std::mutex> sorter_lock; // the ordered list lives in the sorter's buffer until our copy has completed
+  if (h->sorter && n && out) {
+    const swtpg_status st = swtpg_internal::sort_tps_device(h, h->sorter, h->d_tps, stored, s, &src, &finish_on_host, &sorter_lock);
+    if (st != SWTPG_OK)
+      return st;
+  }
   if (n && out)
-    SW_CUDA(h, cudaMemcpyAsync(out, h->d_tps, n * sizeof(swtpg_tp), cudaMemcpyDeviceToHost, s));
+    SW_CUDA(h, cudaMemcpyAsync(out, src, n * sizeof(swtpg_tp), cudaMemcpyDeviceToHost, s));
   SW_CUDA(h, cudaStreamSynchronize(s));
+  if (sorter_lock.owns_lock())
+    sorter_lock.unlock();
+  if (finish_on_host && n == stored)
+    swtpg_sort_tps(out, n); // equal keys / keys wider than 64 bits: the host's tie-break makes both orderings identical
   if (n_out)
     *n_out = found;
   h->counters.tps_emitted += found;
@@ -531,6 +543,8 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
     return fail(nullptr, SWTPG_ERR_INVALID_ARG, "wib2_adc_offset must be a multiple of 4 and leave room for the 448-byte ADC block");
   if (cfg->tap_exponent > 14)
     return fail(nullptr, SWTPG_ERR_INVALID_ARG, "tap_exponent out of range");
+  if (cfg->flags & ~SWTPG_FLAG_SORTED_TPS)
+    return fail(nullptr, SWTPG_ERR_INVALID_ARG, "unknown bits in swtpg_config.flags");
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -632,6 +646,8 @@ swtpg_create(const swtpg_config* cfg, swtpg_handle** out)
     SW_CUDA(hp, cudaMallocHost(&h->h_nunits[i], size_t(cfg->n_links) * 4));
     SW_CUDA(hp, cudaEventCreateWithFlags(&h->ev_nunits[i], cudaEventDisableTiming));
   }
+  if (cfg->flags & SWTPG_FLAG_SORTED_TPS)
+    h->sorter = swtpg_internal::sorter_create();
   *out = h.release();
   return SWTPG_OK;
 }
@@ -669,6 +685,7 @@ swtpg_destroy(swtpg_handle* h)
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->sorter) swtpg_internal::sorter_destroy(h->sorter);
   delete[] h->h_rs_factor;
   delete h;
 }
@@ -988,6 +1005,15 @@ swtpg_get_counters(swtpg_handle* h, swtpg_counters* out)
   out->h2d_bytes = h->counters.h2d_bytes.load();
   out->d2h_bytes = h->counters.d2h_bytes.load();
   swtpg_internal_ingest_counts(h, &out->units_zero_copy, &out->units_staged);
+  return SWTPG_OK;
+}
+
+swtpg_status
+swtpg_sort_stats(swtpg_handle* h, double* last_ms, double* total_ms, uint64_t* lists, uint64_t* finished_on_host)
+{
+  if (!h)
+    return SWTPG_ERR_INVALID_ARG;
+  swtpg_internal::sorter_stats(h->sorter, last_ms, total_ms, lists, finished_on_host);
   return SWTPG_OK;
 }
 

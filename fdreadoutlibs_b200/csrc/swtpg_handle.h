@@ -18,6 +18,7 @@
 
 namespace swtpg_internal {
 struct StreamEngine;
+struct TpSorter;
 }
 
 struct swtpg_handle
@@ -53,6 +54,7 @@ struct swtpg_handle
   int16_t* d_wav = nullptr;
   size_t d_dump_elems = 0;
   uint16_t* h_rs_factor = nullptr; // [n_links][channels] or null
+  swtpg_internal::TpSorter* sorter = nullptr; // SWTPG_FLAG_SORTED_TPS: device-side ordering of TP lists (swtpg_sort.cu)
 
   // streaming path (swtpg_stream.cu), created on the first swtpg_submit / swtpg_register_buffer
   std::mutex engine_mu;
@@ -118,6 +120,13 @@ fail(swtpg_handle* h, swtpg_status s, const char* msg)
 // ([n_links][units_stride][unit_bytes], d_nunits = per-link valid units or nullptr) on stream `s`. TPs go to d_tps / d_count.
 cudaError_t launch_batch_kernel(swtpg_handle* h, const void* d_frames, const uint32_t* d_nunits, uint32_t units_stride, swtpg_tp* d_tps,
                                 unsigned* d_count, cudaStream_t s);
+
+// swtpg_sort.cu: device-side ordering of a batch's TP list (SWTPG_FLAG_SORTED_TPS)
+TpSorter* sorter_create();
+void sorter_destroy(TpSorter* s);
+void sorter_stats(const TpSorter* s, double* last_ms, double* total_ms, uint64_t* calls, uint64_t* host_fallbacks);
+swtpg_status sort_tps_device(swtpg_handle* h, TpSorter* st, const swtpg_tp* d_tps, size_t n, cudaStream_t s, const swtpg_tp** out,
+                             bool* finish_on_host, std::unique_lock<std::mutex>* lock);
 
 // swtpg_stream.cu
 void engine_destroy(swtpg_handle* h);          // stops the threads, frees everything (swtpg_destroy)

@@ -60,7 +60,11 @@ tp_less(const swtpg_tp& a, const swtpg_tp& b)
   if (a.link != b.link) return a.link < b.link;
   if (a.channel != b.channel) return a.channel < b.channel;
   if (a.time_over_threshold != b.time_over_threshold) return a.time_over_threshold < b.time_over_threshold;
-  return a.adc_integral < b.adc_integral;
+  if (a.adc_integral != b.adc_integral) return a.adc_integral < b.adc_integral;
+  // the remaining fields, so that the order is total: records that tie on everything above (only possible when a link delivers
+  // the same timestamps twice) come out the same way whatever order the device emitted them in
+  if (a.time_peak != b.time_peak) return a.time_peak < b.time_peak;
+  return a.adc_peak < b.adc_peak;
 }
 
 // Host-side ordering of a batch's TP list. A 64-frame batch of 148 APAs carries ~0.5 M records: std::sort needs ~110 ms for

@@ -452,12 +452,22 @@ StreamEngine::completer_main()
     if (e == cudaSuccess) {
       const unsigned found = *b->h_count;
       const unsigned stored = std::min<unsigned>(found, h->tp_capacity);
-      if (stored)
-        e = cudaMemcpyAsync(b->h_tps, b->d_tps, size_t(stored) * sizeof(swtpg_tp), cudaMemcpyDeviceToHost, b->stream);
+      const swtpg_tp* src = b->d_tps;
+      bool finish_on_host = false;
+      std::unique_lock<std::mutex> sorter_lock;
+      if (h->sorter && stored > 1 &&
+          sort_tps_device(h, h->sorter, b->d_tps, stored, b->stream, &src, &finish_on_host, &sorter_lock) != SWTPG_OK)
+        e = cudaErrorUnknown; // the text is in the handle's last error already
+      if (stored && e == cudaSuccess)
+        e = cudaMemcpyAsync(b->h_tps, src, size_t(stored) * sizeof(swtpg_tp), cudaMemcpyDeviceToHost, b->stream);
       if (e == cudaSuccess)
         e = cudaEventRecord(b->ev_tps, b->stream);
       if (e == cudaSuccess)
         e = cudaEventSynchronize(b->ev_tps);
+      if (sorter_lock.owns_lock())
+        sorter_lock.unlock();
+      if (finish_on_host && e == cudaSuccess)
+        swtpg_sort_tps(b->h_tps, stored);
       b->n_ready = stored;
       b->overflow = found > stored;
       float g_ms = 0.f, k_ms = 0.f; // device time the gather and the TPG kernel of this batch took (both have completed)

@@ -39,7 +39,8 @@ make_map(const std::string& name)
 }
 
 // ---- TpgEngine ------------------------------------------------------------------------------------------------------
-TpgEngine::TpgEngine(int device, swtpg_format format, uint32_t n_links, uint32_t superchunk_units, uint32_t n_slots, uint32_t tp_capacity)
+TpgEngine::TpgEngine(int device, swtpg_format format, uint32_t n_links, uint32_t superchunk_units, uint32_t n_slots, uint32_t tp_capacity,
+                     uint32_t flags)
 {
   m_cfg.struct_size = sizeof m_cfg;
   m_cfg.device = device;
@@ -48,6 +49,7 @@ TpgEngine::TpgEngine(int device, swtpg_format format, uint32_t n_links, uint32_t
   m_cfg.max_units = superchunk_units;
   m_cfg.n_slots = n_slots;
   m_cfg.tp_capacity = tp_capacity;
+  m_cfg.flags = flags;
   m_procs.assign(n_links, nullptr);
   m_buf.resize(1 << 16);
 }

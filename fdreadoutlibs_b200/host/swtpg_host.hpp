@@ -222,7 +222,9 @@ class FrameProcessorBase;
 class TpgEngine
 {
 public:
-  TpgEngine(int device, swtpg_format format, uint32_t n_links, uint32_t superchunk_units, uint32_t n_slots = 4, uint32_t tp_capacity = 0);
+  // flags: SWTPG_FLAG_* of include/swtpg.h (SWTPG_FLAG_SORTED_TPS: every link's block of a delivered batch is in time order)
+  TpgEngine(int device, swtpg_format format, uint32_t n_links, uint32_t superchunk_units, uint32_t n_slots = 4, uint32_t tp_capacity = 0,
+            uint32_t flags = SWTPG_FLAG_NONE);
   ~TpgEngine();
   TpgEngine(const TpgEngine&) = delete;
   uint32_t attach(FrameProcessorBase* p);      // conf(): returns the link index

@@ -103,6 +103,12 @@ typedef struct swtpg_config
 } swtpg_config;
 
 #define SWTPG_FLAG_NONE 0u
+/* The TP list of every batch (swtpg_process_host, swtpg_fetch_tps, swtpg_poll*) comes back ordered by (time_start, link,
+ * channel) — the order TriggerPrimitiveTypeAdapter::operator< imposes downstream
+ * (include/fdreadoutlibs/TriggerPrimitiveTypeAdapter.hpp:26-29) — ordered ON THE DEVICE before it crosses the host link (an LSD
+ * radix sort of packed keys in HBM), identical to what swtpg_sort_tps makes of the unordered list. Lists of one handle can
+ * then be merged across GPUs with swtpg_merge_sorted without a host sort. */
+#define SWTPG_FLAG_SORTED_TPS 1u
 
 /* Per-channel carried state, by frame channel: ChanState of wibeth/tpg/ProcessingInfo.hpp:20-66 and
  * wib2/tpg/ProcessingInfo.hpp:20-68. Used for parity dumps only. */
@@ -245,6 +251,10 @@ swtpg_status swtpg_stream_timing(swtpg_handle* h, double* gather_ms, double* ker
 /* Carried state of one link, by frame channel (ChanState parity). out has SWTPG_*_CHANNELS entries. */
 swtpg_status swtpg_dump_state(swtpg_handle* h, uint32_t link, swtpg_channel_state* out);
 swtpg_status swtpg_get_counters(swtpg_handle* h, swtpg_counters* out);
+/* SWTPG_FLAG_SORTED_TPS bookkeeping: device time (CUDA events, includes the 16-byte read-back of the key range) of the last
+ * ordered list and of all lists since swtpg_create, how many lists were ordered on the device, and how many of them the host
+ * had to finish (equal keys, or keys wider than 64 bits: links whose timestamps are unrelated). Any pointer may be NULL. */
+swtpg_status swtpg_sort_stats(swtpg_handle* h, double* last_ms, double* total_ms, uint64_t* lists, uint64_t* finished_on_host);
 
 /* Page-locked host memory for frame buffers handed to swtpg_process_host (or used as a latency buffer without a later
  * swtpg_register_buffer). write_combined != 0 asks for write-combined pages: the CPU only ever WRITES frames there (reads are
