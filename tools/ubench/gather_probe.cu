@@ -146,13 +146,41 @@ int main(int argc, char** argv)
       CK(cudaMemcpyAsync(d + size_t(i) * bytes, h + size_t(order[i]) * bytes, size_t(64) * bytes, cudaMemcpyHostToDevice, 0));
   });
   check("memcpy");
+  { // the same per-run copies dealt round-robin over K streams: do the copy engines overlap the per-copy overhead?
+    cudaStream_t st[16];
+    for (int i = 0; i < 16; ++i)
+      CK(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    for (int K : { 2, 4, 8, 16 }) {
+      char nm[64];
+      snprintf(nm, sizeof nm, "memcpy per 64 units, %d streams", K);
+      timeit(nm, [&] {
+        cudaEvent_t j[16];
+        for (int i = 0; i < K; ++i) { // fork from the timing stream
+          CK(cudaEventCreateWithFlags(&j[i], cudaEventDisableTiming));
+          CK(cudaEventRecord(j[i], 0));
+          CK(cudaStreamWaitEvent(st[i], j[i], 0));
+        }
+        uint32_t k = 0;
+        for (uint32_t i = 0; i < n; i += 64, ++k)
+          CK(cudaMemcpyAsync(d + size_t(i) * bytes, h + size_t(order[i]) * bytes, size_t(64) * bytes, cudaMemcpyHostToDevice, st[k % K]));
+        for (int i = 0; i < K; ++i) { // join
+          CK(cudaEventRecord(j[i], st[i]));
+          CK(cudaStreamWaitEvent(0, j[i], 0));
+          CK(cudaEventDestroy(j[i]));
+        }
+      });
+    }
+    check("memcpy streams");
+  }
 #define TMA(ST, G)                                                                                                                  \
   {                                                                                                                                 \
     const size_t sm = size_t(ST) * bytes + ST * 8;                                                                                  \
+    if (sm <= 227 * 1024) {                                                                                                         \
     CK(cudaFuncSetAttribute(gather_tma<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));                                 \
     char nm[64];                                                                                                                    \
     snprintf(nm, sizeof nm, "tma stages=%d ctas=%d", ST, G);                                                                        \
     timeit(nm, [&] { gather_tma<ST><<<G, 32, sm>>>(d_items, n, d, bytes); });                                                       \
+    }                                                                                                                               \
   }
   TMA(2, 16) TMA(4, 16) TMA(8, 16) TMA(4, 32) TMA(8, 32) TMA(4, 64) TMA(8, 64) TMA(16, 64) TMA(4, 148) TMA(8, 148) TMA(8, 296) TMA(24, 148)
   check("tma");
