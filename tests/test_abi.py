@@ -143,6 +143,31 @@ def test_sort_and_merge_match_a_lexicographic_sort(n, wide):
     assert (F.sort_tps(merged) == F.sort_tps(tps)).all()
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 7, 8])
+def test_kway_merge_is_the_total_order(k):
+    """swtpg_merge_sorted (tree of two-way merges) over k lists, some of them empty, equals numpy's lexsort of the union on ALL
+    seven fields — the order is total, so records that tie on (time_start, link, channel) come out the same way whatever order
+    the device emitted them in."""
+    rng = np.random.default_rng(k)
+    n = 30000
+    tps = np.zeros(n, dtype=F.TP_DTYPE)
+    tps["time_start"] = 10**15 + 32 * rng.integers(0, 300, n)
+    tps["link"] = rng.integers(0, 8, n)
+    tps["channel"] = rng.integers(0, 64, n)
+    tps["time_over_threshold"] = 32 * rng.integers(1, 3, n)
+    tps["adc_integral"] = rng.integers(1, 3, n)
+    tps["time_peak"] = tps["time_start"] + 32 * rng.integers(0, 3, n).astype(np.uint64)
+    tps["adc_peak"] = rng.integers(0, 3, n)
+    order = np.lexsort((tps["adc_peak"], tps["time_peak"], tps["adc_integral"], tps["time_over_threshold"], tps["channel"], tps["link"], tps["time_start"]))
+    want = tps[order]
+    owner = rng.integers(0, k, n)
+    owner[owner == k // 2] = 0 if k > 2 else owner[owner == k // 2]  # an empty list in the middle when there are enough lists
+    parts = [S.sort_tps(tps[owner == r].copy()) for r in range(k)]
+    merged = S.merge_sorted(parts)
+    assert merged.size == n and (merged == want).all()
+    assert (S.sort_tps(tps.copy()) == want).all()
+
+
 def test_firwin_int_host():
     assert list(S.firwin_int(7, 0.1, 64)) == [1, 6, 15, 20, 15, 6, 1]
 
