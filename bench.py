@@ -535,9 +535,10 @@ def main():
               "device_sort_ms": dev_sort_ms, "host_sort_ms_per_gpu": sort_ms, "merge_ms": merge_ms, "gather_to_rank0_ms": transport_ms, "merged_tps": int(merged_n), "verified_links": v_strong,
               "merge": "each rank's list comes back ordered by (time_start, link, channel), ordered on the device (SWTPG_FLAG_SORTED_TPS: an LSD radix "
                        "sort of packed keys in HBM = device_sort_ms; host_sort_ms_per_gpu = the same ordering by swtpg_sort_tps on one host core, "
-                       "for comparison, and the two lists are asserted identical); rank 0 gathers the lists (torch.distributed object gather: "
-                       "pickling + transport = gather_to_rank0_ms, a test-harness transport, not part of the path) and merges them with a k-way "
-                       "merge (swtpg_merge_sorted = merge_ms): no device collective in the data path"}
+                       "for comparison, and the two lists are asserted identical); rank 0 receives the ordered lists (gather_to_rank0_ms: torch.distributed "
+                       "all_gather of the lists as byte tensors, device-to-device under NCCL, + one copy to the host; bench plumbing — in a readout "
+                       "application the lists arrive over its own network layer) and merges them with a k-way merge (swtpg_merge_sorted = "
+                       "merge_ms): no collective inside the TPG path itself"}
     del d_m
 
     # --- BASELINE config[1]: ONE APA (40 links) on one GPU, and the shards of config[2] at 8 / 4 / 2 GPUs: launches that cannot fill a GPU ---

@@ -7,5 +7,5 @@ mkdir -p build/variants
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr "$@" \
   -c -o build/variants/capi_$NAME.o fdreadoutlibs_b200/csrc/swtpg_capi.cu
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/libswtpg_$NAME.so build/variants/capi_$NAME.o \
-  build/obj/swtpg_stream.o build/obj/swtpg_hostutil.o -lpthread
+  build/obj/swtpg_stream.o build/obj/swtpg_sort.o build/obj/swtpg_hostutil.o -lpthread
 rm -f build/variants/capi_$NAME.o
