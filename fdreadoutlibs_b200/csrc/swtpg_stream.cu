@@ -146,6 +146,7 @@ struct Batch
   uint32_t n_items = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_gather = nullptr, ev_kernel = nullptr, ev_count = nullptr, ev_tps = nullptr;
+  cudaEvent_t ev_up = nullptr;                  // pointer table and lengths are on the device (serial gather stream only)
   cudaEvent_t ev_g0 = nullptr, ev_k0 = nullptr; // timing: start of the gather / of the TPG kernel (device clocks, swtpg_stream_timing)
   uint32_t n_ready = 0, n_taken = 0;
   bool overflow = false;
@@ -188,6 +189,7 @@ struct StreamEngine
   std::chrono::microseconds timeout{ 5000 };
 
   int gather_mode = 0, gather_ctas = 64; // 0 = TMA ring, 1 = LSU
+  cudaStream_t gather_stream = nullptr;  // the gathers of all batches run one after the other on this stream (null: each on its batch's)
 
   void kick()
   {
@@ -207,7 +209,7 @@ struct StreamEngine
     cv_flush.notify_all();
     cv_space.notify_all();
   }
-  cudaError_t launch_gather(Batch& b);
+  cudaError_t launch_gather(Batch& b, cudaStream_t gs);
   cudaError_t enqueue(Batch& b);
   void dispatcher_main();
   void releaser_main();
@@ -233,6 +235,7 @@ free_batch(Batch& b)
   if (b.ev_gather) cudaEventDestroy(b.ev_gather);
   if (b.ev_kernel) cudaEventDestroy(b.ev_kernel);
   if (b.ev_g0) cudaEventDestroy(b.ev_g0);
+  if (b.ev_up) cudaEventDestroy(b.ev_up);
   if (b.ev_k0) cudaEventDestroy(b.ev_k0);
   if (b.ev_count) cudaEventDestroy(b.ev_count);
   if (b.ev_tps) cudaEventDestroy(b.ev_tps);
@@ -249,22 +252,22 @@ env_int(const char* name, int dflt)
 } // namespace
 
 cudaError_t
-StreamEngine::launch_gather(Batch& b)
+StreamEngine::launch_gather(Batch& b, cudaStream_t gs)
 {
   if (b.n_items == 0)
     return cudaSuccess;
   const unsigned grid = std::min<unsigned>(unsigned(gather_ctas), b.n_items);
   if (gather_mode == 0) {
     const size_t smem = size_t(kGatherStages) * unit_bytes + kGatherStages * 8;
-    gather_units_tma<kGatherStages><<<grid, 32, smem, b.stream>>>(b.d_items, b.n_items, b.d_frames, unit_bytes);
+    gather_units_tma<kGatherStages><<<grid, 32, smem, gs>>>(b.d_items, b.n_items, b.d_frames, unit_bytes);
   } else {
-    gather_units_lsu<8><<<grid, 256, 0, b.stream>>>(b.d_items, b.n_items, b.d_frames, unit_bytes / 16);
+    gather_units_lsu<8><<<grid, 256, 0, gs>>>(b.d_items, b.n_items, b.d_frames, unit_bytes / 16);
   }
   return cudaGetLastError();
 }
 
-// Everything a batch needs on the device, in order: pointer table + ragged lengths up, gather on the batch's own stream
-// (overlaps the previous batch's TPG kernel), TPG kernel on the handle's compute stream (state is carried: kernels of
+// Everything a batch needs on the device, in order: pointer table + ragged lengths up on the batch's own stream, gather on the
+// engine's gather stream (behind the previous batch's gather, overlapping its TPG kernel), TPG kernel on the handle's compute stream (state is carried: kernels of
 // consecutive batches must run in order), TP count back on the batch's stream.
 cudaError_t
 StreamEngine::enqueue(Batch& b)
@@ -275,9 +278,16 @@ StreamEngine::enqueue(Batch& b)
   return e
   TRY(cudaMemcpyAsync(b.d_items, b.h_items, size_t(b.n_items) * sizeof(GatherItem), cudaMemcpyHostToDevice, b.stream));
   TRY(cudaMemcpyAsync(b.d_nunits, b.h_nunits, size_t(n_links) * 4, cudaMemcpyHostToDevice, b.stream));
-  TRY(cudaEventRecord(b.ev_g0, b.stream));
-  TRY(launch_gather(b));
-  TRY(cudaEventRecord(b.ev_gather, b.stream));
+  cudaStream_t gs = gather_stream ? gather_stream : b.stream;
+  if (gather_stream) {
+    TRY(cudaEventRecord(b.ev_up, b.stream));
+    TRY(cudaStreamWaitEvent(gs, b.ev_up, 0));
+  }
+  TRY(cudaEventRecord(b.ev_g0, gs));
+  TRY(launch_gather(b, gs));
+  TRY(cudaEventRecord(b.ev_gather, gs));
+  if (gather_stream)
+    TRY(cudaStreamWaitEvent(b.stream, b.ev_gather, 0));
   TRY(cudaMemsetAsync(b.d_count, 0, sizeof(unsigned), b.stream));
   TRY(cudaStreamWaitEvent(h->stream, b.ev_gather, 0));
   TRY(cudaEventRecord(b.ev_k0, h->stream));
@@ -518,6 +528,11 @@ engine_create(swtpg_handle* h, StreamEngine** out)
   e->ring_ptr.reset(new const uint8_t*[size_t(e->n_links) * e->R]());
   e->gather_mode = env_int("SWTPG_GATHER_MODE", 0);
   e->gather_ctas = std::max(1, env_int("SWTPG_GATHER_CTAS", 64));
+  // One gather stream for all batches: their gathers run one after the other. Side by side (each on its batch's stream,
+  // SWTPG_GATHER_SERIAL=0) they share the host link worse than they use it one at a time: 45.4-46.8 against 48.2-48.8 GB/s at 240
+  // links with 3-6 slots (profiles/r02_gather_serial_probe.txt).
+  if (env_int("SWTPG_GATHER_SERIAL", 1) != 0)
+    SW_CUDA(h, cudaStreamCreateWithFlags(&e->gather_stream, cudaStreamNonBlocking));
   if (e->gather_mode == 0) {
     const size_t smem = size_t(kGatherStages) * e->unit_bytes + kGatherStages * 8;
     SW_CUDA(h, cudaFuncSetAttribute(gather_units_tma<kGatherStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -527,6 +542,8 @@ engine_create(swtpg_handle* h, StreamEngine** out)
   auto cleanup = [&]() {
     for (auto& b : e->batches)
       free_batch(*b);
+    if (e->gather_stream)
+      cudaStreamDestroy(e->gather_stream);
   };
   for (uint32_t i = 0; i < h->cfg.n_slots; ++i) {
     e->batches.emplace_back(new Batch);
@@ -547,6 +564,7 @@ engine_create(swtpg_handle* h, StreamEngine** out)
     ok(cudaEventCreateWithFlags(&b.ev_gather, cudaEventBlockingSync));
     ok(cudaEventCreateWithFlags(&b.ev_kernel, cudaEventDefault));
     ok(cudaEventCreate(&b.ev_g0));
+    ok(cudaEventCreateWithFlags(&b.ev_up, cudaEventDisableTiming));
     ok(cudaEventCreate(&b.ev_k0));
     ok(cudaEventCreateWithFlags(&b.ev_count, cudaEventDisableTiming | cudaEventBlockingSync));
     ok(cudaEventCreateWithFlags(&b.ev_tps, cudaEventDisableTiming | cudaEventBlockingSync));
@@ -759,6 +777,8 @@ engine_destroy(swtpg_handle* h)
   for (const auto& r : e->ranges)
     if (r.ours && cudaHostUnregister(reinterpret_cast<void*>(r.lo)) != cudaSuccess)
       cudaGetLastError();
+  if (e->gather_stream)
+    cudaStreamDestroy(e->gather_stream);
   delete e;
 }
 
