@@ -516,6 +516,8 @@ def main():
         merged_n, merge_ms, transport_ms = mine.size, 0.0, 0.0
         if dist is not None:
             barrier()
+            sharding.gather_and_merge(mine)  # untimed: the first collective of a shape pays for the communicator's set-up
+            barrier()
             tm = {}
             merged = sharding.gather_and_merge(mine, timings=tm)  # host side: rank 0 receives the sorted lists and merges them
             merge_ms, transport_ms = tm.get("merge_s", 0.0) * 1e3, tm.get("gather_s", 0.0) * 1e3
