@@ -411,6 +411,35 @@ def test_more_links_than_persistent_warps_ragged():
         assert_same_tps(np.concatenate([a2, b2]), got, f"{algorithm} run-to-run")
 
 
+def test_more_links_than_persistent_warps_whole_batches():
+    """The same hand-out with every link carrying the same number of units — the bench's shape: two launches on one handle (the
+    cursor and the per-link slice counters re-arm themselves), SimpleThreshold and a running sum, sampled links against the
+    oracle incl. their pedestals, and the whole TP list against a second run. Under SWTPG_PARTS (test_links_handed_out_in_slices)
+    every link of these batches is handed out in slices."""
+    n_links, stride = 4500, 16
+    units = S.gen_wibeth_host(S.gen_params(57, 0.05), n_links, 2 * stride)
+    for algorithm, thr in (("SimpleThreshold", 20), ("StandardRS", 40)):
+        cfg = B.make_config(algorithm=S.ALGORITHMS[algorithm], threshold=thr)
+        check = list(range(0, n_links, 211)) + [n_links - 1, 4143, 4144, 4145]
+        want, ped = [], {}
+        for l in check:
+            o = B.Oracle(cfg, link_id=l)
+            want.append(o.process(units[l]))
+            ped[l] = o.state()["pedestal"]
+        runs = []
+        for _ in range(2):
+            with S.TPGenerator(n_links, stride, algorithm=algorithm, threshold=thr, tp_capacity=1 << 22) as g:
+                g.start()
+                a = g.process_host(np.ascontiguousarray(units[:, :stride]))
+                b = g.process_host(np.ascontiguousarray(units[:, stride:]))
+                runs.append(np.concatenate([a, b]))
+                assert g.counters()["units_processed"] == 2 * n_links * stride
+                for l in check:
+                    assert (g.dump_state(l)["pedestal"] == ped[l]).all(), f"{algorithm} link {l}"
+        assert_same_tps(runs[0][np.isin(runs[0]["link"], check)], np.concatenate(want), f"{algorithm} whole batches")
+        assert_same_tps(runs[1], runs[0], f"{algorithm} run-to-run")
+
+
 @pytest.mark.skipif(os.environ.get("SWTPG_PARTS") is not None, reason="already running with forced slicing")
 @pytest.mark.parametrize("parts", [2, 8])
 def test_links_handed_out_in_slices(parts):
@@ -419,7 +448,8 @@ def test_links_handed_out_in_slices(parts):
     the ragged / empty / carried-state / dump / hand-out cases above are repeated under it: units fewer than slices (empty
     slices), hits open across a slice boundary, FIR ring phase, running sums, the scalar policies."""
     env = dict(os.environ, SWTPG_PARTS=str(parts))
-    sel = ("test_more_links_than_persistent_warps_ragged or test_ragged_and_empty_batches or test_against_oracle_with_state_and_dumps or "
+    sel = ("test_more_links_than_persistent_warps_ragged or test_more_links_than_persistent_warps_whole_batches or "
+           "test_ragged_and_empty_batches or test_against_oracle_with_state_and_dumps or "
            "test_batching_does_not_change_results or test_extreme_amplitudes_wrap_and_saturate_like_the_reference")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k", sel, "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
