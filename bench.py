@@ -350,7 +350,7 @@ def main():
     algo_bytes = n_links * frames * FRAME_BYTES + tps_per_step * TP_BYTES + 2 * STATE_BYTES_PER_CHANNEL * n_links * 64
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "wibeth_kernel<PackedSimpleT<false>, 1 warp per CTA, ring 2 x 16 ticks> (28 persistent warps per SM, links handed out in slices)", "kernel_ms": k_ms,
+                "peak_source": peak_src, "kernel": "wibeth_kernel<PackedSimpleT<true>, 1 warp per CTA, ring 2 x 32 ticks> (software-pipelined policy, 20 persistent warps per SM, links handed out in 4 halving slices)", "kernel_ms": k_ms,
                 "kernel_ms_per_launch_events": sum(kernel_ms) / len(kernel_ms), "algorithmic_bytes_per_launch": algo_bytes,
                 "verified_links": verified_main}
     prof = os.path.join(ROOT, "profiles", "dram_traffic.json")

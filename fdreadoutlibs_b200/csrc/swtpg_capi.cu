@@ -58,7 +58,13 @@ struct Geo
 #endif
 using GeoDefault = Geo<1, SWTPG_GEO_STAGES, SWTPG_GEO_CHUNK, SWTPG_GEO_MINCTAS>;
 
-template<class Algo, bool DUMP, class G, int WARPS_PER_SM = 0> // WARPS_PER_SM: 0 = the policy's own measured optimum (Algo::kWarpsPerSm)
+#ifndef SWTPG_AUTO_SLICE_GEOM
+#define SWTPG_AUTO_SLICE_GEOM 1 // sliced launches: equal slices (0) or halving ones (1)
+#endif
+
+// WARPS_PER_SM: 0 = the policy's own measured optimum (Algo::kWarpsPerSm). SLICE_WHOLE_ROUNDS: hand the links out in slices
+// even when their number is a whole multiple of the persistent warps.
+template<class Algo, bool DUMP, class G, int WARPS_PER_SM = 0, bool SLICE_WHOLE_ROUNDS = false>
 cudaError_t
 launch_wibeth_geo(const KernelParams& kp, cudaStream_t s)
 {
@@ -101,16 +107,20 @@ launch_wibeth_geo(const KernelParams& kp, cudaStream_t s)
   if (warps_override > 0)
     warps = std::min<unsigned>(unsigned(warps_override), kp.n_links);
   const unsigned grid = std::min<unsigned>((warps + G::warps - 1) / G::warps, unsigned(resident[dev]));
-  // More links than persistent warps = several rounds of links per warp, and whatever the last round leaves idle is lost: 6000
-  // links on 4144 warps run at 64.9 % of the HBM peak, 8288 (two full rounds) at 73.0 %. Handing the links out in 4 slices of >= 16
-  // units makes the rounds short — 6000 links 68.7 %, 4440 links 61.7 -> 64.8 %, the dense-hit batch +6 %, AbsRS +3 % — at a cost of
-  // about 3 % per launch for the extra state round trips, which is why a link count that is a whole number of rounds keeps
-  // whole links (8288: 73.0 % against 70.8 % sliced; profiles/r02_sliced_handout_probe.txt). A launch that cannot fill the GPU
-  // keeps whole links too: time is sequential per link, slices could only wait for each other.
+  // More links than persistent warps = several rounds of links per warp, and whatever the last round leaves idle is lost (round 2,
+  // straight-line SimpleThreshold policy: 6000 links on 4144 warps 64.9 % of the HBM peak, 8288 = two full rounds 73.0 %). Handing
+  // the links out in 4 slices makes the rounds short, at the price of the extra state round trips (about 3 % per launch):
+  //   * HALVING slices (n/2, n/4, n/8, n/8 units): what the launch's last round leaves idle is at most one LAST slice, so small
+  //     last slices shorten the tail without more round trips per link than four equal ones (pipelined SimpleThreshold policy at
+  //     20 warps per SM, 5920 links: whole links 68.9 %, equal slices 70.8 %, halving 73.1 %; 6000 links 71.0 -> 73.3 %; AbsRS + 2.5 %;
+  //     profiles/r02_halving_slices_probe.txt). The straight-line policy at 28 warps per SM is the one case that loses with them.
+  //   * For most policies a link count that is a whole number of rounds keeps whole links (straight-line form, 8288 links: 73.0 %
+  //     against 70.8 % sliced); the pipelined SimpleThreshold policy gains from slices even then (SLICE_WHOLE_ROUNDS).
+  // A launch that cannot fill the GPU keeps whole links: time is sequential per link, slices could only wait for each other.
   KernelParams kq = kp;
   unsigned parts = 1;
   const unsigned persistent = grid * unsigned(G::warps);
-  if (kp.n_links > persistent && kp.n_links % persistent != 0)
+  if (kp.n_links > persistent && (SLICE_WHOLE_ROUNDS || kp.n_links % persistent != 0))
     parts = std::max(1u, std::min(4u, kp.units_stride / 16u));
   static const int parts_override = [] { const char* e = getenv("SWTPG_PARTS"); return e ? atoi(e) : 0; }(); // tuning aid
   if (parts_override > 0)
@@ -118,6 +128,8 @@ launch_wibeth_geo(const KernelParams& kp, cudaStream_t s)
   kq.parts_log2 = 0;
   while ((2u << kq.parts_log2) <= parts) // the largest power of two not above it
     ++kq.parts_log2;
+  static const int geom = [] { const char* e = getenv("SWTPG_SLICE_GEOM"); return e ? atoi(e) : SWTPG_AUTO_SLICE_GEOM; }(); // tuning aid
+  kq.slice_geom = geom != 0 ? 1u : 0u;
   k<<<grid, G::warps * 32, G::smem, s>>>(kq);
   return cudaGetLastError();
 }
@@ -169,18 +181,17 @@ launch_wibeth_quad(const KernelParams& kp, cudaStream_t s)
 // 2-5 % faster for SimpleThreshold and the running sums (the quad's lock-step costs more than the producer bookkeeping it
 // saves). SWTPG_WIBETH_KERNEL=warp forces the latter.
 // WIBEth SimpleThreshold, the production algorithm: which form of its policy runs, on which ring and with how many persistent
-// warps, is decided per launch from the number of links — from whether the launch can fill the GPU (measured:
-// profiles/r02_simple_pipeline_sweep.txt, profiles/r02_simple_geometry_sweep.txt).
-//   * A launch below 36 links per SM (a 750-link shard of an 8-GPU module, the streaming path's 240 links, one APA) is bound
-//     by what ONE warp does per tick: it runs the software-pipelined form (prefetch + deferred quiet test,
-//     PackedSimpleT<true>, 88 registers) on the 2 x 32-tick ring with at most 16 warps per SM: 40 links +18 %, 750 links
-//     +12 %, 3000 links +7 % over the straight-line form.
-//   * A launch that can runs the straight-line form (70 registers) on a ring of 2 x 16 ticks — half the shared memory per
-//     warp — with 28 warps per SM, 7 per sub-partition: what limits a full GPU is how many warps the scheduler can pick from,
-//     and the smaller footprint buys two more per sub-partition. 5920 links: 67.6 % of the HBM peak (pipelined form, 16 warps
-//     per SM: 66.3 %; round 1: 64.5 %); the dense-hit stress batch 2.11 ms against 2.60 ms.
-// A deeper ring (4 stages) never helps: not even a lone warp is bound by the copy engine's latency.
-// SWTPG_SIMPLE_PIPE = 0 | 1 forces one form on the default ring (tuning aid).
+// warps is a measured choice (profiles/r02_simple_pipeline_sweep.txt, profiles/r02_halving_slices_probe.txt).
+//   * The software-pipelined form (prefetch of the next group's rows + deferred quiet test, PackedSimpleT<true>, 92 registers) on
+//     the 2 x 32-tick ring runs every launch since its dependent chain lost an instruction (the accumulator reset as one IMAD):
+//     with 20 warps per SM and halving slices it beats the straight-line form with 28 at every link count — 5920 links 73.1 %
+//     against 67.8 % of the HBM peak, 6000 links 73.3 / 67.8 %, 8288 links 74.3 / 73.2 %, 4440 links 72.1 / 67.6 % — except on
+//     a dense-hit batch (20.2 / 21.0 %).
+//   * Up to one link per warp of the 20-per-SM grid (2960 links on B200: a 750-link shard of an 8-GPU module, the streaming
+//     path's 240 links, one APA) a launch is bound by what ONE warp does per tick and keeps at most 16 warps per SM (measured
+//     optimum of the round-2 sweep); beyond that 20 warps per SM and slices even for whole rounds.
+// SWTPG_SIMPLE_PIPE (tuning aid): 1 = the pipelined form with the policy's own 16 warps per SM, 0 = the straight-line form on the
+// default ring (20 warps per SM), 2 = the straight-line form on the 2 x 16-tick ring with 28 warps per SM (round 2's full-load form).
 template<bool DUMP>
 cudaError_t
 launch_wibeth_simple(const KernelParams& kp, cudaStream_t s)
@@ -190,12 +201,14 @@ launch_wibeth_simple(const KernelParams& kp, cudaStream_t s)
     return launch_wibeth_geo<PackedSimpleWibEth, DUMP, GeoDefault>(kp, s);
   if (forced == 1)
     return launch_wibeth_geo<PackedSimpleWibEthPipe, DUMP, GeoDefault>(kp, s);
+  if (forced == 2)
+    return launch_wibeth_geo<PackedSimpleWibEth, DUMP, Geo<1, 2, 16>, 28>(kp, s);
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  constexpr int kFullWarpsPerSm = 28, kFullFromLinksPerSm = 36; // measured cross-over: 4440 links (30 per SM) still favour the pipelined form
-  if (kp.n_links >= unsigned(kFullFromLinksPerSm * sms))
-    return launch_wibeth_geo<PackedSimpleWibEth, DUMP, Geo<1, 2, 16>, kFullWarpsPerSm>(kp, s);
+  constexpr int kFullWarpsPerSm = 20;
+  if (kp.n_links > unsigned(kFullWarpsPerSm * sms))
+    return launch_wibeth_geo<PackedSimpleWibEthPipe, DUMP, GeoDefault, kFullWarpsPerSm, true>(kp, s);
   return launch_wibeth_geo<PackedSimpleWibEthPipe, DUMP, GeoDefault>(kp, s);
 }
 
@@ -310,6 +323,7 @@ make_params(const swtpg_handle* h, const void* d_frames, const uint32_t* d_nunit
   kp.waveform_out = wav;
   kp.threshold = h->cfg.threshold;
   kp.acc_limit = h->cfg.frugal_acc_limit;
+  kp.acc_limit_neg = 0u - (uint32_t(h->cfg.frugal_acc_limit) & 0xFFFFu);
   kp.rs_scale = int16_t(h->cfg.rs_scale_factor);
   kp.tap_exponent = h->cfg.tap_exponent;
   for (int i = 0; i < 8; ++i)

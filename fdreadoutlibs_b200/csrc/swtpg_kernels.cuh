@@ -16,6 +16,12 @@
 
 #include <type_traits>
 
+#ifndef SWTPG_STEP_NEGL
+#define SWTPG_STEP_NEGL 1 // integer frugal step of SimpleThreshold / the running sums: accumulator reset as ONE IMAD with -L (0: c - L * D)
+#endif
+#ifndef SWTPG_SLICE_FENCES
+#define SWTPG_SLICE_FENCES 2 // sliced hand-out: 2 = every lane fences before lane 0's release store; 1 = the release alone
+#endif
 #ifndef SWTPG_GROUP_UNROLL
 #define SWTPG_GROUP_UNROLL 4
 #endif
@@ -77,12 +83,15 @@ struct KernelParams
   uint32_t* link_cursor;   // [2] {links claimed beyond each warp's first, warps finished}; zero between launches (WIBEth kernel)
   uint32_t* link_done;     // [n_links] slices of the link finished in THIS launch; zero between launches (wibeth_kernel, sliced)
   uint32_t parts_log2;     // wibeth_kernel: a link's units are handed out in 2^parts_log2 consecutive slices (0 = whole links)
+  uint32_t slice_geom;     // ... of equal length (0) or halving: n/2, n/4, ..., and the rest (1)
   TpSink sink;
   int16_t* pedestal_out;   // debug dumps [link][unit][tick][channel] or nullptr
   int16_t* waveform_out;
   // configuration (swtpg_config)
   uint32_t threshold;      // u16
   int32_t acc_limit;       // i16
+  uint32_t acc_limit_neg;  // -acc_limit as its own parameter: the integer tracker's IMAD then takes it straight from the constant
+                           // bank (derived from acc_limit in the kernel it costs a register or a negation per group of ticks)
   int32_t rs_scale;        // i16
   int32_t tap_exponent;
   int32_t taps[8];
@@ -468,7 +477,7 @@ struct PackedSimpleT
   static constexpr bool kWib2Fields = false; // which process_swtpg_hits derives the TP fields (and whether the peak is tracked)
   uint32_t Mq, A, prev, C, Tn, PK1, PTn;
   uint32_t cUp, cDn, thr1;
-  uint32_t cL, c2L, cL1, cLL, kM1; // integer accumulator form: L, (2L, 2L), L + 1, (L, L); 0xFFFFFFFF in a register
+  uint32_t cL, cLn, c2L, cL1, cLL, kM1; // integer accumulator form: L, -L, (2L, 2L), L + 1, (L, L); 0xFFFFFFFF in a register
   uint32_t shift, shmask; // WIB2 flavour only
   uint32_t raw[8];        // software pipeline: words of the next group's four rows ...
   uint32_t dsp[4], dwhen; // ... and the deferred group: its four s' + 1 and (unit << 6 | first tick); dvalid below
@@ -484,6 +493,7 @@ struct PackedSimpleT
     cUp = up | (up << 16);
     cDn = dn | (dn << 16);
     cL = L;
+    cLn = p.acc_limit_neg;
     cL1 = L + 1u;
     cLL = L * 0x00010001u;
     c2L = 2u * L * 0x00010001u;
@@ -574,7 +584,13 @@ struct PackedSimpleT
     A = cL1 * c + V;                                            // c - L (U - 1 - c)
 #else
     const uint32_t D = U - c - 0x00010001u;                     // the step
-    A = c - cL * D;                                             // back to L where it stepped
+#if SWTPG_STEP_NEGL
+    A = cLn * D + c;                                            // back to L where it stepped: c - L D as ONE IMAD with -L from the
+                                                                // constant bank (written c - L * D ptxas negates D first: 62
+                                                                // instead of 59 instructions per quiet 4-tick group)
+#else
+    A = c - cL * D;
+#endif
     Mq -= D;                                                    // (steering these adds to the FMA pipe measured 1 % slower here)
 #endif
     return add2(Sb, Mq);                                        // s' + 1 with the UPDATED median
@@ -723,6 +739,7 @@ struct PackedSimpleWib2 : PackedSimpleWibEth
   {
     KernelParams q = p;
     q.acc_limit = 10; // wib2/tpg/ProcessAVX2.hpp:79
+    q.acc_limit_neg = 0u - 10u;
     PackedSimpleWibEth::configure(q);
     shift = uint32_t(p.tap_exponent);
     const uint32_t m = 0xFFFFu >> shift;
@@ -1651,8 +1668,9 @@ wibeth_kernel(const KernelParams p)
     return link;
   };
   // Work items: item i = slice (i / n_links) of link (i % n_links); slice k of a link with n units is its units
-  // [k n >> parts_log2, (k + 1) n >> parts_log2). Items are claimed in increasing order, so every first slice is handed out
-  // before any second one.
+  // [k n >> parts_log2, (k + 1) n >> parts_log2), or, with slice_geom, halving slices (what the launch's last round leaves idle is
+  // at most one LAST slice, so small last slices shorten the tail without more state round trips per link). Items are claimed
+  // in increasing order, so every first slice is handed out before any second one.
   auto slice_of = [&](uint32_t item, uint32_t& link, uint32_t& u0, uint32_t& u1) -> uint32_t { // returns the slice number
     uint32_t part = 0;
     link = item;
@@ -1661,9 +1679,23 @@ wibeth_kernel(const KernelParams p)
       ++part;
     }
     const uint32_t n = units_of(link);
-    u0 = (part * n) >> p.parts_log2;
-    u1 = ((part + 1u) * n) >> p.parts_log2;
+    if (p.slice_geom) { // halving slices: n/2, n/4, ... and the rest (slice k starts ceil(n / 2^k) units before the end)
+      u0 = n - ((n + (1u << part) - 1u) >> part);
+      u1 = part + 1u == (1u << p.parts_log2) ? n : n - ((n + (2u << part) - 1u) >> (part + 1u));
+    } else {
+      u0 = (part * n) >> p.parts_log2;
+      u1 = ((part + 1u) * n) >> p.parts_log2;
+    }
     return part;
+  };
+  // How many of the slices before `part` hold units (with fewer units than slices some are empty and never run). Equal slices:
+  // below one unit per slice every non-empty one holds exactly one, so u0 of them; halving slices: slice k < last is empty
+  // unless n > 2^k. The last slice is never empty in either scheme (it re-arms the link's counter).
+  auto slices_before = [&](uint32_t link, uint32_t part, uint32_t u0) -> uint32_t {
+    if (!p.slice_geom)
+      return min(part, u0);
+    const uint32_t n = units_of(link);
+    return min(part, n > 1u ? 32u - uint32_t(__clz(int(n - 1u))) : 0u);
   };
   // same value in every lane -> uniform register, so that the producer's per-chunk bookkeeping stays on the uniform datapath
   auto uniform = [](uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); };
@@ -1744,7 +1776,7 @@ wibeth_kernel(const KernelParams p)
     // the time a second slice is claimed every first one was handed out a whole round ago, so this hardly ever spins; it cannot
     // dead-lock because every warp of the persistent grid is resident and items are taken in dependency order.
     if (part != 0u && u0 != 0u) {
-      const uint32_t before = min(part, u0);
+      const uint32_t before = slices_before(link, part, u0);
       wait_for_slices(p.link_done + link, before); // out of line: the spin must not cost the tick loop registers
     }
     const uint32_t flags = *reinterpret_cast<volatile uint32_t*>(p.group_flags + link);
@@ -1805,10 +1837,12 @@ wibeth_kernel(const KernelParams p)
     if (lane == 0)
       p.group_flags[link] = kFlagInitialized | (k_end << 8);
     if (p.parts_log2 != 0u) { // publish the state to the warp that runs the link's next slice; the last slice re-arms the counter
+#if SWTPG_SLICE_FENCES == 2
       __threadfence();
-      __syncwarp();
+#endif
+      __syncwarp(); // orders the lanes' stores before lane 0's release, which is cumulative
       if (lane == 0) {
-        const uint32_t done = part + 1u == (1u << p.parts_log2) ? 0u : min(part, u0) + 1u;
+        const uint32_t done = part + 1u == (1u << p.parts_log2) ? 0u : slices_before(link, part, u0) + 1u;
         asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.link_done + link), "r"(done) : "memory");
       }
     }
