@@ -187,7 +187,7 @@ launch_wibeth_quad(const KernelParams& kp, cudaStream_t s)
 //     with 20 warps per SM and halving slices it beats the straight-line form with 28 at every link count — 5920 links 73.1 %
 //     against 67.8 % of the HBM peak, 6000 links 73.3 / 67.8 %, 8288 links 74.3 / 73.2 %, 4440 links 72.1 / 67.6 % — except on
 //     a dense-hit batch (20.2 / 21.0 %).
-//   * Up to one link per warp of the 20-per-SM grid (2960 links on B200: a 750-link shard of an 8-GPU module, the streaming
+//   * Below one link per warp of the 20-per-SM grid (2960 links on B200: a 750-link shard of an 8-GPU module, the streaming
 //     path's 240 links, one APA) a launch is bound by what ONE warp does per tick and keeps at most 16 warps per SM (measured
 //     optimum of the round-2 sweep); beyond that 20 warps per SM and slices even for whole rounds.
 // SWTPG_SIMPLE_PIPE (tuning aid): 1 = the pipelined form with the policy's own 16 warps per SM, 0 = the straight-line form on the
@@ -207,7 +207,7 @@ launch_wibeth_simple(const KernelParams& kp, cudaStream_t s)
   if (cudaGetDevice(&dev) == cudaSuccess)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   constexpr int kFullWarpsPerSm = 20;
-  if (kp.n_links > unsigned(kFullWarpsPerSm * sms))
+  if (kp.n_links >= unsigned(kFullWarpsPerSm * sms)) // 2960 links: 66.5 % with 20 warps per SM against 64.2 % with 16; 2500: 56.7 / 58.2 %
     return launch_wibeth_geo<PackedSimpleWibEthPipe, DUMP, GeoDefault, kFullWarpsPerSm, true>(kp, s);
   return launch_wibeth_geo<PackedSimpleWibEthPipe, DUMP, GeoDefault>(kp, s);
 }
@@ -225,6 +225,17 @@ launch_wibeth(const KernelParams& kp, cudaStream_t s)
     }();
     if (!warp_form)
       return launch_wibeth_quad<Algo, DUMP>(kp, s);
+  }
+  // The running sums (AbsRS, StandardRS; one-warp-per-CTA form): a launch of more than one round of a 20-per-SM grid runs 20
+  // warps per SM with halving slices, whole rounds included — AbsRS 28.7 -> 30.4 % of the HBM peak at 5920 links (its own
+  // optimum of 16 warps per SM holds for whole links: 20 unsliced 26.9 %), StandardRS 35.4 -> 36.7 %
+  // (profiles/r02_warps_crossover_probe.txt).
+  if constexpr (std::is_same<Algo, PackedRsWibEth<false>>::value || std::is_same<Algo, PackedRsWibEth<true>>::value) {
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess)
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (kp.n_links > unsigned(20 * sms))
+      return launch_wibeth_geo<Algo, DUMP, GeoDefault, 20, true>(kp, s);
   }
   return launch_wibeth_geo<Algo, DUMP, GeoDefault>(kp, s);
 }
