@@ -462,15 +462,17 @@ struct ScalarAlgo
 // group's arithmetic starts (prefetch across the quiet-test branch), and the quiet test / hit bookkeeping of a group is
 // DEFERRED by one group, so that it is scheduled in the shadow of the next group's pedestal chain.
 // =====================================================================================================================
-// PIPE = true: the two-stage software pipeline (for launches that cannot fill the GPU: a warp alone on its scheduler runs at
-// the speed of its dependent chain); PIPE = false: straight-line groups, fewer registers and instructions (for full launches,
-// where the other warps of the sub-partition hide the latencies anyway). The host picks per launch (swtpg_capi.cu).
+// PIPE = true: the two-stage software pipeline, the form every WIBEth SimpleThreshold launch runs (a warp runs at the speed of
+// its dependent chain; since the accumulator reset is one IMAD that chain is short enough for 20 such warps per SM to beat 28
+// straight-line ones); PIPE = false: straight-line groups, fewer registers and instructions — the WIB2 kernel's form and the
+// base of the running-sum policies. The host picks per launch (launch_wibeth_simple, swtpg_capi.cu).
 template<bool PIPE>
 struct PackedSimpleT
 {
   static constexpr int kGroupUnroll = SWTPG_GROUP_UNROLL;
   // persistent warps per SM, measured: 5 per sub-partition for the straight-line form (profiles/r01_warps_sweep.txt), 4 for the
-  // pipelined one (88 registers; profiles/r02_simple_pipeline_sweep.txt)
+  // pipelined one below one round of links (92 registers; profiles/r02_simple_pipeline_sweep.txt); from 2960 links on the host
+  // asks for 20 (profiles/r02_pipelined_full_load_probe.txt, r02_warps_crossover_probe.txt)
   static constexpr int kWarpsPerSm = PIPE ? 16 : 20;
   static constexpr int kQuadCtasPerSm = SWTPG_QUAD_SIMPLE; // 0: one warp per CTA (measured faster for this policy)
   static constexpr int kWib2MinCtas = 5;
